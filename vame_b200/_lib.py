@@ -1,0 +1,57 @@
+"""ctypes loader for the C-ABI library.  There is NO CPU fallback: if the library is missing this raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvame_b200.so")
+
+_lib = None
+
+c_void_p, c_int, c_long, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t,
+                                                        ctypes.c_float, ctypes.c_double)
+
+# name -> (restype, argtypes); mirrors include/vame_b200.h
+SIGNATURES = {
+    "vame_last_error": (ctypes.c_char_p, []),
+    "vame_abi_version": (c_int, []),
+    "vame_p16_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vame_pack_p16": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "vame_gemm_p16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p]),
+}
+
+
+class VameB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes library with typed signatures."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VameB200Error(
+                "vame_b200: %s not found. Build it with `python -m vame_b200.build` "
+                "(there is no CPU / PyTorch fallback for the hot path)." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().vame_last_error()
+        raise VameB200Error("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

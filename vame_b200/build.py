@@ -1,0 +1,79 @@
+"""Build the in-tree CUDA library ``vame_b200/libvame_b200.so`` for sm_100a with nvcc.
+
+The library is a plain C-ABI shared object (no torch / pybind dependency, cudart linked statically) loaded with
+ctypes by ``vame_b200._lib``.  nvcc cross-compiles without a GPU, so this runs in the CPU-only dev container.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libvame_b200.so")
+STAMP = os.path.join(HERE, ".build_stamp")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--use_fast_math" if os.environ.get("VAME_FAST_MATH") else "-DVAME_ACCURATE_MATH=1"]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    inc = os.path.join(os.path.dirname(HERE), "include", "vame_b200.h")
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [inc]
+    for f in files:
+        h.update(f.encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def nvcc_path():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into one shared library (parallel per-file compile, then link)."""
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = nvcc_path()
+    procs = []
+    objs = []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out))
+        elif verbose or "warning" in out:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("vame_b200: CUDA build failed")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("vame_b200: link failed:\n" + r.stdout)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,44 @@
+// extern "C" entry points for the low-level building blocks (packing, tensor-core GEMM, SIMT GEMM).
+#include "../../include/vame_b200.h"
+#include "api_common.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+thread_local char g_err[512] = {0};
+}
+
+extern "C" {
+
+const char* vame_last_error(void) { return vb::g_err; }
+
+int vame_abi_version(void) { return VAME_B200_ABI_VERSION; }
+
+size_t vame_p16_bytes(int rows, int k, int row_block) { return vb::p16_bytes(rows, k, row_block); }
+
+int vame_pack_p16(const float* src, long ld, int transposed, int rows, int k, int rows_src, int k_src, const int* row_map,
+                  const int* col_map, int row_block, void* out, void* stream) {
+  VB_REQUIRE(src && out, "vame_pack_p16: null pointer");
+  VB_REQUIRE(row_block > 0 && row_block % 8 == 0, "vame_pack_p16: row_block must be a positive multiple of 8");
+  VB_REQUIRE(rows > 0 && k > 0, "vame_pack_p16: empty matrix");
+  vb::launch_pack_p16(src, ld, transposed, rows, k, rows_src, k_src, row_map, col_map, row_block, out, (cudaStream_t)stream);
+  return vb::check_launch("vame_pack_p16");
+}
+
+int vame_gemm_p16(const void* a_p, int a_nkc, const void* b_p, int b_nkc, int M, int N, float* C, long ldc, const float* bias,
+                  int accumulate, int splits, void* stream) {
+  VB_REQUIRE(a_p && b_p && C, "vame_gemm_p16: null pointer");
+  VB_REQUIRE(a_nkc == b_nkc && a_nkc > 0, "vame_gemm_p16: A and B must have the same number of K chunks");
+  VB_REQUIRE(M > 0 && N > 0, "vame_gemm_p16: empty output");
+  VB_REQUIRE(splits >= 1 && (splits == 1 || accumulate), "vame_gemm_p16: split-K requires accumulate=1");
+  vb::GemmArgs g{};
+  g.a[0] = {a_p, a_nkc, a_nkc};
+  g.a[1] = {nullptr, 0, 0};
+  g.b[0] = {b_p, b_nkc, b_nkc};
+  g.b[1] = {nullptr, 0, 0};
+  g.M = M; g.N = N; g.C = C; g.ldc = ldc; g.bias = bias; g.atomic = accumulate; g.splits = splits;
+  vb::launch_gemm_p16(g, (cudaStream_t)stream);
+  return vb::check_launch("vame_gemm_p16");
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+// Per-timestep bi-GRU kernels (forward gate update and BPTT step) on tcgen05 tensor cores.
+//
+// Forward step (replaces one time step of nn.GRU as used at vame/model/rnn_model.py:41,106,141; cell equations from
+// the torch.nn.GRU documentation, gate order r,z,n):
+//     gh = h_{t-1} W_hh^T            -> tcgen05.mma, M = 128 batch rows, N = 96 (r,z,n of 32 hidden units), K = H
+//     r = s(gi_r + gh_r) ; z = s(gi_z + gh_z) ; n = tanh(gi_n + r (gh_n + b_hn)) ; h = (1-z) n + z h_{t-1}
+//   grid = (H/32 unit slices, batch tiles of 128, directions).  Each CTA keeps its 96 x H slice of W_hh (bf16 hi/lo)
+//   and the 128 x H tile of h_{t-1} in shared memory (both fetched by the TMA engine as whole P16 tiles), issues
+//   3 x H/16 MMAs into 96 TMEM columns and runs the gate math in the TMEM->register epilogue; the new h is written
+//   as fp32 (sequence output / next step's elementwise operand) and as P16 hi/lo (next step's MMA operand).
+//   Steps are chained with programmatic dependent launch: the W slice and the input-projection rows are fetched
+//   before griddepcontrol.wait, so only the h tile load + MMA + epilogue are on the recurrence's critical path.
+//
+// Backward step (BPTT equations of SURVEY.md §3.5, verified against autograd in oracle/gru_numpy.py):
+//     dh = sum(parts) + dout_t ; gate gradients ; dgh = [da_r, da_z, da_n r]
+//     partial_c = dgh[:, gates of slice c] W_hh[gates of slice c, :]   -> tcgen05.mma, M = 128, N = H, K = 96
+//   The K-split keeps the A operand local to the CTA (written to shared memory by its own threads); the H/32 partial
+//   sums plus the carry dh*z are summed by the next step's prologue.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+
+#ifdef VAME_ACCURATE_MATH
+__device__ __forceinline__ float gate_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return tanhf(x); }
+#else
+__device__ __forceinline__ float gate_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
+#endif
+
+__device__ __forceinline__ void ld16(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void st16(float* p, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// write 16 consecutive k-values of one row into a P16 tile (two atoms), hi and lo planes; generic pointer (smem or global)
+__device__ __forceinline__ void st16_p16(__nv_bfloat16* tile, int rows_in_tile, int r, int k, const float* v) {
+  uint4 hi0, lo0, hi1, lo1;
+  split8(v, hi0, lo0);
+  split8(v + 8, hi1, lo1);
+  const int off = p16_in_tile(r, k);
+  __nv_bfloat16* lo = tile + (size_t)rows_in_tile * KCHUNK;
+  *reinterpret_cast<uint4*>(tile + off) = hi0;
+  *reinterpret_cast<uint4*>(tile + off + 64) = hi1;
+  *reinterpret_cast<uint4*>(lo + off) = lo0;
+  *reinterpret_cast<uint4*>(lo + off + 64) = lo1;
+}
+
+// =================================================================================================
+// forward step
+// =================================================================================================
+constexpr int F_WTILE = 96 * KCHUNK * 2 * 2;     // 24576 B : one K chunk of the W slice (hi + lo)
+constexpr int F_ATILE = 128 * KCHUNK * 2 * 2;    // 32768 B : one K chunk of the h tile (hi + lo)
+
+__global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int H = a.H, nkc = (H + KCHUNK - 1) / KCHUNK;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + (size_t)nkc * F_WTILE;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + (size_t)nkc * F_ATILE);
+  uint64_t* abar = wbar + 4;
+  uint64_t* done = abar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int c = blockIdx.x, tile = blockIdx.y;
+  const GruDirFwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&wbar[i], 1);
+      mbar_init(&abar[i], 1);
+    }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- prologue: everything that does not depend on the previous time step ----
+  if (tid == 0) {
+    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
+    for (int kc = 0; kc < nkc; ++kc) {
+      mbar_expect_tx(&wbar[kc], F_WTILE);
+      bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+    }
+  }
+  const int r_in = q * 32 + lane;
+  const long b = (long)tile * 128 + r_in;
+  const int j0 = half * 16;            // first unit inside the slice
+  const int u0 = c * 32 + j0;          // first hidden unit handled by this thread
+  float gir[16], giz[16], gin[16], bhn[16];
+  {
+    const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts) * d.gi_pitch;
+    ld16(gi_row + u0, gir);
+    ld16(gi_row + H + u0, giz);
+    ld16(gi_row + 2 * H + u0, gin);
+    ld16(d.b_hn + u0, bhn);
+  }
+
+  if (a.pdl) pdl_wait();               // previous step's h is now complete and visible
+  if (a.pdl) pdl_launch_dependents();  // let the next step start its prologue
+
+  if (tid == 0) {
+    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(d.h_in_p) + (size_t)tile * nkc * p16_tile_elems(128);
+    for (int kc = 0; kc < nkc; ++kc) {
+      mbar_expect_tx(&abar[kc], F_ATILE);
+      bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
+    }
+    const uint32_t idesc = make_idesc_bf16(128, 96);
+    const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
+    for (int kc = 0; kc < nkc; ++kc) {
+      mbar_wait(&wbar[kc], 0);
+      mbar_wait(&abar[kc], 0);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
+      const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t ko = ks * 2 * ATOM_BYTES;
+        const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
+        const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+        umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+        umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+        umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+      }
+    }
+    umma_commit(done);
+  }
+
+  float hprev[16];
+  ld16(d.h_in + b * H + u0, hprev);
+
+  mbar_wait(done, 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  float ar[16], az[16], an[16];
+  tmem_ld16(taddr + j0, ar);
+  tmem_ld16(taddr + 32 + j0, az);
+  tmem_ld16(taddr + 64 + j0, an);
+  tmem_ld_wait();
+
+  float hn[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float r = gate_sigmoid(gir[i] + ar[i]);
+    const float z = gate_sigmoid(giz[i] + az[i]);
+    const float ghn = an[i] + bhn[i];
+    const float n = gate_tanh(gin[i] + r * ghn);
+    hn[i] = (1.0f - z) * n + z * hprev[i];
+    ar[i] = r; az[i] = z; an[i] = n; bhn[i] = ghn;
+  }
+  st16(d.h_out + b * H + u0, hn);
+  {
+    const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
+    __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
+    st16_p16(t, 128, r_in, kk, hn);
+  }
+  if (d.sv_r) {
+    st16(d.sv_r + b * H + u0, ar);
+    st16(d.sv_z + b * H + u0, az);
+    st16(d.sv_n + b * H + u0, an);
+    st16(d.sv_ghn + b * H + u0, bhn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+static void launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int threads, size_t smem, cudaStream_t st,
+                       int pdl) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.numAttrs = 0;
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+}
+
+void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st) {
+  const int nkc = (a.H + KCHUNK - 1) / KCHUNK;
+  const size_t smem = (size_t)nkc * (F_WTILE + F_ATILE) + 256;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(gru_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
+  cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel, a);
+}
+
+// =================================================================================================
+// backward step
+// =================================================================================================
+constexpr int B_APLANE = 128 * KCHUNK * 2;        // 16 KB: one plane of a 128-row K chunk
+
+__global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int H = a.H, nrb = (H + 127) / 128, nsl = H / 32;
+  // B operand (W_hh^T slice): per K chunk kc (2 chunks): hi plane [nrb*128 rows][64], lo plane likewise
+  const size_t wchunk = (size_t)nrb * 2 * B_APLANE;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + 2 * wchunk;                 // A operand: 2 K chunks x (hi, lo) x 16 KB
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + 4 * B_APLANE);
+  uint64_t* done = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int c = blockIdx.x, tile = blockIdx.y;
+  const GruDirBwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const uint32_t tmem_cols = (H <= 32) ? 32 : (H <= 64) ? 64 : (H <= 128) ? 128 : 256;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- prologue independent of the previous BPTT step: weights + saved forward activations ----
+  if (tid == 0) {
+    // global layout: [slice c][rb][kc(2)][plane(2)][128x64]; shared layout per kc: hi[rb0..], lo[rb0..]
+    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
+    mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
+    for (int kc = 0; kc < 2; ++kc)
+      for (int rb = 0; rb < nrb; ++rb) {
+        const __nv_bfloat16* t = wp + ((size_t)rb * 2 + kc) * p16_tile_elems(128);
+        bulk_g2s(sW + kc * wchunk + (size_t)rb * B_APLANE, t, B_APLANE, wbar);                                    // hi
+        bulk_g2s(sW + kc * wchunk + (size_t)(nrb + rb) * B_APLANE, t + 128 * KCHUNK, B_APLANE, wbar);             // lo
+      }
+  }
+  const int r_in = q * 32 + lane;
+  const long b = (long)tile * 128 + r_in;
+  const int j0 = half * 16, u0 = c * 32 + j0;
+  float r[16], z[16], n[16], ghn[16], hp[16], dh[16];
+  ld16(d.sv_r + b * H + u0, r);
+  ld16(d.sv_z + b * H + u0, z);
+  ld16(d.sv_n + b * H + u0, n);
+  ld16(d.sv_ghn + b * H + u0, ghn);
+  ld16(d.h_prev + b * H + u0, hp);
+  if (d.dout) ld16(d.dout + b * d.dout_pitch + u0, dh);
+  else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+  }
+
+  if (a.pdl) pdl_wait();
+  if (a.pdl) pdl_launch_dependents();
+
+  const long bpad = (long)a.tiles * 128;
+  for (int p = 0; p < d.n_parts; ++p) {
+    float t[16];
+    ld16(d.parts + (long)p * d.parts_stride + b * d.parts_pitch + u0, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dh[i] += t[i];
+  }
+
+  float dar[16], daz[16], dan[16], dgn[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float dn = dh[i] * (1.0f - z[i]);
+    const float dz = dh[i] * (hp[i] - n[i]);
+    dan[i] = dn * (1.0f - n[i] * n[i]);
+    daz[i] = dz * z[i] * (1.0f - z[i]);
+    dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
+    dgn[i] = dan[i] * r[i];
+    dh[i] = dh[i] * z[i];                                   // carry
+  }
+  // A operand (dgh slice) into shared memory: k = g*32 + j ; chunk 0 = gates r,z ; chunk 1 = gate n (k 64..95)
+  {
+    __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(sA);
+    __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sA + 2 * B_APLANE);
+    st16_p16(a0, 128, r_in, j0, dar);
+    st16_p16(a0, 128, r_in, 32 + j0, daz);
+    st16_p16(a1, 128, r_in, j0, dgn);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  if (tid == 0) {
+    mbar_wait(wbar, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, H);
+    for (int kc = 0; kc < 2; ++kc) {
+      const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
+      const uint32_t sw = smem_u32(sW + kc * wchunk);
+      const uint32_t wplane = (uint32_t)nrb * B_APLANE;
+      const int ksteps = kc == 0 ? 4 : 2;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t ko = ks * 2 * ATOM_BYTES;
+        const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
+        const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+        umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+        umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+        umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+      }
+    }
+    umma_commit(done);
+  }
+
+  // outputs that do not need the MMA
+  st16(d.parts_out + ((long)nsl * bpad + b) * H + u0, dh);            // carry slot
+  st16(d.dgi + b * 3 * H + u0, dar);
+  st16(d.dgi + b * 3 * H + H + u0, daz);
+  st16(d.dgi + b * 3 * H + 2 * H + u0, dan);
+  st16(d.dgh + b * 3 * H + u0, dar);
+  st16(d.dgh + b * 3 * H + H + u0, daz);
+  st16(d.dgh + b * 3 * H + 2 * H + u0, dgn);
+  if (d.dgi_p) {
+    const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int k = g * H + u0;
+      st16_p16(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+    }
+  }
+
+  mbar_wait(done, 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  float* prow = d.parts_out + ((long)c * bpad + b) * H;
+  const int hh = H / 2;
+  for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
+    float v[16];
+    tmem_ld16(taddr + c0, v);
+    tmem_ld_wait();
+    st16(prow + c0, v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st) {
+  const int nrb = (a.H + 127) / 128;
+  const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * B_APLANE + 256;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(gru_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
+  cudaLaunchKernelEx(&cfg, gru_step_bwd_kernel, a);
+}
+
+}  // namespace vb

@@ -1,0 +1,93 @@
+// Internal launch prototypes shared between the .cu translation units (not part of the public C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vb {
+
+// ---- pack.cu -------------------------------------------------------------------------------------
+// value(r, k) = src[i * ld + j] with (i, j) = transposed ? (k, r) : (r, k); zero outside i < nrows_src, j < ncols_src
+void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
+                     const int* col_map, int RB, void* out, cudaStream_t st);
+// W_hh [3H, H] -> forward-step slices (mode 0: P16 RB=96, rows (slice c, gate g, unit j) = W_hh[g*H + 32c + j, :], K = H)
+//               or backward-step slices (mode 1: per slice c a P16 RB=128 matrix [rows = unit u, K = 128]:
+//                                        value(u, k = g*32 + j) = W_hh[g*H + 32c + j, u], zero for k >= 96)
+void launch_pack_whh(const float* w_hh, int H, int mode, void* out, cudaStream_t st);
+// fused input-projection bias: out[d*3H + g*H + u] = b_ih_d[g*H+u] + (g < 2 ? b_hh_d[g*H+u] : 0)
+void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1, const float* b_hh1, int H, float* out, cudaStream_t st);
+void launch_h0_prepare(const float* src, int D, int B, int B_pad, int H, float* h32, void* hp, cudaStream_t st);
+void launch_bt_to_tb(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, cudaStream_t st);
+void launch_tb_to_bt(const float* src, int B, int T, int C, int B_pad, float* dst, cudaStream_t st);
+
+// ---- gemm.cu -------------------------------------------------------------------------------------
+struct GemmSeg {
+  const void* p;        // P16 tiles (RB = 128): tile(rb, kc) = p + (rb * rb_stride + kc) * tile_elems
+  long rb_stride;       // in tiles
+  int nkc;              // number of 64-wide K chunks in this segment
+};
+struct GemmArgs {
+  GemmSeg a[4], b[4];   // A: [M, K] , B: [N, K]; K = concatenation of up to 4 segments (A and B split independently)
+  int M, N;             // logical output extent (rows >= M / cols >= N are masked)
+  float* C;             // fp32 row-major
+  long ldc;
+  const float* bias;    // [N] or nullptr (added only by split 0)
+  int atomic;           // 1: red.add into C (split-K / accumulation), 0: plain store
+  int splits;           // gridDim.z
+};
+void launch_gemm_p16(const GemmArgs& g, cudaStream_t st);
+
+// ---- gru.cu --------------------------------------------------------------------------------------
+struct GruDirFwd {
+  const void* w_p;        // P16 (RB=96) W_hh slices: [H/32][KC][2][96x64], slice rows = r,z,n gates of 32 units
+  const float* b_hn;      // [H] hidden bias of the n gate (b_hr, b_hz are folded into gi)
+  const float* gi;        // input projections incl. biases; row(b,t) = gi + (b*gi_bs + t*gi_ts) * gi_pitch, gates at 0,H,2H
+  long gi_bs, gi_ts, gi_pitch;
+  int t;                  // time index of this step for this direction
+  const void* h_in_p;     // P16 (RB=128) [tiles][KC][2][128x64]
+  const float* h_in;      // fp32 [B_pad][H]
+  void* h_out_p;          // P16 like h_in_p
+  float* h_out;           // fp32 [B_pad][H]
+  float* sv_r; float* sv_z; float* sv_n; float* sv_ghn;   // saved gates for BPTT, each fp32 [B_pad][H] slot of this t (or nullptr)
+};
+struct GruFwdArgs {
+  GruDirFwd d[2];
+  int ndir, H, tiles;
+  int pdl;                // launch with programmatic stream serialization
+};
+void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
+
+struct GruDirBwd {
+  const void* wT_p;       // P16 (RB=128) [H/32 slices][rb: H_pad/128][KC=2][2][128x64]: B[n=u, k=g*32+j] = W_hh[g*H+32c+j, u]
+  const float* parts;     // incoming dh pieces: part p, row b at parts + p*parts_stride + b*parts_pitch (H wide); their sum is
+  int n_parts;            //   the dh flowing into this step
+  long parts_stride, parts_pitch;
+  const float* dout;      // upstream gradient of this step's output: row b at dout + b*dout_pitch (H wide) or nullptr
+  long dout_pitch;
+  const float* sv_r; const float* sv_z; const float* sv_n; const float* sv_ghn; const float* h_prev;   // [B_pad][H] slots of this t
+  float* parts_out;       // [H/32 + 1][B_pad][H]: slice partial sums of dgh @ W_hh, last slot = carry dh*z
+  float* dgi;             // [B_pad][3H] slot of this t (dgi_r, dgi_z, dgi_n)
+  float* dgh;             // [B_pad][3H] slot of this t (dgi_r, dgi_z, dgi_n * r)
+  void* dgi_p;            // optional P16 (RB=128) A-operand copy of dgi for the dx GEMM: [tiles][KC3H][2][128x64] slot of this t
+};
+struct GruBwdArgs {
+  GruDirBwd d[2];
+  int ndir, H, tiles;
+  int pdl;
+};
+void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st);
+
+// ---- simt.cu -------------------------------------------------------------------------------------
+// C[m,n] (=|+=) sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]); generic strides cover NT / NN / TN forms.
+struct SgemmArgs {
+  const float* A; long sam, sak;
+  const float* B; long sbk, sbn;
+  float* C; long scm, scn;
+  const float* bias;
+  int M, N, K;
+  int accumulate;        // 1: atomicAdd into C (also enables split-K), 0: store
+  int splitk;            // >= 1
+  float alpha;
+};
+void launch_sgemm(const SgemmArgs& g, cudaStream_t st);
+
+}  // namespace vb

@@ -1,0 +1,205 @@
+// fp32 -> P16 (bf16 hi/lo, UMMA canonical tiles) packing kernels and small layout helpers.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+
+// One thread produces one 16-byte atom row (8 consecutive k) of both planes.
+// value(r, k) = src[rm * ld + km]  (or src[km * ld + rm] when transposed), rm = row_map ? row_map[r] : r, idem km;
+// out-of-range / negative map entries give 0.
+__global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src, int K_src,
+                                const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
+                                __nv_bfloat16* __restrict__ out) {
+  const int nkc = (K + KCHUNK - 1) / KCHUNK;
+  const int nrb = (R + RB - 1) / RB;
+  const long total = (long)nrb * RB * nkc * 8;           // atom rows
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    // transposed sources are contiguous along r, others along k: pick the thread order that coalesces the reads
+    long r, k8g;
+    if (transposed) {
+      r = idx % ((long)nrb * RB);
+      k8g = idx / ((long)nrb * RB);
+    } else {
+      k8g = idx % ((long)nkc * 8);
+      r = idx / ((long)nkc * 8);
+    }
+    const int kbase = (int)k8g * 8;
+    float v[8];
+    const int rm = (r < R) ? (row_map ? row_map[r] : (int)r) : -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kbase + i;
+      const int km = (k < K) ? (col_map ? col_map[k] : k) : -1;
+      float x = 0.f;
+      if (rm >= 0 && km >= 0 && rm < R_src && km < K_src) x = transposed ? src[(long)km * ld + rm] : src[(long)rm * ld + km];
+      v[i] = x;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const int rb = (int)(r / RB), rr = (int)(r % RB);
+    const int kc = kbase / KCHUNK, kk = kbase % KCHUNK;
+    __nv_bfloat16* tile = out + ((size_t)rb * nkc + kc) * p16_tile_elems(RB);
+    const int off = p16_in_tile(rr, kk);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + (size_t)RB * KCHUNK + off) = lo;
+  }
+}
+
+void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
+                     const int* col_map, int RB, void* out, cudaStream_t st) {
+  const int nkc = (K + KCHUNK - 1) / KCHUNK, nrb = (R + RB - 1) / RB;
+  long total = (long)nrb * RB * nkc * 8;
+  int threads = 256;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  pack_p16_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, ld, transposed, R, K, R_src, K_src, row_map, col_map, RB,
+                                                        (__nv_bfloat16*)out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// W_hh slices for the recurrent step kernels (see kernels.h)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out) {
+  const int nsl = H / 32;
+  if (mode == 0) {
+    const int nkc = (H + KCHUNK - 1) / KCHUNK;
+    const long total = (long)nsl * 96 * nkc * 8;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+      const int k8g = (int)(idx % (nkc * 8));
+      const int p = (int)(idx / (nkc * 8));            // packed row
+      const int c = p / 96, g = (p % 96) / 32, j = p % 32;
+      const int srow = g * H + 32 * c + j, kbase = k8g * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (kbase + i < H) ? w[(long)srow * H + kbase + i] : 0.f;
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      __nv_bfloat16* tile = out + ((size_t)c * nkc + kbase / KCHUNK) * p16_tile_elems(96);
+      const int off = p16_in_tile(p % 96, kbase % KCHUNK);
+      *reinterpret_cast<uint4*>(tile + off) = hi;
+      *reinterpret_cast<uint4*>(tile + 96 * KCHUNK + off) = lo;
+    }
+  } else {
+    const int nrb = (H + 127) / 128;
+    const long total = (long)nsl * nrb * 128 * 2 * 8;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+      const int u = (int)(idx % (nrb * 128));          // coalesced along u (source columns)
+      const long rest = idx / (nrb * 128);
+      const int k8g = (int)(rest % 16), c = (int)(rest / 16);
+      const int kbase = k8g * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kbase + i, g = k / 32, j = k % 32;
+        v[i] = (k < 96 && u < H) ? w[(long)(g * H + 32 * c + j) * H + u] : 0.f;
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      __nv_bfloat16* tile = out + (((size_t)c * nrb + u / 128) * 2 + kbase / KCHUNK) * p16_tile_elems(128);
+      const int off = p16_in_tile(u % 128, kbase % KCHUNK);
+      *reinterpret_cast<uint4*>(tile + off) = hi;
+      *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
+    }
+  }
+}
+void launch_pack_whh(const float* w_hh, int H, int mode, void* out, cudaStream_t st) {
+  pack_whh_kernel<<<148, 256, 0, st>>>(w_hh, H, mode, (__nv_bfloat16*)out);
+}
+__global__ void bias_fuse_kernel(const float* __restrict__ bi0, const float* __restrict__ bh0, const float* __restrict__ bi1,
+                                 const float* __restrict__ bh1, int H, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 6 * H) return;
+  const int d = i / (3 * H), r = i % (3 * H);
+  const float* bi = d ? bi1 : bi0;
+  const float* bh = d ? bh1 : bh0;
+  out[i] = bi[r] + (r < 2 * H ? bh[r] : 0.f);
+}
+void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1, const float* b_hh1, int H, float* out, cudaStream_t st) {
+  bias_fuse_kernel<<<(6 * H + 255) / 256, 256, 0, st>>>(b_ih0, b_hh0, b_ih1, b_hh1, H, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// h0 preparation: src is a flat fp32 buffer viewed as [D][B][H] (for the decoder this is the raw
+// reinterpretation of the (B, 2H) latent_to_hidden output, vame/model/rnn_model.py:104,137); src == nullptr -> zeros.
+// Writes fp32 [D][B_pad][H] and packed P16 [D][tiles][KC][2][128x64].
+// ------------------------------------------------------------------------------------------------
+__global__ void h0_prepare_kernel(const float* __restrict__ src, int D, int B, int B_pad, int H, float* __restrict__ h32,
+                                  __nv_bfloat16* __restrict__ hp) {
+  const int nkc = (H + KCHUNK - 1) / KCHUNK;
+  const long total = (long)D * B_pad * nkc * 8;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k8g = (int)(idx % (nkc * 8));
+    const long rest = idx / (nkc * 8);
+    const int b = (int)(rest % B_pad), d = (int)(rest / B_pad);
+    const int kbase = k8g * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kbase + i;
+      v[i] = (src && b < B && k < H) ? src[((long)d * B + b) * H + k] : 0.f;
+    }
+    if (h32 && kbase < H) {
+      float* o = h32 + ((long)d * B_pad + b) * H + kbase;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (kbase + i < H) o[i] = v[i];
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const int tile_i = b / 128, rr = b % 128;
+    const int kc = kbase / KCHUNK, kk = kbase % KCHUNK;
+    __nv_bfloat16* tile = hp + (((size_t)d * (B_pad / 128) + tile_i) * nkc + kc) * p16_tile_elems(128);
+    const int off = p16_in_tile(rr, kk);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
+  }
+}
+
+void launch_h0_prepare(const float* src, int D, int B, int B_pad, int H, float* h32, void* hp, cudaStream_t st) {
+  const int nkc = (H + KCHUNK - 1) / KCHUNK;
+  long total = (long)D * B_pad * nkc * 8;
+  int threads = 256;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  h0_prepare_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, D, B, B_pad, H, h32, (__nv_bfloat16*)hp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (B, T, C) <-> time-major (T, B_pad, C) transposes (tiny tensors: x, fut, pred)
+// ------------------------------------------------------------------------------------------------
+__global__ void bt_to_tb_kernel(const float* __restrict__ src, int B, int T, int C, long src_bstride, long src_tstride,
+                                int B_pad, float* __restrict__ dst) {
+  const long total = (long)T * B_pad * C;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long r = idx / C;
+    const int b = (int)(r % B_pad), t = (int)(r / B_pad);
+    dst[idx] = (b < B) ? src[b * src_bstride + t * src_tstride + c] : 0.f;
+  }
+}
+__global__ void tb_to_bt_kernel(const float* __restrict__ src, int B, int T, int C, int B_pad, float* __restrict__ dst) {
+  const long total = (long)B * T * C;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long r = idx / C;
+    const int t = (int)(r % T), b = (int)(r / T);
+    dst[idx] = src[((long)t * B_pad + b) * C + c];
+  }
+}
+void launch_bt_to_tb(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, cudaStream_t st) {
+  long total = (long)T * B_pad * C;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  bt_to_tb_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, B, T, C, bs, ts, B_pad, dst);
+}
+void launch_tb_to_bt(const float* src, int B, int T, int C, int B_pad, float* dst, cudaStream_t st) {
+  long total = (long)B * T * C;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  tb_to_bt_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, B, T, C, B_pad, dst);
+}
+
+}  // namespace vb

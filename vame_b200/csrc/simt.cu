@@ -1,0 +1,415 @@
+// HBM-bound elementwise / reduction kernels of the RNN-VAE hot path: Lambda reparameterisation + KL, MSE loss with its
+// gradient, the k-means prior (cluster_loss) via a Z x Z Gram matrix and an in-kernel fp64 Jacobi eigensolver,
+// bias-gradient column sums, AMSGrad Adam.  Vectorised global accesses, warp-shuffle reductions, one atomic per warp/CTA.
+#include "common.cuh"
+#include "kernels.h"
+#include "simt.h"
+
+namespace vb {
+
+// -------------------------------------------------------------------------------------------------
+// Lambda forward (vame/model/rnn_model.py:63-76) on the fused [mu | logvar] linear output + KL partial sum
+// (vame/model/rnn_vae.py:53-60: KLD = -0.5 * mean(1 + logvar - mu^2 - exp(logvar)))
+//   lin: [B_pad, ldl] with mu in cols [0,Z), pre-activation logvar in [Z,2Z)
+//   eps == nullptr -> eval mode, z = mu.   acc[ACC_KL] += sum(1 + lv - mu^2 - e^lv)
+// -------------------------------------------------------------------------------------------------
+__global__ void lambda_fwd_kernel(const float* __restrict__ lin, long ldl, const float* __restrict__ eps, int B, int Z,
+                                  int softplus, float* __restrict__ z, float* __restrict__ mu, float* __restrict__ logvar,
+                                  double* __restrict__ acc) {
+  const long total = (long)B * Z;
+  float part = 0.f;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Z);
+    const long b = idx / Z;
+    const float m = lin[b * ldl + j];
+    float lv = lin[b * ldl + Z + j];
+    if (softplus) lv = (lv > 20.f) ? lv : log1pf(expf(lv));
+    mu[idx] = m;
+    logvar[idx] = lv;
+    z[idx] = eps ? eps[idx] * expf(0.5f * lv) + m : m;
+    part += 1.f + lv - m * m - expf(lv);
+  }
+  part = warp_sum(part);
+  if (acc && (threadIdx.x & 31) == 0) atomicAdd(acc + ACC_KL, (double)part);
+}
+
+// Lambda backward: dlin = [dmu | dlv_lin] for valid rows, 0 for padded rows.
+//   dz = sum of up to 4 gradient pieces (cluster prior, decoder, future decoder, external)
+//   dmu = dz + dmu_ext + c_kl * mu ;  dlv = dz * eps * 0.5 * exp(0.5 lv) + dlv_ext + c_kl * 0.5 * (exp(lv) - 1)
+__global__ void lambda_bwd_kernel(LambdaBwdArgs a) {
+  const long total = (long)a.B_pad * a.Z;
+  const float c_kl = a.hyper ? a.hyper[HY_BETA] * a.hyper[HY_KLW] / (float)((long)a.B * a.Z) : a.c_kl;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % a.Z);
+    const long b = idx / a.Z;
+    float dmu = 0.f, dlv = 0.f;
+    if (b < a.B) {
+      const long i = b * a.Z + j;
+      float dz = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (a.dz[p]) dz += a.dz[p][i];
+      const float m = a.mu[i], lv = a.logvar[i];
+      dmu = dz + c_kl * m + (a.dmu_ext ? a.dmu_ext[i] : 0.f);
+      dlv = c_kl * 0.5f * (expf(lv) - 1.f) + (a.dlv_ext ? a.dlv_ext[i] : 0.f);
+      if (a.eps) dlv += dz * a.eps[i] * 0.5f * expf(0.5f * lv);
+      if (a.softplus) {
+        const float x = a.lin[b * a.ldl + a.Z + j];
+        dlv *= 1.f / (1.f + expf(-x));
+      }
+    }
+    a.dlin[b * a.ldd + j] = dmu;
+    a.dlin[b * a.ldd + a.Z + j] = dlv;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// MSE (vame/model/rnn_vae.py:35-43, nn.MSELoss(reduction)) on time-major buffers + gradient
+//   pred, target: [T * B_pad, F] ; rows with (row % B_pad) >= B are padding.  acc[slot] += sum (pred - target)^2
+//   dpred = gscale * (pred - target) on valid rows, 0 on padding (gscale = 2 for 'sum', 2/(B*T*F) for 'mean')
+// -------------------------------------------------------------------------------------------------
+__global__ void mse_kernel(const float* __restrict__ pred, long ldp, const float* __restrict__ target, int rows, int B,
+                           int B_pad, int F, float gscale, float* __restrict__ dpred, double* __restrict__ acc, int slot) {
+  const long total = (long)rows * F;
+  float part = 0.f;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % F);
+    const long r = idx / F;
+    float d = 0.f;
+    if ((int)(r % B_pad) < B) d = pred[r * ldp + f] - target[idx];
+    part += d * d;
+    if (dpred) dpred[idx] = gscale * d;
+  }
+  part = warp_sum(part);
+  if (acc && (threadIdx.x & 31) == 0) atomicAdd(acc + slot, (double)part);
+}
+
+// -------------------------------------------------------------------------------------------------
+// k-means prior (vame/model/rnn_vae.py:45-50 called as cluster_loss(latent.T, k, lambda, bsize) at :126,:137):
+//   loss = lambda * sum_{i<k} sqrt(sv_i(latent latent^T / bsize)).  The B x B matrix's non-zero singular values are
+//   the eigenvalues of G = latent^T latent / bsize (Z x Z), so G is built with a coalesced batch reduction and
+//   diagonalised in-kernel by a parallel cyclic Jacobi sweep in fp64 (Z <= 64).
+//   grad wrt latent = coef * 2 * latent * (V_k diag(0.5 / sqrt(ev)) V_k^T) / bsize.
+// One CTA of 1024 threads.
+// -------------------------------------------------------------------------------------------------
+constexpr int CP_MAXZ = 64;
+constexpr size_t CP_SMEM = 2 * CP_MAXZ * (CP_MAXZ + 1) * 8 + (CP_MAXZ + CP_MAXZ + 1) * 8 + (CP_MAXZ * 2) * 4 + 64 * (CP_MAXZ + 1) * 4 + 64;
+
+__global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __restrict__ z, int B, int Z, int kloss,
+                                                                double lmbda, double bsize, double gcoef,
+                                                                const float* __restrict__ hyper,
+                                                                float* __restrict__ dz, double* __restrict__ acc) {
+  if (hyper) {
+    lmbda = (double)hyper[HY_KMLAMBDA];
+    gcoef = (double)hyper[HY_KLW];
+  }
+  extern __shared__ __align__(16) uint8_t cp_smem[];
+  typedef double Row[CP_MAXZ + 1];
+  Row* A = reinterpret_cast<Row*>(cp_smem);
+  Row* V = A + CP_MAXZ;
+  double* cs = reinterpret_cast<double*>(V + CP_MAXZ);
+  double* sn = cs + CP_MAXZ / 2;
+  double* ev = sn + CP_MAXZ / 2;
+  double* offmax_p = ev + CP_MAXZ;
+  int* pp = reinterpret_cast<int*>(offmax_p + 1);
+  int* qq = pp + CP_MAXZ / 2;
+  int* order = qq + CP_MAXZ / 2;
+  typedef float ZRow[CP_MAXZ + 1];
+  ZRow* zs = reinterpret_cast<ZRow*>(order + CP_MAXZ);
+#define offmax (*offmax_p)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n = (Z + 1) & ~1;                       // even size for the round-robin pairing (pad row/col is zero)
+
+  // ---- Gram matrix in fp64: each thread owns entries (i,j) = tid, tid+nt, ... of the n x n matrix
+  double g[4] = {0, 0, 0, 0};                        // n*n <= 4096 = 4 * 1024
+  for (int b0 = 0; b0 < B; b0 += 64) {
+    const int nb = min(64, B - b0);
+    for (int e = tid; e < nb * Z; e += nt) zs[e / Z][e % Z] = z[(long)(b0 + e / Z) * Z + e % Z];
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int e = tid + s * nt;
+      if (e < Z * Z) {
+        const int i = e / Z, j = e % Z;
+        double t = 0;
+        for (int b = 0; b < nb; ++b) t += (double)zs[b][i] * (double)zs[b][j];
+        g[s] += t;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < CP_MAXZ * CP_MAXZ; e += nt) {
+    A[e / CP_MAXZ][e % CP_MAXZ] = 0;
+    V[e / CP_MAXZ][e % CP_MAXZ] = (e / CP_MAXZ == e % CP_MAXZ) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int e = tid + s * nt;
+    if (e < Z * Z) A[e / Z][e % Z] = g[s] / bsize;
+  }
+  __syncthreads();
+
+  // ---- parallel cyclic Jacobi (round-robin tournament ordering: n-1 rounds of n/2 disjoint rotations)
+  const int half = n / 2;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    if (tid == 0) offmax = 0;
+    __syncthreads();
+    {
+      double m = 0;
+      for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e % n;
+        if (i != j) m = fmax(m, fabs(A[i][j]));
+      }
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((tid & 31) == 0 && m > 0) atomicMax(reinterpret_cast<unsigned long long*>(&offmax), (unsigned long long)__double_as_longlong(m));
+    }
+    __syncthreads();
+    double dmax = 0;
+    for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i][i]));
+    if (offmax <= 1e-18 * dmax || offmax == 0) break;
+    for (int round = 0; round < n - 1; ++round) {
+      if (tid < half) {
+        // circle method: player n-1 fixed, the others rotate
+        const int a0 = (tid == 0) ? n - 1 : (round + tid) % (n - 1);
+        const int b0 = (tid == 0) ? round : (round - tid + (n - 1)) % (n - 1);
+        const int p = min(a0, b0), q = max(a0, b0);
+        pp[tid] = p; qq[tid] = q;
+        const double apq = A[p][q];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1e-300) {
+          const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+          const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+        }
+        cs[tid] = c; sn[tid] = s;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int e = tid; e < half * n; e += nt) {
+        const int k = e / n, i = e % n;
+        const int p = pp[k], q = qq[k];
+        const double c = cs[k], s = sn[k];
+        const double aip = A[i][p], aiq = A[i][q];
+        A[i][p] = c * aip - s * aiq;
+        A[i][q] = s * aip + c * aiq;
+        const double vip = V[i][p], viq = V[i][q];
+        V[i][p] = c * vip - s * viq;
+        V[i][q] = s * vip + c * viq;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < half * n; e += nt) {
+        const int k = e / n, j = e % n;
+        const int p = pp[k], q = qq[k];
+        const double c = cs[k], s = sn[k];
+        const double apj = A[p][j], aqj = A[q][j];
+        A[p][j] = c * apj - s * aqj;
+        A[q][j] = s * apj + c * aqj;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- eigenvalues, top-k selection (rank bound min(k, B, Z)), loss
+  if (tid < n) ev[tid] = (tid < Z) ? A[tid][tid] : -1e300;
+  __syncthreads();
+  if (tid < n) {
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (ev[j] > ev[tid]) || (ev[j] == ev[tid] && j < tid);
+    order[rank] = tid;
+  }
+  __syncthreads();
+  const int k = min(kloss, min(B, Z));
+  if (tid == 0 && acc) {
+    double s = 0;
+    for (int i = 0; i < k; ++i) s += sqrt(fmax(ev[order[i]], 0.0));
+    acc[ACC_KMEANS] = lmbda * s;
+  }
+  if (!dz) return;
+  // S = V_k diag(0.5 / sqrt(ev)) V_k^T  -> reuse A
+  __syncthreads();
+  for (int e = tid; e < Z * Z; e += nt) {
+    const int i = e / Z, j = e % Z;
+    double t = 0;
+    for (int m = 0; m < k; ++m) {
+      const int col = order[m];
+      const double l = ev[col];
+      if (l > 0) t += V[i][col] * V[j][col] * (0.5 / sqrt(l));
+    }
+    A[i][j] = t;
+  }
+  __syncthreads();
+  const double sc = gcoef * lmbda * 2.0 / bsize;
+  for (int b0 = 0; b0 < B; b0 += 64) {
+    const int nb = min(64, B - b0);
+    for (int e = tid; e < nb * Z; e += nt) zs[e / Z][e % Z] = z[(long)(b0 + e / Z) * Z + e % Z];
+    __syncthreads();
+    for (int e = tid; e < nb * Z; e += nt) {
+      const int b = e / Z, j = e % Z;
+      double t = 0;
+      for (int i = 0; i < Z; ++i) t += (double)zs[b][i] * A[i][j];
+      dz[(long)(b0 + b) * Z + j] = (float)(sc * t);
+    }
+    __syncthreads();
+  }
+}
+
+#undef offmax
+// -------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] (+)= sum_m X[m*ld + n]
+// -------------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const float* __restrict__ X, long ld, long rows, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  for (long r = r0; r < r1; ++r) s += X[r * ld + n];
+  atomicAdd(out + n, s);
+}
+
+// out[b, :] = sum_t X[t][b][:]   (X: [T][rows][C])
+__global__ void timesum_kernel(const float* __restrict__ X, int T, long rowsC, float* __restrict__ out) {
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < rowsC; idx += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += X[(long)t * rowsC + idx];
+    out[idx] = s;
+  }
+}
+
+// sum of the dh pieces left by the last BPTT step -> dense dh0; optionally written in the UNPADDED [D][B][H] order
+// (the flat buffer that the reference's hidden.view(2,B,H) aliases, rnn_model.py:104)
+__global__ void parts_reduce_kernel(const float* __restrict__ parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H,
+                                    float* __restrict__ out, int unpadded) {
+  const long total = (long)D * B_pad * H;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % H);
+    const long r = idx / H;
+    const int b = (int)(r % B_pad), d = (int)(r / B_pad);
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += parts[d * dir_stride + ((long)p * B_pad + b) * H + k];
+    if (unpadded) {
+      if (b < B) out[((long)d * B + b) * H + k] = s;
+    } else {
+      out[idx] = s;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// AMSGrad Adam, flat multi-tensor (torch.optim.Adam(amsgrad=True), vame/model/rnn_vae.py:332,143)
+//   36 B/param of HBM traffic (p, g, m, v, vmax read; p, m, v, vmax written); grad_scale folds the DP 1/world average.
+// -------------------------------------------------------------------------------------------------
+// prepare: increments the device step counter and derives the bias corrections (1 thread)
+__global__ void adam_prepare_kernel(int* __restrict__ step_dev, float* __restrict__ sc, float lr, const float* __restrict__ hyper,
+                                    float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int step = *step_dev + 1;
+    *step_dev = step;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const double l = hyper ? (double)hyper[HY_LR] : (double)lr;
+    sc[0] = (float)(l / bc1);
+    sc[1] = (float)sqrt(bc2);
+  }
+}
+__global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, float* __restrict__ vmax, long n, const float* __restrict__ sc,
+                                    float beta1, float beta2, float eps, float grad_scale) {
+  const long n4 = n / 4;
+  const float step_size = sc[0], bc2_sqrt = sc[1];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], Vv = reinterpret_cast<float4*>(v)[i], X = reinterpret_cast<float4*>(vmax)[i];
+    float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &Vv.x; float* xx = &X.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gg[j] * grad_scale;
+      mm[j] = beta1 * mm[j] + (1.f - beta1) * gr;
+      vv[j] = beta2 * vv[j] + (1.f - beta2) * gr * gr;
+      xx[j] = fmaxf(xx[j], vv[j]);
+      const float denom = sqrtf(xx[j]) / bc2_sqrt + eps;
+      pp[j] -= step_size * (mm[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = Vv;
+    reinterpret_cast<float4*>(vmax)[i] = X;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long i = n4 * 4 + threadIdx.x;
+    const float gr = g[i] * grad_scale;
+    m[i] = beta1 * m[i] + (1.f - beta1) * gr;
+    v[i] = beta2 * v[i] + (1.f - beta2) * gr * gr;
+    vmax[i] = fmaxf(vmax[i], v[i]);
+    p[i] -= step_size * (m[i] / (sqrtf(vmax[i]) / bc2_sqrt + eps));
+  }
+}
+
+// losses: acc (double[8]) -> out (float[8]) following rnn_vae.py:124-129
+__global__ void finalize_losses_kernel(const double* __restrict__ acc, float* __restrict__ out, double rec_div, double fut_div,
+                                       double kl_n, double beta, double klw, const float* __restrict__ hyper, int future) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (hyper) {
+      beta = (double)hyper[HY_BETA];
+      klw = (double)hyper[HY_KLW];
+    }
+    const double rec = acc[ACC_REC] / rec_div;
+    const double fut = future ? acc[ACC_FUT] / fut_div : 0.0;
+    const double kl = -0.5 * acc[ACC_KL] / kl_n;
+    const double km = acc[ACC_KMEANS];
+    out[0] = (float)rec; out[1] = (float)fut; out[2] = (float)kl; out[3] = (float)km;
+    out[4] = (float)(rec + fut + beta * klw * kl + klw * km);
+  }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+static inline unsigned grid_for(long total, int threads, int cap = 148 * 8) {
+  long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+void launch_lambda_fwd(const float* lin, long ldl, const float* eps, int B, int Z, int softplus, float* z, float* mu, float* logvar,
+                       double* acc, cudaStream_t st) {
+  lambda_fwd_kernel<<<grid_for((long)B * Z, 256), 256, 0, st>>>(lin, ldl, eps, B, Z, softplus, z, mu, logvar, acc);
+}
+void launch_lambda_bwd(const LambdaBwdArgs& a, cudaStream_t st) {
+  lambda_bwd_kernel<<<grid_for((long)a.B_pad * a.Z, 256), 256, 0, st>>>(a);
+}
+void launch_mse(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
+                double* acc, int slot, cudaStream_t st) {
+  mse_kernel<<<grid_for((long)rows * F, 256), 256, 0, st>>>(pred, ldp, target, rows, B, B_pad, F, gscale, dpred, acc, slot);
+}
+void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
+                          float* dz, double* acc, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(cluster_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
+    attr = true;
+  }
+  cluster_prior_kernel<<<1, 1024, CP_SMEM, st>>>(z, B, Z, kloss, lmbda, bsize, gcoef, hyper, dz, acc);
+}
+void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st) {
+  int ysplit = (int)min((long)64, (rows + 127) / 128);
+  if (ysplit < 1) ysplit = 1;
+  colsum_kernel<<<dim3((N + 127) / 128, ysplit), 128, 0, st>>>(X, ld, rows, N, out);
+}
+void launch_timesum(const float* X, int T, long rowsC, float* out, cudaStream_t st) {
+  timesum_kernel<<<grid_for(rowsC, 256), 256, 0, st>>>(X, T, rowsC, out);
+}
+void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, int unpadded,
+                         cudaStream_t st) {
+  parts_reduce_kernel<<<grid_for((long)D * B_pad * H, 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out, unpadded);
+}
+void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
+                 float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st) {
+  adam_prepare_kernel<<<1, 32, 0, st>>>(step_dev, scratch2, lr, hyper, b1, b2);
+  adam_amsgrad_kernel<<<grid_for(n / 4 + 1, 256, 148 * 4), 256, 0, st>>>(p, g, m, v, vmax, n, scratch2, b1, b2, eps, grad_scale);
+}
+void launch_finalize_losses(const double* acc, float* out, double rec_div, double fut_div, double kl_n, double beta, double klw,
+                            const float* hyper, int future, cudaStream_t st) {
+  finalize_losses_kernel<<<1, 32, 0, st>>>(acc, out, rec_div, fut_div, kl_n, beta, klw, hyper, future);
+}
+
+}  // namespace vb

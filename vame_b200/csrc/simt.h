@@ -1,0 +1,42 @@
+// Launch prototypes of the SIMT (HBM-bound) kernels in simt.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vb {
+
+enum { ACC_REC = 0, ACC_FUT = 1, ACC_KL = 2, ACC_KMEANS = 3, ACC_COUNT = 8 };
+// device-resident hyper-parameters that change between steps (kept out of kernel arguments so that a captured
+// CUDA graph of the whole train step stays valid): hyper[HY_*]
+enum { HY_LR = 0, HY_KLW = 1, HY_BETA = 2, HY_KMLAMBDA = 3, HY_COUNT = 8 };
+
+struct LambdaBwdArgs {
+  const float* dz[4];          // gradient pieces wrt z, each [B, Z] or nullptr
+  const float* dmu_ext;        // optional external gradient wrt mu / logvar outputs ([B, Z])
+  const float* dlv_ext;
+  const float* mu; const float* logvar; const float* eps;   // [B, Z]; eps nullptr -> eval (no reparam term)
+  const float* lin; long ldl;  // forward linear output (needed for softplus')
+  const float* hyper;          // device hyper-parameters or nullptr
+  float c_kl;                  // used when hyper == nullptr: beta * kl_weight / (B * Z)
+  int B, B_pad, Z, softplus;
+  float* dlin; long ldd;       // [B_pad, 2Z]
+};
+
+void launch_lambda_fwd(const float* lin, long ldl, const float* eps, int B, int Z, int softplus, float* z, float* mu, float* logvar,
+                       double* acc, cudaStream_t st);
+void launch_lambda_bwd(const LambdaBwdArgs& a, cudaStream_t st);
+void launch_mse(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
+                double* acc, int slot, cudaStream_t st);
+// hyper != nullptr: lambda = hyper[HY_KMLAMBDA], gradient coefficient = hyper[HY_KLW]; else the scalar arguments
+void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
+                          float* dz, double* acc, cudaStream_t st);
+void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st);
+void launch_timesum(const float* X, int T, long rowsC, float* out, cudaStream_t st);
+void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, int unpadded,
+                         cudaStream_t st);
+// step_dev: device int32 step counter (incremented by the kernel chain); lr from hyper[HY_LR] when hyper != nullptr
+void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
+                 float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st);
+void launch_finalize_losses(const double* acc, float* out, double rec_div, double fut_div, double kl_n, double beta, double klw,
+                            const float* hyper, int future, cudaStream_t st);
+
+}  // namespace vb
