@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — pose-windows/s of the RNN-VAE train step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 10                      # our CUDA path (one JSON line)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      # weak scaling, one rank per GPU, NCCL allreduce
+    python bench.py --impl reference --steps 5 --warmup 1                 # the reference's CPU arithmetic (oracle port)
+
+A "step" = forward + 4 losses + backward + [gradient allreduce] + AMSGrad over one batch of synthetic pose windows
+(SURVEY.md §8d).  `value` is measured with the batch resident in HBM; `e2e` repeats it through host buffers (pinned
+H2D copy of the batch and D2H read of the loss inside the timed region).  See DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (F, T, Z, H, future, S, per-GPU batch)
+    "c2": (24, 30, 30, 256, False, 0, 256),      # BASELINE configs[1]: the configuration `metric` is quoted on
+    "c2fut": (24, 30, 30, 256, True, 15, 256),
+    "c3": (60, 60, 50, 256, True, 30, 512),      # BASELINE configs[2]
+    "c5": (24, 30, 30, 256, False, 0, 512),      # BASELINE configs[4]: 512 windows per GPU (global 4096 at 8 GPUs)
+}
+
+
+def fwd_flops_per_window(F, T, Z, H, fut, S):
+    """Algorithmic forward FLOPs per window, MAC = 2 FLOP, reference-as-written."""
+    G = 3 * H
+    enc = 2 * T * (F * G + H * G) * 2 + 2 * T * (2 * H * G + H * G) * 2
+    lam = 2 * (4 * H) * Z * 2
+    dec = Z * 2 * H * 2 + 2 * T * (Z * G + H * G) * 2 + T * 2 * H * F * 2
+    f = enc + lam + dec
+    if fut:
+        f += Z * 2 * H * 2 + 2 * S * (Z * G + H * G) * 2 + S * 2 * H * F * 2
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_step_time(F, T, Z, H, fut, S, B, steps, warmup, threads=None):
+    """The reference's CPU arithmetic (oracle torch port: same ATen calls) for the same step, all host cores."""
+    import torch
+    from oracle import vame_oracle as vo
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
+    opt = vo.make_optimizer(port)
+    x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z)
+    hp = dict(beta=1.0, kl_weight=1.0, kmeans_loss=Z, kmeans_lambda=0.1, bsize=B)
+    for _ in range(warmup):
+        vo.train_step(port, x, xf[:, :S] if fut else xf, eps, hp, optimizer=opt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vo.train_step(port, x, xf[:, :S] if fut else xf, eps, hp, optimizer=opt)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, torch.get_num_threads()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--per-gpu-batch", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    F, T, Z, H, fut, S, B = WORKLOADS[args.workload]
+    if args.per_gpu_batch:
+        B = args.per_gpu_batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    K = args.steps
+    cfg_desc = {"workload": "%s: synthetic pose windows F=%d T=%d Z=%d H=%d, %d windows/GPU, %s, train step = fwd + rec/KL/k-means%s losses + "
+                            "bwd + %sAMSGrad" % (args.workload, F, T, Z, H, B, "future decoder S=%d" % S if fut else "no future decoder",
+                                                 "/future" if fut else "", "NCCL grad allreduce + " if world > 1 else ""),
+                "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+                "l2": "per-step working set (activations + P16 operand copies, > 1 GB) exceeds the 126 MB L2; no explicit flush"}
+    step_flops = 3 * fwd_flops_per_window(F, T, Z, H, fut, S) * B            # train = 3 x forward
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dt, thr = cpu_port_step_time(F, T, Z, H, fut, S, B, K, W)
+        v = B / dt
+        line = {"impl": "reference", "metric": "pose_windows_per_sec_train_step", "value": v, "unit": "windows/s", "n_gpus": args.gpus,
+                "steps": K, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": dict(cfg_desc, parallelism="cpu"),
+                "cpu_baseline": {"value": v, "unit": "windows/s", "cores": thr, "kind": "port",
+                                 "sample": "%d steps of the same %d-window batch on the host CPU (oracle torch port = the reference's ATen calls)" % (K, B)},
+                "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the vame_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from oracle import vame_oracle as vo     # only for the deterministic synthetic inputs / reference init
+    from vame_b200.engine import Engine, TrainStep
+    from vame_b200 import _lib as L
+    import ctypes
+
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)                  # reference default init under seed 19 (rnn_vae.py:292)
+    eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda:%d" % local_rank)
+    eng.load_state_dict(port.state_dict())
+    x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z, seed=19 + rank)
+    xf = xf[:, :S] if fut else None
+    cfg = eng.loss_cfg(kmeans_loss=Z, kmeans_lambda=0.1, bsize=B, beta=1.0, kl_weight=1.0)
+    eng.set_hyper(lr=5e-4, kl_weight=1.0, beta=1.0, kmeans_lambda=0.1)
+    ts = TrainStep(eng, B, cfg, world=world, use_graph=not args.no_graph)
+    graphed = ts.capture()
+    ts.load(x.cuda(), xf.cuda() if fut else None, eps.cuda())
+    lib = L.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(W):
+        ts.run()
+    barrier()
+    launches0 = lib.vame_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        ts.run()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / K
+    launches_eager = lib.vame_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss_after = float(ts.losses[4].item())
+
+    # ---- end to end through host buffers: pinned H2D of the batch + D2H of the loss every step
+    xh, eh = x.pin_memory(), eps.pin_memory()
+    fh = xf.pin_memory() if fut else None
+    loss_h = torch.zeros(8).pin_memory()
+    for _ in range(3):
+        ts.load(xh, fh, eh)
+        ts.run()
+    barrier()
+    e0.record()
+    for _ in range(K):
+        ts.load(xh, fh, eh)
+        loss_h.copy_(ts.run(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()           # the caller consumes the loss every step
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    h2d = xh.numel() * 4 + eh.numel() * 4 + (fh.numel() * 4 if fut else 0)
+
+    # ---- launches per step: count one eager step (graph replays do not pass through the host launchers)
+    if graphed:
+        c0 = lib.vame_launch_count()
+        ts._phase1(); ts._phase2()
+        torch.cuda.synchronize()
+        per_step = lib.vame_launch_count() - c0
+        gpu_launches = per_step * K
+    else:
+        gpu_launches = launches_eager
+
+    # ---- roofline of the dominant kernels: the recurrent step kernels, timed alone with CUDA events on their stream
+    roof = None
+    if rank == 0:
+        ts._phase1()                                       # leaves forward + backward state in the workspace
+        ws = eng.workspace(B, True)
+        res = {}
+        for which, name in ((0, "gru_step_fwd_kernel"), (1, "gru_step_bwd_kernel")):
+            for _ in range(3):
+                L.check(lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, which, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream()), "sweep")
+            torch.cuda.synchronize()
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                L.check(lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, which, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream()), "sweep")
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) * 1e-3 / (reps * T)      # seconds per launch (both directions in one launch)
+        peak_burst, peak_sus, hbm, how = peaks()
+        flops_launch = 2 * B * (3 * H) * H * 2                      # both directions: [B,H] x [H,3H] MACs, MAC = 2 FLOP
+        dom = max(res, key=res.get)
+        ach = flops_launch / res[dom] / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
+                "traffic": None, "peak_source": how + ", burst figure (kernel timed alone)",
+                "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 3 * flops_launch,
+                "us_per_launch": {k: v * 1e6 for k, v in res.items()},
+                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction; the kernel issues 3x that in bf16 MMAs "
+                        "(hi*hi + hi*lo + lo*hi), so the algorithmic ceiling is 1/3 of the bf16 peak; B=%d leaves most SMs idle "
+                        "(latency-bound recurrence)" % B,
+                "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
+                "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, thr = cpu_port_step_time(F, T, Z, H, fut, S, B, 3, 1)
+        cpu = {"value": B / dt, "unit": "windows/s", "cores": thr, "kind": "port",
+               "sample": "3 timed steps (1 warm-up) of the same %d-window train step on the host CPU, %d torch threads" % (B, thr),
+               "ms_per_step": dt * 1e3}
+
+    if rank == 0:
+        line = {"metric": "pose_windows_per_sec_train_step", "value": B * world / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tensor-core products as 3-pass bf16 hi/lo split, fp32 accumulate)", "data": "synthetic",
+                "config": dict(cfg_desc, cuda_graph=bool(graphed)), "clocks": clocks,
+                "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 32},
+                "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu, "loss_after": loss_after}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

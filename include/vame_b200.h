@@ -18,6 +18,10 @@ extern "C" {
 
 const char* vame_last_error(void);
 int vame_abi_version(void);
+/* number of kernels enqueued by this library so far (host counter) */
+long vame_launch_count(void);
+/* runtime options: "pdl" (default 1) chains the recurrent step kernels with programmatic dependent launch */
+int vame_set_option(const char* name, int value);
 
 /* ---- building blocks ------------------------------------------------------------------------ */
 /* bytes of a P16 (bf16 hi/lo split, tensor-core tiled) copy of a [rows, k] matrix */
@@ -30,6 +34,101 @@ int vame_pack_p16(const float* src, long ld, int transposed, int rows, int k, in
  * (vame/model/rnn_model.py:34-35,41) and their backward. */
 int vame_gemm_p16(const void* a_p, int a_nkc, const void* b_p, int b_nkc, int M, int N, float* C, long ldc,
                   const float* bias, int accumulate, int splits, void* stream);
+
+/* ---- model level ----------------------------------------------------------------------------- */
+/* Mirrors the constructor arguments of RNN_VAE (vame/model/rnn_model.py:148-161); time_window is the model's
+ * seq_len = TEMPORAL_WINDOW/2 (rnn_model.py:154).  hidden sizes must be multiples of 32 and <= 256. */
+typedef struct {
+  int num_features;    /* NUM_FEATURES */
+  int time_window;     /* seq_len */
+  int zdims;           /* ZDIMS (<= 64) */
+  int hidden_enc;      /* hidden_size_layer_1 (the reference ignores hidden_size_layer_2, rnn_model.py:34) */
+  int hidden_rec;      /* hidden_size_rec */
+  int hidden_pred;     /* hidden_size_pred */
+  int future_decoder;  /* FUTURE_DECODER */
+  int future_steps;    /* FUTURE_STEPS */
+  int softplus;        /* Lambda softplus flag */
+} vame_dims;
+
+/* loss configuration of train()/test() (vame/model/rnn_vae.py:94-210) */
+typedef struct {
+  int mse_red_mean;      /* mse_reconstruction_reduction: 0 = 'sum', 1 = 'mean' */
+  int mse_pred_mean;     /* mse_prediction_reduction */
+  int kmeans_loss;       /* number of singular values kept (cfg['kmeans_loss']) */
+  float kmeans_lambda;   /* used when hyper == NULL */
+  float bsize;           /* the batch_size argument of cluster_loss (cfg['batch_size']) */
+  float beta;            /* used when hyper == NULL */
+  float kl_weight;       /* used when hyper == NULL */
+  int with_future;       /* include the future-reconstruction term (train) or not (test, rnn_vae.py:186-190) */
+} vame_loss_cfg;
+
+/* Number of parameter tensors (44 with the future decoder, 32 without) and their placement in the flat fp32 buffer.
+ * offsets[i]/sizes[i] follow the reference's state_dict order; returns the total float count. */
+int vame_param_tensors(const vame_dims* d);
+long vame_param_layout(const vame_dims* d, long* offsets, long* sizes);
+
+/* bf16 hi/lo tensor-core copies of the weights; must be refreshed after every parameter update */
+size_t vame_packed_weights_bytes(const vame_dims* d);
+int vame_pack_weights(const vame_dims* d, const float* params, void* packed, void* stream);
+
+size_t vame_workspace_bytes(const vame_dims* d, int batch, int training);
+
+/* RNN_VAE.forward (vame/model/rnn_model.py:162-179).  x: [B, T, F] (strides in floats, feature stride 1).
+ * eps: [B, Z] reparameterisation noise (the reference draws it with randn_like, rnn_model.py:73) or NULL for eval
+ * mode (z = mu).  save_for_backward keeps the activations BPTT needs in the workspace.  Outputs may be NULL. */
+int vame_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* x, long x_bs,
+                 long x_ts, const float* eps, int save_for_backward, float* pred, float* future, float* z, float* mu,
+                 float* logvar, void* ws, size_t ws_bytes, void* stream);
+
+/* The four loss terms of train()/test() on the last vame_forward (rnn_vae.py:124-129,135-138,188-197) and their
+ * gradients wrt pred / future / z (kept in the workspace for vame_backward).
+ * hyper: device float[8] {lr, kl_weight, beta, kmeans_lambda, ...} or NULL to use the cfg scalars.
+ * losses_out: device float[8] = {rec, fut, kl, kmeans, total, 0, 0, 0}. */
+int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts, const float* hyper, float* losses_out, int want_grads, void* ws,
+              size_t ws_bytes, void* stream);
+
+/* Backward of the last vame_forward (replaces loss.backward(), rnn_vae.py:142).  If use_loss_grads != 0 the upstream
+ * gradients are the ones vame_loss left in the workspace (d pred, d future, d z from the k-means prior, KL through
+ * hyper / cfg); otherwise they are the external tensors (autograd path), any of which may be NULL.
+ * grads: flat fp32 buffer in the vame_param_layout order, OVERWRITTEN (zero_grad + backward). */
+int vame_backward(const vame_dims* d, int batch, const float* params, const void* packed, int use_loss_grads,
+                  const vame_loss_cfg* cfg, const float* hyper, const float* dpred, const float* dfuture,
+                  const float* dz, const float* dmu, const float* dlogvar, float* grads, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* torch.optim.Adam(amsgrad=True) (rnn_vae.py:332,143) over the flat buffers.  lr is read from hyper[0] when hyper is
+ * not NULL.  step_dev: device int32 step counter (incremented here).  scratch: device float[2].
+ * grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). */
+int vame_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
+                   float lr, const float* hyper, int* step_dev, float* scratch, float beta1, float beta2, float eps,
+                   float grad_scale, void* stream);
+
+/* embedd_latent_vectors (vame/analysis/pose_segmentation.py:87-98): mu of every stride-1 window.
+ * series: [n_frames, F] fp32 (frame-major, i.e. the transpose of the reference's (F, N) array);
+ * windows first_window .. first_window + n_windows - 1 (window i covers frames i .. i+T-1) -> mu_out [n_windows, Z]. */
+size_t vame_embed_workspace_bytes(const vame_dims* d, long n_frames, int chunk);
+int vame_embed_windows(const vame_dims* d, const float* params, const void* packed, const float* series, long n_frames,
+                       long first_window, long n_windows, int chunk, float* mu_out, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* standalone sub-module forwards (inference): Encoder.forward (rnn_model.py:40-45) -> hidden [B, 4H];
+ * Lambda.forward (:63-76) ; Decoder.forward / Decoder_Future.forward (:99-109 / :133-144) with the input being the
+ * broadcast of z (rnn_model.py:169-170). */
+int vame_encoder_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* x, long x_bs,
+                         long x_ts, float* hidden, void* ws, size_t ws_bytes, void* stream);
+int vame_lambda_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* hidden,
+                        const float* eps, float* z, float* mu, float* logvar, void* ws, size_t ws_bytes, void* stream);
+int vame_decoder_forward(const vame_dims* d, int batch, int which, const float* params, const void* packed, const float* z,
+                         float* pred, void* ws, size_t ws_bytes, void* stream);
+
+/* measurement hook: re-run the encoder layer-1 forward (which=0) or backward (which=1) sweep on the buffers of the last
+ * vame_forward(save)/vame_backward so that bench.py can time the recurrent step kernels with CUDA events */
+int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* params, const void* packed, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* k-means prior on its own (cluster_loss, rnn_vae.py:45-50): loss_out device double[1], dlatent [B, Z] or NULL */
+int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef,
+                      double* loss_out, float* dlatent, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,43 @@
+"""GPU parity of the drop-in train()/test() epoch functions with the reference's own train()/test()
+(fixture produced by oracle/gen_golden.py: 5 fixed batches, future decoder, StepLR).  Lambda's eps is drawn from the
+RNG in both implementations, so the comparison injects the reference's CPU draws."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_and_test_epoch_match_reference(golden_dir):
+    from vame_b200.rnn_model import RNN_VAE
+    from vame_b200 import rnn_vae as rv
+    g = np.load(os.path.join(golden_dir, "train_fn.npz"))
+    B, T, F, Z, H, fut, S = (int(v) for v in g["cfg"])
+    torch.manual_seed(19)
+    model = RNN_VAE(2 * T, Z, F, True, S, H, H, H, H, 0, 0, 0, False).cuda()
+    batches = [torch.from_numpy(b) for b in g["batches"]]
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, amsgrad=True)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=1)
+    # the reference drew eps with torch.manual_seed(123) then randn_like on CPU, one (B, Z) draw per batch
+    torch.manual_seed(123)
+    draws = [torch.randn(B, Z) for _ in batches]
+    it = iter(draws)
+    orig = torch.randn
+    torch.randn = lambda *a, **k: next(it).to(k.get("device", "cpu")) if tuple(a[:2]) == (B, Z) else orig(*a, **k)
+    try:
+        ret = rv.train(batches, 3, model, opt, "linear", 1, 0, 4, 2 * T, True, S, sched, "sum", "sum", Z, 0.1, B, False)
+    finally:
+        torch.randn = orig
+    ref = g["train_ret"]
+    assert ret[0] == ref[0]
+    for a, b in zip(ret[1:], ref[1:]):
+        assert abs(a - b) <= 2e-4 * max(abs(b), 1e-3), (ret, ref)
+    sd = model.state_dict()
+    for k in sd:
+        err = (sd[k].cpu() - torch.from_numpy(g["w_after/" + k])).abs()
+        assert float((err > 1e-5).float().mean()) <= 1e-3 and float(err.max()) <= 5 * 5e-4 + 1e-6, k
+    ret_t = rv.test(batches, 3, model, opt, 1, ret[0], 2 * T, "sum", Z, 0.1, True, B)
+    for a, b in zip(ret_t, g["test_ret"]):
+        assert abs(float(a) - b) <= 5e-3 * max(abs(b), 1e-3), (ret_t, g["test_ret"])

@@ -14,9 +14,32 @@ c_void_p, c_int, c_long, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.
 SIGNATURES = {
     "vame_last_error": (ctypes.c_char_p, []),
     "vame_abi_version": (c_int, []),
+    "vame_launch_count": (c_long, []),
+    "vame_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "vame_debug_gru_sweep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vame_p16_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vame_pack_p16": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "vame_gemm_p16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p]),
+    "vame_param_tensors": (c_int, [c_void_p]),
+    "vame_param_layout": (c_long, [c_void_p, c_void_p, c_void_p]),
+    "vame_packed_weights_bytes": (c_size_t, [c_void_p]),
+    "vame_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vame_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vame_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_loss": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "vame_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_void_p, c_void_p, c_void_p,
+                               c_float, c_float, c_float, c_float, c_void_p]),
+    "vame_embed_workspace_bytes": (c_size_t, [c_void_p, c_long, c_int]),
+    "vame_embed_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_long, c_long, c_int, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    "vame_encoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_lambda_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "vame_decoder_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_cluster_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -1,0 +1,858 @@
+// Model-level C-ABI: forward / loss / backward / optimizer / embedding of the RNN-VAE, expressed as sequences of
+// kernel launches on the caller's stream.  Host code only: all arithmetic happens in gemm.cu / gru.cu / simt.cu / pack.cu.
+#include "../../include/vame_b200.h"
+#include "api_common.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "model_layout.h"
+#include "simt.h"
+
+namespace vb {
+
+typedef __nv_bfloat16 bf16;
+
+// ================================================================================================
+// workspace
+// ================================================================================================
+struct GruBuf {
+  int steps, H, In;
+  float* gi; long gi_bs, gi_ts, gi_pitch;
+  float* out[2];  int out_slots;        // fp32 h sequence [slots][B_pad][H]; slots = steps (training) or 2 (ping-pong)
+  void* out_p[2]; int out_p_slots;      // P16 h sequence [slots][tiles][nkc]
+  float* sv[2][4];
+  float* h0[2]; void* h0_p[2];          // initial state (zeros for the encoder)
+  float* dgi[2]; float* dgh[2]; void* dgi_p[2];
+  float* parts[2];
+  void* dghT_p[2]; void* dgiT_p[2]; void* outT_p[2]; void* h0T_p[2];
+};
+
+struct DecBuf {
+  GruBuf g;
+  float* hid;        // [B, 2H] latent_to_hidden output (flat buffer aliased as [2][B][H] by the .view quirk)
+  float* pred_tb;    // [steps*B_pad, F]
+  float* dpred_tb;   // [steps*B_pad, F]
+  void* dpred_p;     // P16 [steps*B_pad, K=F]
+  void* dpredT_p;    // P16 [F rows, K = steps*B_pad]
+  float* ddec;       // [steps*B_pad, 2H]
+  float* dgi_sum[2]; // [B_pad, 3H]
+  void* dgi_sum_p[2]; void* dgi_sumT_p[2];
+  float* dhid;       // [B, 2H]
+  void* dhid_p; void* dhidT_p;
+  float* dz;         // [B, Z]
+  float* target_tb;  // [steps*B_pad, F]  (future decoder only; the reconstruction target is x_tb)
+};
+
+struct Ws {
+  int B, B_pad, tiles;
+  float* x_tb; void* x_p; void* xT_p;
+  float* zeros_f32; void* zeros_p; size_t zeros_p_bytes; int Hmax;   // [B_pad][Hmax] fp32 zeros, P16 zero tiles
+  void* hid_p[4];                       // P16 copies of an externally supplied hidden (vame_lambda_forward)
+  GruBuf e0, e1;
+  float* lin;        // [B_pad, 2Z]
+  float* z; float* mu; float* logvar; float* eps;   // [B, Z]
+  void* z_p; void* zT_p;
+  DecBuf dec[2];
+  float* dz_km;      // [B, Z]
+  float* dlin; void* dlin_p; void* dlinT_p;
+  void* hidT_p[4];   // [H rows, K = B_pad] per hidden piece
+  float* dhidden;    // [B_pad, 4H]
+  float* dx1;        // [T*B_pad, 2H]
+  double* acc;       // [8]
+  size_t bytes;
+};
+
+static void carve_gru(Arena& A, GruBuf& g, int steps, int H, int In, int B_pad, bool training, bool per_t_p16, bool gi_full,
+                      bool want_dgi_p, bool want_dgiT, bool own_h0) {
+  const int tiles = B_pad / 128, nkc = nkc_of(H), nkc3 = nkc_of(3 * H);
+  const size_t slotf = (size_t)B_pad * H;
+  const size_t slotp = (size_t)tiles * nkc * p16_tile_bytes(128);
+  const long rows = (long)steps * B_pad;
+  g.steps = steps; g.H = H; g.In = In;
+  if (gi_full) {
+    g.gi = A.f32((size_t)rows * 6 * H);
+    g.gi_bs = 1; g.gi_ts = B_pad; g.gi_pitch = 6 * H;
+  } else {
+    g.gi = A.f32((size_t)B_pad * 6 * H);            // time-invariant input (decoder): one row per sample
+    g.gi_bs = 1; g.gi_ts = 0; g.gi_pitch = 6 * H;
+  }
+  g.out_slots = training ? steps : 2;
+  g.out_p_slots = per_t_p16 ? steps : 2;
+  for (int d = 0; d < 2; ++d) {
+    g.out[d] = A.f32(slotf * g.out_slots);
+    g.out_p[d] = A.raw(slotp * g.out_p_slots);
+    if (own_h0) {
+      g.h0[d] = A.f32(slotf);
+      g.h0_p[d] = A.raw(slotp);
+    }
+    if (training) {
+      for (int i = 0; i < 4; ++i) g.sv[d][i] = A.f32(slotf * steps);
+      g.dgi[d] = A.f32((size_t)rows * 3 * H);
+      g.dgh[d] = A.f32((size_t)rows * 3 * H);
+      g.dgi_p[d] = want_dgi_p ? A.raw((size_t)steps * tiles * nkc3 * p16_tile_bytes(128)) : nullptr;
+      g.parts[d] = A.f32((size_t)2 * (H / 32 + 1) * slotf);
+      g.dghT_p[d] = A.raw(p16_bytes(3 * H, (int)rows, 128));
+      g.dgiT_p[d] = want_dgiT ? A.raw(p16_bytes(3 * H, (int)rows, 128)) : nullptr;
+      g.outT_p[d] = A.raw(p16_bytes(H, (int)rows, 128));
+      g.h0T_p[d] = own_h0 ? A.raw(p16_bytes(H, B_pad, 128)) : nullptr;
+    }
+  }
+}
+
+static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
+  Ws w{};
+  Arena A(base);
+  const int T = d.time_window, F = d.num_features, Z = d.zdims, H = d.hidden_enc;
+  w.B = B; w.B_pad = pad128(B); w.tiles = w.B_pad / 128;
+  const int Bp = w.B_pad;
+  const long rows = (long)T * Bp;
+  int Hmax = H;
+  if (d.hidden_rec > Hmax) Hmax = d.hidden_rec;
+  if (d.future_decoder && d.hidden_pred > Hmax) Hmax = d.hidden_pred;
+  w.x_tb = A.f32((size_t)rows * F);
+  w.x_p = A.raw(p16_bytes((int)rows, F, 128));
+  w.xT_p = training ? A.raw(p16_bytes(F, (int)rows, 128)) : nullptr;
+  w.zeros_f32 = A.f32((size_t)Bp * Hmax);
+  {
+    size_t zp = (size_t)w.tiles * nkc_of(Hmax) * p16_tile_bytes(128);
+    size_t zt = p16_bytes(Hmax, Bp, 128);                 // also used as the transposed h0 (= 0) of the encoder
+    w.zeros_p_bytes = zp > zt ? zp : zt;
+    w.zeros_p = A.raw(w.zeros_p_bytes);
+    w.Hmax = Hmax;
+  }
+  for (int i = 0; i < 4; ++i) w.hid_p[i] = A.raw(p16_bytes(Bp, H, 128));
+  carve_gru(A, w.e0, T, H, F, Bp, training, /*per_t_p16=*/true, /*gi_full=*/true, /*dgi_p=*/false, /*dgiT=*/true, /*own_h0=*/false);
+  carve_gru(A, w.e1, T, H, 2 * H, Bp, training, false, true, /*dgi_p=*/true, /*dgiT=*/true, false);
+  w.lin = A.f32((size_t)Bp * 2 * Z);
+  w.z = A.f32((size_t)B * Z); w.mu = A.f32((size_t)B * Z); w.logvar = A.f32((size_t)B * Z); w.eps = A.f32((size_t)B * Z);
+  w.z_p = A.raw(p16_bytes(Bp, Z, 128));
+  w.zT_p = training ? A.raw(p16_bytes(Z, Bp, 128)) : nullptr;
+  for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
+    DecBuf& D = w.dec[i];
+    const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
+    const int steps = i == 0 ? T : d.future_steps;
+    const long r = (long)steps * Bp;
+    carve_gru(A, D.g, steps, Hd, Z, Bp, training, true, /*gi_full=*/false, false, false, /*own_h0=*/true);
+    D.hid = A.f32((size_t)B * 2 * Hd);
+    D.pred_tb = A.f32((size_t)r * F);
+    D.target_tb = i == 1 ? A.f32((size_t)r * F) : nullptr;
+    if (training) {
+      D.dpred_tb = A.f32((size_t)r * F);
+      D.dpred_p = A.raw(p16_bytes((int)r, F, 128));
+      D.dpredT_p = A.raw(p16_bytes(F, (int)r, 128));
+      D.ddec = A.f32((size_t)r * 2 * Hd);
+      for (int dd = 0; dd < 2; ++dd) {
+        D.dgi_sum[dd] = A.f32((size_t)Bp * 3 * Hd);
+        D.dgi_sum_p[dd] = A.raw(p16_bytes(Bp, 3 * Hd, 128));
+        D.dgi_sumT_p[dd] = A.raw(p16_bytes(3 * Hd, Bp, 128));
+      }
+      D.dhid = A.f32((size_t)B * 2 * Hd);
+      D.dhid_p = A.raw(p16_bytes(Bp, 2 * Hd, 128));
+      D.dhidT_p = A.raw(p16_bytes(2 * Hd, Bp, 128));
+      D.dz = A.f32((size_t)B * Z);
+    }
+  }
+  if (training) {
+    w.dz_km = A.f32((size_t)B * Z);
+    w.dlin = A.f32((size_t)Bp * 2 * Z);
+    w.dlin_p = A.raw(p16_bytes(Bp, 2 * Z, 128));
+    w.dlinT_p = A.raw(p16_bytes(2 * Z, Bp, 128));
+    for (int i = 0; i < 4; ++i) w.hidT_p[i] = A.raw(p16_bytes(H, Bp, 128));
+    w.dhidden = A.f32((size_t)Bp * 4 * H);
+    w.dx1 = A.f32((size_t)rows * 2 * H);
+  }
+  w.acc = (double*)A.raw(8 * sizeof(double));
+  w.bytes = (A.off + 1023) & ~(size_t)1023;
+  return w;
+}
+
+// ================================================================================================
+// small host helpers
+// ================================================================================================
+static inline GemmSeg seg(const void* p, long rb_stride, int nkc) { return GemmSeg{p, rb_stride, nkc}; }
+
+struct GemmB {
+  GemmArgs g{};
+  int na = 0, nb = 0;
+  GemmB& A(const void* p, long rbs, int nkc) { g.a[na++] = seg(p, rbs, nkc); return *this; }
+  GemmB& Bm(const void* p, long rbs, int nkc) { g.b[nb++] = seg(p, rbs, nkc); return *this; }
+  void run(int M, int N, float* C, long ldc, const float* bias, int atomic, int splits, cudaStream_t st) {
+    g.M = M; g.N = N; g.C = C; g.ldc = ldc; g.bias = bias; g.atomic = atomic; g.splits = splits;
+    launch_gemm_p16(g, st);
+  }
+};
+// plain (non-transposed) pack of a row-major [R_src, K] matrix into P16 with R rows (zero padded)
+static inline void pack_rows(const float* src, long ld, int R, int K, int R_src, void* out, cudaStream_t st) {
+  launch_pack_p16(src, ld, 0, R, K, R_src, K, nullptr, nullptr, 128, out, st);
+}
+// transposed pack: source [K_src rows, R cols] row-major -> P16 [R rows, K] with K = padded K_src
+static inline void pack_T(const float* src, long ld, int R, int K, int K_src, void* out, cudaStream_t st) {
+  launch_pack_p16(src, ld, 1, R, K, R, K_src, nullptr, nullptr, 128, out, st);
+}
+static inline int splits_for(int M, int N, int nkc) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int s = 148 / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > nkc) s = nkc;
+  if (s > 32) s = 32;
+  return s;
+}
+
+// ================================================================================================
+// weights
+// ================================================================================================
+static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, cudaStream_t st) {
+  const int H = o.H, In = o.In;
+  for (int d = 0; d < 2; ++d) {
+    launch_pack_whh(P + o.whh[d], H, 0, W.whh_p[d], st);
+    launch_pack_whh(P + o.whh[d], H, 1, W.whhT_p[d], st);
+    pack_T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d], st);           // [In rows, K = 3H]
+  }
+  // both directions' W_ih are adjacent in the flat buffer -> one [6H, In] matrix; K split in wih_nseg column blocks
+  const int Ks = In / W.wih_nseg;
+  for (int s = 0; s < W.wih_nseg; ++s) pack_rows(P + o.wih[0] + (long)s * Ks, In, 6 * H, Ks, 6 * H, W.wih_p[s], st);
+  launch_bias_fuse(P + o.bih[0], P + o.bhh[0], P + o.bih[1], P + o.bhh[1], H, W.bias_gi, st);
+}
+
+static void pack_all_weights(const vame_dims& d, const float* P, const PackedWeights& W, cudaStream_t st) {
+  const ParamLayout L = param_layout(d);
+  const int H = d.hidden_enc, F = d.num_features, Z = d.zdims;
+  pack_gru_weights(P, L.e0, W.e0, st);
+  pack_gru_weights(P, L.e1, W.e1, st);
+  for (int i = 0; i < 4; ++i) pack_rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i], st);
+  pack_T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p, st);
+  for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
+    const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
+    pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, st);
+    pack_rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i], st);
+    pack_T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i], st);
+    for (int dd = 0; dd < 2; ++dd) pack_rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd], st);
+    pack_T(P + L.h2o_w[i], 2 * Hd, 2 * Hd, F, F, W.h2oT_p[i], st);
+  }
+}
+
+// ================================================================================================
+// GRU sweeps
+// ================================================================================================
+// The step kernels write only the valid k-range of their P16 outputs; when the range does not fill whole 64-wide chunks
+// (H or 3H not a multiple of 64) the padding must be zero because the generic GEMM always consumes full chunks.
+static void zero_p16_padding(GruBuf& L, int tiles, bool fwd, cudaStream_t st) {
+  const int H = L.H;
+  if (fwd && (H % KCHUNK) != 0) {
+    const size_t slotp = (size_t)tiles * nkc_of(H) * p16_tile_bytes(128);
+    for (int d = 0; d < 2; ++d) cudaMemsetAsync(L.out_p[d], 0, slotp * L.out_p_slots, st);
+  }
+  if (!fwd && ((3 * H) % KCHUNK) != 0) {
+    for (int d = 0; d < 2; ++d)
+      if (L.dgi_p[d]) cudaMemsetAsync(L.dgi_p[d], 0, (size_t)L.steps * tiles * nkc_of(3 * H) * p16_tile_bytes(128), st);
+  }
+}
+
+static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b_hn1, GruBuf& L, int tiles, bool save, bool pdl,
+                          cudaStream_t st) {
+  const int H = L.H;
+  zero_p16_padding(L, tiles, true, st);
+  const size_t slotf = (size_t)tiles * 128 * H;
+  const size_t slotp = (size_t)tiles * nkc_of(H) * p16_tile_elems(128);
+  for (int s = 0; s < L.steps; ++s) {
+    GruFwdArgs a{};
+    a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
+    for (int d = 0; d < 2; ++d) {
+      const int t = d == 0 ? s : L.steps - 1 - s;
+      const int tprev = d == 0 ? t - 1 : t + 1;
+      GruDirFwd& D = a.d[d];
+      D.w_p = W.whh_p[d];
+      D.b_hn = d == 0 ? b_hn0 : b_hn1;
+      D.gi = L.gi + (size_t)d * 3 * H;
+      D.gi_bs = L.gi_bs; D.gi_ts = L.gi_ts; D.gi_pitch = L.gi_pitch; D.t = t;
+      const int so = (L.out_slots == L.steps) ? t : (s & 1), so_prev = (L.out_slots == L.steps) ? tprev : ((s - 1) & 1);
+      const int sp = (L.out_p_slots == L.steps) ? t : (s & 1), sp_prev = (L.out_p_slots == L.steps) ? tprev : ((s - 1) & 1);
+      D.h_in = s == 0 ? L.h0[d] : L.out[d] + so_prev * slotf;
+      D.h_in_p = s == 0 ? L.h0_p[d] : (void*)((bf16*)L.out_p[d] + sp_prev * slotp);
+      D.h_out = L.out[d] + so * slotf;
+      D.h_out_p = (bf16*)L.out_p[d] + sp * slotp;
+      if (save) {
+        D.sv_r = L.sv[d][0] + t * slotf; D.sv_z = L.sv[d][1] + t * slotf;
+        D.sv_n = L.sv[d][2] + t * slotf; D.sv_ghn = L.sv[d][3] + t * slotf;
+      }
+    }
+    launch_gru_step_fwd(a, st);
+  }
+}
+// location of the final hidden state of direction d after a forward sweep
+static inline const float* final_h(const GruBuf& L, int d, int tiles) {
+  const size_t slotf = (size_t)tiles * 128 * L.H;
+  const int t = d == 0 ? L.steps - 1 : 0;
+  const int so = (L.out_slots == L.steps) ? t : ((L.steps - 1) & 1);
+  return L.out[d] + so * slotf;
+}
+static inline const void* final_h_p(const GruBuf& L, int d, int tiles) {
+  const size_t slotp = (size_t)tiles * nkc_of(L.H) * p16_tile_elems(128);
+  const int t = d == 0 ? L.steps - 1 : 0;
+  const int sp = (L.out_p_slots == L.steps) ? t : ((L.steps - 1) & 1);
+  return (bf16*)L.out_p[d] + sp * slotp;
+}
+
+static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float* dout0, const float* dout1, long dout_pitch,
+                          long dout_tstride, const float* dhl0, const float* dhl1, long dhl_pitch, bool pdl, cudaStream_t st) {
+  const int H = L.H, nsl = H / 32, nkc3 = nkc_of(3 * H);
+  const long Bp = (long)tiles * 128;
+  const size_t slotf = (size_t)Bp * H;
+  const size_t pslot = (size_t)(nsl + 1) * slotf;
+  zero_p16_padding(L, tiles, false, st);
+  for (int s = 0; s < L.steps; ++s) {
+    GruBwdArgs a{};
+    a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
+    for (int d = 0; d < 2; ++d) {
+      const int t = d == 0 ? L.steps - 1 - s : s;           // reverse of the forward order
+      const bool first_fwd = d == 0 ? (t == 0) : (t == L.steps - 1);
+      const int tprev = d == 0 ? t - 1 : t + 1;
+      GruDirBwd& D = a.d[d];
+      D.wT_p = W.whhT_p[d];
+      const float* dhl = d == 0 ? dhl0 : dhl1;
+      if (s == 0) {
+        D.parts = dhl; D.n_parts = dhl ? 1 : 0; D.parts_stride = 0; D.parts_pitch = dhl_pitch;
+      } else {
+        D.parts = L.parts[d] + ((s - 1) & 1) * pslot; D.n_parts = nsl + 1; D.parts_stride = (long)slotf; D.parts_pitch = H;
+      }
+      const float* dout = d == 0 ? dout0 : dout1;
+      D.dout = dout ? dout + (long)t * dout_tstride : nullptr;
+      D.dout_pitch = dout_pitch;
+      D.sv_r = L.sv[d][0] + t * slotf; D.sv_z = L.sv[d][1] + t * slotf;
+      D.sv_n = L.sv[d][2] + t * slotf; D.sv_ghn = L.sv[d][3] + t * slotf;
+      D.h_prev = first_fwd ? L.h0[d] : L.out[d] + tprev * slotf;
+      D.parts_out = L.parts[d] + (s & 1) * pslot;
+      D.dgi = L.dgi[d] + (size_t)t * Bp * 3 * H;
+      D.dgh = L.dgh[d] + (size_t)t * Bp * 3 * H;
+      D.dgi_p = L.dgi_p[d] ? (void*)((bf16*)L.dgi_p[d] + (size_t)t * tiles * nkc3 * p16_tile_elems(128)) : nullptr;
+    }
+    launch_gru_step_bwd(a, st);
+  }
+}
+static inline const float* final_parts(const GruBuf& L, int d, int tiles) {
+  const size_t pslot = (size_t)(L.H / 32 + 1) * tiles * 128 * L.H;
+  return L.parts[d] + ((L.steps - 1) & 1) * pslot;
+}
+
+// weight / bias gradients of the recurrent part of one bi-GRU layer after its backward sweep:
+//   dW_hh[d] = dgh[d]^T hprev[d],  db_hh[d] = colsum(dgh[d]),  db_ih[d] = colsum(dgi[d])
+static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st) {
+  const int H = L.H;
+  const long rows = (long)L.steps * Bp;
+  const int cB = Bp / KCHUNK, nk = (int)(rows / KCHUNK);
+  for (int d = 0; d < 2; ++d) {
+    pack_T(L.dgh[d], 3 * H, 3 * H, (int)rows, (int)rows, L.dghT_p[d], st);
+    pack_T(L.out[d], H, H, (int)rows, (int)rows, L.outT_p[d], st);
+    const void* h0T = d == 0 ? h0T0 : h0T1;
+    GemmB gb;
+    gb.A(L.dghT_p[d], nk, nk);
+    const bf16* oT = (const bf16*)L.outT_p[d];
+    if (d == 0) {                                   // hprev(t) = out(t-1), hprev(0) = h0
+      gb.Bm(h0T, cB, cB);
+      if (nk > cB) gb.Bm(oT, nk, nk - cB);
+    } else {                                        // hprev(t) = out(t+1), hprev(T-1) = h0
+      if (nk > cB) gb.Bm(oT + (size_t)cB * p16_tile_elems(128), nk, nk - cB);
+      gb.Bm(h0T, cB, cB);
+    }
+    gb.run(3 * H, H, G + o.whh[d], H, nullptr, 1, splits_for(3 * H, H, nk), st);
+    launch_colsum(L.dgh[d], 3 * H, rows, 3 * H, G + o.bhh[d], st);
+    launch_colsum(L.dgi[d], 3 * H, rows, 3 * H, G + o.bih[d], st);
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+static void encoder_forward(const vame_dims& d, const float* P, const ParamLayout& L, const PackedWeights& W, Ws& w, const float* x,
+                            long x_bs, long x_ts, bool save, cudaStream_t st) {
+  const int T = d.time_window, F = d.num_features, H = d.hidden_enc, Bp = w.B_pad;
+  const int rows = T * Bp, nkcH = nkc_of(H);
+  cudaMemsetAsync(w.zeros_f32, 0, (size_t)Bp * w.Hmax * 4, st);
+  cudaMemsetAsync(w.zeros_p, 0, w.zeros_p_bytes, st);
+  for (int dd = 0; dd < 2; ++dd) {
+    w.e0.h0[dd] = w.zeros_f32; w.e0.h0_p[dd] = w.zeros_p;
+    w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
+  }
+  launch_bt_to_tb(x, w.B, T, F, x_bs, x_ts, Bp, w.x_tb, st);
+  pack_rows(w.x_tb, F, rows, F, rows, w.x_p, st);
+  // layer 0: gi = x W_ih^T + (b_ih + [b_hr, b_hz, 0]) for both directions at once
+  GemmB().A(w.x_p, nkc_of(F), nkc_of(F)).Bm(W.e0.wih_p[0], nkc_of(F), nkc_of(F))
+      .run(rows, 6 * H, w.e0.gi, 6 * H, W.e0.bias_gi, 0, 1, st);
+  gru_sweep_fwd(W.e0, P + L.e0.bhh[0] + 2 * H, P + L.e0.bhh[1] + 2 * H, w.e0, w.tiles, save, true, st);
+  // layer 1: input = [out_f(t), out_b(t)] (rnn_model.py:41, inter-layer dropout is 0 by default)
+  GemmB().A(w.e0.out_p[0], nkcH, nkcH).A(w.e0.out_p[1], nkcH, nkcH)
+      .Bm(W.e1.wih_p[0], nkcH, nkcH).Bm(W.e1.wih_p[1], nkcH, nkcH)
+      .run(rows, 6 * H, w.e1.gi, 6 * H, W.e1.bias_gi, 0, 1, st);
+  gru_sweep_fwd(W.e1, P + L.e1.bhh[0] + 2 * H, P + L.e1.bhh[1] + 2 * H, w.e1, w.tiles, save, true, st);
+}
+
+// mu/logvar linear on hidden = cat(h_n[0..3]) (rnn_model.py:43,65-69); hidden pieces given as P16 [tiles][nkc]
+static void lambda_linear(const vame_dims& d, const float* P, const ParamLayout& L, const PackedWeights& W, Ws& w, const void* hp[4],
+                          cudaStream_t st) {
+  const int H = d.hidden_enc, Z = d.zdims, nkcH = nkc_of(H);
+  GemmB gb;
+  for (int i = 0; i < 4; ++i) gb.A(hp[i], nkcH, nkcH);
+  for (int i = 0; i < 4; ++i) gb.Bm(W.lam_p[i], nkcH, nkcH);
+  gb.run(w.B, 2 * Z, w.lin, 2 * Z, P + L.lam_b, 0, 1, st);
+}
+
+static void decoder_forward(const vame_dims& d, int which, const float* P, const ParamLayout& L, const PackedWeights& W, Ws& w,
+                            bool save, cudaStream_t st) {
+  const int F = d.num_features, Z = d.zdims, Bp = w.B_pad;
+  const int Hd = which == 0 ? d.hidden_rec : d.hidden_pred;
+  const GruOff& o = which == 0 ? L.dec : L.fut;
+  const GruPacked& Wg = which == 0 ? W.dec : W.fut;
+  DecBuf& D = w.dec[which];
+  const int steps = D.g.steps, nkcZ = nkc_of(Z), nkcH = nkc_of(Hd);
+  // hidden = latent_to_hidden(z); h0 = hidden.view(2, B, H)  (raw reinterpretation, rnn_model.py:102-104)
+  GemmB().A(w.z_p, nkcZ, nkcZ).Bm(W.l2h_p[which], nkcZ, nkcZ).run(w.B, 2 * Hd, D.hid, 2 * Hd, P + L.l2h_b[which], 0, 1, st);
+  for (int dd = 0; dd < 2; ++dd)
+    launch_h0_prepare(D.hid + (size_t)dd * w.B * Hd, 1, w.B, Bp, Hd, D.g.h0[dd], D.g.h0_p[dd], st);
+  // the decoder input is z at every time step (rnn_model.py:169-170): one projection per sample
+  GemmB().A(w.z_p, nkcZ, nkcZ).Bm(Wg.wih_p[0], nkcZ, nkcZ).run(Bp, 6 * Hd, D.g.gi, 6 * Hd, Wg.bias_gi, 0, 1, st);
+  gru_sweep_fwd(Wg, P + o.bhh[0] + 2 * Hd, P + o.bhh[1] + 2 * Hd, D.g, w.tiles, save, true, st);
+  // prediction = hidden_to_output([out_f, out_b])
+  GemmB().A(D.g.out_p[0], nkcH, nkcH).A(D.g.out_p[1], nkcH, nkcH).Bm(W.h2o_p[which][0], nkcH, nkcH).Bm(W.h2o_p[which][1], nkcH, nkcH)
+      .run(steps * Bp, F, D.pred_tb, F, P + L.h2o_b[which], 0, 1, st);
+}
+
+static int check_dims(const vame_dims* d) {
+  VB_REQUIRE(d, "null dims");
+  VB_REQUIRE(d->num_features > 0 && d->time_window > 0 && d->zdims > 0 && d->zdims <= 64, "dims: need F>0, T>0, 0<Z<=64");
+  VB_REQUIRE(d->hidden_enc % 32 == 0 && d->hidden_enc >= 32 && d->hidden_enc <= 256, "dims: hidden_enc must be a multiple of 32 in [32,256]");
+  VB_REQUIRE(d->hidden_rec % 32 == 0 && d->hidden_rec >= 32 && d->hidden_rec <= 256, "dims: hidden_rec must be a multiple of 32 in [32,256]");
+  if (d->future_decoder) {
+    VB_REQUIRE(d->hidden_pred % 32 == 0 && d->hidden_pred >= 32 && d->hidden_pred <= 256, "dims: hidden_pred must be a multiple of 32 in [32,256]");
+    VB_REQUIRE(d->future_steps > 0 && d->future_steps <= d->time_window, "dims: need 0 < future_steps <= time_window");
+  }
+  return 0;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vame_param_tensors(const vame_dims* d) { return d && d->future_decoder ? 44 : 32; }
+
+long vame_param_layout(const vame_dims* d, long* offsets, long* sizes) {
+  if (check_dims(d)) return -1;
+  const ParamLayout L = param_layout(*d);
+  if (offsets && sizes) {
+    int n = 0;
+    auto gru = [&](const GruOff& g) {
+      for (int dir = 0; dir < 2; ++dir) {      // state_dict order: w_ih, w_hh, b_ih, b_hh, then the *_reverse four
+        offsets[n] = g.wih[dir]; sizes[n++] = 3L * g.H * g.In;
+        offsets[n] = g.whh[dir]; sizes[n++] = 3L * g.H * g.H;
+        offsets[n] = g.bih[dir]; sizes[n++] = 3L * g.H;
+        offsets[n] = g.bhh[dir]; sizes[n++] = 3L * g.H;
+      }
+    };
+    const int H = d->hidden_enc, Z = d->zdims, F = d->num_features;
+    // encoder.encoder_rnn: l0, l0_reverse, l1, l1_reverse
+    gru(L.e0);
+    gru(L.e1);
+    offsets[n] = L.lam_w; sizes[n++] = (long)Z * 4 * H;                       // hidden_to_mean.weight
+    offsets[n] = L.lam_b; sizes[n++] = Z;                                     // hidden_to_mean.bias
+    offsets[n] = L.lam_w + (long)Z * 4 * H; sizes[n++] = (long)Z * 4 * H;     // hidden_to_logvar.weight
+    offsets[n] = L.lam_b + Z; sizes[n++] = Z;                                 // hidden_to_logvar.bias
+    for (int i = 0; i < (d->future_decoder ? 2 : 1); ++i) {
+      const int Hd = i == 0 ? d->hidden_rec : d->hidden_pred;
+      gru(i == 0 ? L.dec : L.fut);
+      offsets[n] = L.l2h_w[i]; sizes[n++] = 2L * Hd * Z;
+      offsets[n] = L.l2h_b[i]; sizes[n++] = 2L * Hd;
+      offsets[n] = L.h2o_w[i]; sizes[n++] = (long)F * 2 * Hd;
+      offsets[n] = L.h2o_b[i]; sizes[n++] = F;
+    }
+  }
+  return L.total;
+}
+
+size_t vame_packed_weights_bytes(const vame_dims* d) {
+  if (check_dims(d)) return 0;
+  return packed_layout(*d, nullptr).bytes;
+}
+
+int vame_pack_weights(const vame_dims* d, const float* params, void* packed, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(params && packed, "vame_pack_weights: null pointer");
+  pack_all_weights(*d, params, packed_layout(*d, packed), (cudaStream_t)stream);
+  return check_launch("vame_pack_weights");
+}
+
+size_t vame_workspace_bytes(const vame_dims* d, int batch, int training) {
+  if (check_dims(d) || batch <= 0) return 0;
+  return carve_ws(*d, batch, training != 0, nullptr).bytes;
+}
+
+int vame_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* x, long x_bs, long x_ts,
+                 const float* eps, int save_for_backward, float* pred, float* future, float* z, float* mu, float* logvar, void* ws,
+                 size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && x && ws, "vame_forward: null pointer / empty batch");
+  const bool save = save_for_backward != 0;
+  Ws w = carve_ws(*d, batch, save, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_forward: workspace too small (see vame_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int T = d->time_window, F = d->num_features, Z = d->zdims;
+  cudaMemsetAsync(w.acc, 0, 8 * sizeof(double), st);
+  encoder_forward(*d, params, L, W, w, x, x_bs, x_ts, save, st);
+  const void* hp[4] = {final_h_p(w.e0, 0, w.tiles), final_h_p(w.e0, 1, w.tiles), final_h_p(w.e1, 0, w.tiles), final_h_p(w.e1, 1, w.tiles)};
+  lambda_linear(*d, params, L, W, w, hp, st);
+  if (eps) cudaMemcpyAsync(w.eps, eps, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
+  launch_lambda_fwd(w.lin, 2 * Z, eps ? w.eps : nullptr, batch, Z, d->softplus, w.z, w.mu, w.logvar, w.acc, st);
+  pack_rows(w.z, Z, w.B_pad, Z, batch, w.z_p, st);
+  decoder_forward(*d, 0, params, L, W, w, save, st);
+  if (d->future_decoder) decoder_forward(*d, 1, params, L, W, w, save, st);
+  if (pred) launch_tb_to_bt(w.dec[0].pred_tb, batch, T, F, w.B_pad, pred, st);
+  if (future && d->future_decoder) launch_tb_to_bt(w.dec[1].pred_tb, batch, d->future_steps, F, w.B_pad, future, st);
+  if (z) cudaMemcpyAsync(z, w.z, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
+  if (mu) cudaMemcpyAsync(mu, w.mu, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
+  if (logvar) cudaMemcpyAsync(logvar, w.logvar, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
+  // remember whether eps was given (backward needs it): all-ones / all-zero bytes in acc[7]
+  cudaMemsetAsync(w.acc + 7, eps ? 0xFF : 0, sizeof(double), st);
+  return check_launch("vame_forward");
+}
+
+int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts, const float* hyper,
+              float* losses_out, int want_grads, void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(cfg && ws && losses_out && batch > 0, "vame_loss: null pointer");
+  const bool training = want_grads != 0;
+  Ws w = carve_ws(*d, batch, training, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_loss: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = d->time_window, F = d->num_features, Z = d->zdims, Bp = w.B_pad;
+  const bool with_fut = d->future_decoder && cfg->with_future;
+  VB_REQUIRE(!with_fut || fut, "vame_loss: future target missing");
+  const double nrec = (double)batch * T * F;
+  launch_mse(w.dec[0].pred_tb, F, w.x_tb, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
+             training ? w.dec[0].dpred_tb : nullptr, w.acc, ACC_REC, st);
+  double nfut = 1.0;
+  if (with_fut) {
+    const int S = d->future_steps;
+    nfut = (double)batch * S * F;
+    launch_bt_to_tb(fut, batch, S, F, f_bs, f_ts, Bp, w.dec[1].target_tb, st);
+    launch_mse(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f,
+               training ? w.dec[1].dpred_tb : nullptr, w.acc, ACC_FUT, st);
+  }
+  launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
+                       training ? w.dz_km : nullptr, w.acc, st);
+  launch_finalize_losses(w.acc, losses_out, cfg->mse_red_mean ? nrec : 1.0, cfg->mse_pred_mean ? nfut : 1.0, (double)batch * Z,
+                         cfg->beta, cfg->kl_weight, hyper, with_fut ? 1 : 0, st);
+  return check_launch("vame_loss");
+}
+
+int vame_backward(const vame_dims* d, int batch, const float* params, const void* packed, int use_loss_grads, const vame_loss_cfg* cfg,
+                  const float* hyper, const float* dpred, const float* dfuture, const float* dz_ext, const float* dmu_ext,
+                  const float* dlv_ext, float* grads, void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && grads && ws, "vame_backward: null pointer");
+  VB_REQUIRE(!use_loss_grads || cfg, "vame_backward: cfg required with use_loss_grads");
+  Ws w = carve_ws(*d, batch, true, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_backward: workspace too small (forward must have used save_for_backward)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc, Bp = w.B_pad, B = batch;
+  const int nkcB = Bp / KCHUNK;
+  float* G = grads;
+  cudaMemsetAsync(G, 0, (size_t)L.total * 4, st);
+  for (int dd = 0; dd < 2; ++dd) {           // encoder buffers alias the zero regions (not stored in the workspace)
+    w.e0.h0[dd] = w.zeros_f32; w.e0.h0_p[dd] = w.zeros_p;
+    w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
+  }
+  pack_T(w.z, Z, Z, Bp, B, w.zT_p, st);                                   // [Z rows, K = B_pad]
+
+  const int ndec = d->future_decoder ? 2 : 1;
+  const float* dz_dec[2] = {nullptr, nullptr};
+  for (int i = 0; i < ndec; ++i) {
+    DecBuf& D = w.dec[i];
+    const float* ext = i == 0 ? dpred : dfuture;
+    const bool have_grad = use_loss_grads ? (i == 0 || cfg->with_future) : (ext != nullptr);
+    if (!have_grad) continue;                                             // this decoder received no gradient
+    const int Hd = D.g.H, steps = D.g.steps;
+    const long rows = (long)steps * Bp;
+    const int nk = (int)(rows / KCHUNK), nkcF = nkc_of(F), nkc3 = nkc_of(3 * Hd), nkc2H = nkc_of(2 * Hd);
+    const GruOff& o = i == 0 ? L.dec : L.fut;
+    const GruPacked& Wg = i == 0 ? W.dec : W.fut;
+    if (!use_loss_grads) launch_bt_to_tb(ext, B, steps, F, (long)steps * F, F, Bp, D.dpred_tb, st);
+    // hidden_to_output backward
+    pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, st);
+    GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run((int)rows, 2 * Hd, D.ddec, 2 * Hd, nullptr, 0, 1, st);
+    pack_T(D.dpred_tb, F, F, (int)rows, (int)rows, D.dpredT_p, st);
+    launch_colsum(D.dpred_tb, F, rows, F, G + L.h2o_b[i], st);
+    // BPTT
+    gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + Hd, 2 * Hd, (long)Bp * 2 * Hd, nullptr, nullptr, 0, true, st);
+    for (int dd = 0; dd < 2; ++dd) pack_T(D.g.h0[dd], Hd, Hd, Bp, Bp, D.g.h0T_p[dd], st);
+    gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, st);       // also fills outT_p
+    for (int dd = 0; dd < 2; ++dd)                                        // dW_out[:, dd*H:(dd+1)*H] = dpred^T out_dd
+      GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
+          .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), st);
+    // input projection: the input is z at every step -> reduce dgi over time first
+    for (int dd = 0; dd < 2; ++dd) {
+      launch_timesum(D.g.dgi[dd], steps, (long)Bp * 3 * Hd, D.dgi_sum[dd], st);
+      pack_rows(D.dgi_sum[dd], 3 * Hd, Bp, 3 * Hd, Bp, D.dgi_sum_p[dd], st);
+      pack_T(D.dgi_sum[dd], 3 * Hd, 3 * Hd, Bp, Bp, D.dgi_sumT_p[dd], st);
+      GemmB().A(D.dgi_sumT_p[dd], nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB)
+          .run(3 * Hd, Z, G + o.wih[dd], Z, nullptr, 1, splits_for(3 * Hd, Z, nkcB), st);
+    }
+    GemmB().A(D.dgi_sum_p[0], nkc3, nkc3).A(D.dgi_sum_p[1], nkc3, nkc3).Bm(Wg.wihT_p[0], nkc3, nkc3).Bm(Wg.wihT_p[1], nkc3, nkc3)
+        .run(B, Z, D.dz, Z, nullptr, 0, 1, st);
+    // latent_to_hidden backward through the inverse of the .view(2,B,H) quirk
+    launch_parts_reduce(final_parts(D.g, 0, w.tiles), Hd / 32 + 1, (long)(final_parts(D.g, 1, w.tiles) - final_parts(D.g, 0, w.tiles)), 2, B,
+                        Bp, Hd, D.dhid, 1, st);
+    pack_rows(D.dhid, 2 * Hd, Bp, 2 * Hd, B, D.dhid_p, st);
+    pack_T(D.dhid, 2 * Hd, 2 * Hd, Bp, B, D.dhidT_p, st);
+    GemmB().A(D.dhidT_p, nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB).run(2 * Hd, Z, G + L.l2h_w[i], Z, nullptr, 1, splits_for(2 * Hd, Z, nkcB), st);
+    launch_colsum(D.dhid, 2 * Hd, B, 2 * Hd, G + L.l2h_b[i], st);
+    GemmB().A(D.dhid_p, nkc2H, nkc2H).Bm(W.l2hT_p[i], nkc2H, nkc2H).run(B, Z, D.dz, Z, nullptr, 1, 1, st);
+    dz_dec[i] = D.dz;
+  }
+
+  // Lambda backward
+  {
+    LambdaBwdArgs a{};
+    a.dz[0] = use_loss_grads ? w.dz_km : nullptr;
+    a.dz[1] = dz_dec[0]; a.dz[2] = dz_dec[1];
+    a.dz[3] = use_loss_grads ? nullptr : dz_ext;
+    a.dmu_ext = use_loss_grads ? nullptr : dmu_ext;
+    a.dlv_ext = use_loss_grads ? nullptr : dlv_ext;
+    a.mu = w.mu; a.logvar = w.logvar; a.eps = w.eps; a.use_eps_flag = reinterpret_cast<const long long*>(w.acc + 7);
+    a.lin = w.lin; a.ldl = 2 * Z;
+    a.hyper = use_loss_grads ? hyper : nullptr;
+    a.c_kl = use_loss_grads ? cfg->beta * cfg->kl_weight / (float)((long)B * Z) : 0.f;
+    a.B = B; a.B_pad = Bp; a.Z = Z; a.softplus = d->softplus;
+    a.dlin = w.dlin; a.ldd = 2 * Z;
+    launch_lambda_bwd(a, st);
+  }
+  const int nkc2Z = nkc_of(2 * Z), nkcH = nkc_of(H);
+  pack_rows(w.dlin, 2 * Z, Bp, 2 * Z, Bp, w.dlin_p, st);
+  pack_T(w.dlin, 2 * Z, 2 * Z, Bp, Bp, w.dlinT_p, st);
+  launch_colsum(w.dlin, 2 * Z, Bp, 2 * Z, G + L.lam_b, st);
+  {
+    const float* hf[4] = {final_h(w.e0, 0, w.tiles), final_h(w.e0, 1, w.tiles), final_h(w.e1, 0, w.tiles), final_h(w.e1, 1, w.tiles)};
+    for (int i = 0; i < 4; ++i) {
+      pack_T(hf[i], H, H, Bp, Bp, w.hidT_p[i], st);
+      GemmB().A(w.dlinT_p, nkcB, nkcB).Bm(w.hidT_p[i], nkcB, nkcB)
+          .run(2 * Z, H, G + L.lam_w + (long)i * H, 4 * H, nullptr, 1, splits_for(2 * Z, H, nkcB), st);
+    }
+  }
+  GemmB().A(w.dlin_p, nkc2Z, nkc2Z).Bm(W.lamT_p, nkc2Z, nkc2Z).run(Bp, 4 * H, w.dhidden, 4 * H, nullptr, 0, 1, st);
+
+  // encoder layer 1 (only h_n is used downstream, rnn_model.py:41-43: no per-step output gradient)
+  const long rows = (long)T * Bp;
+  const int nk = (int)(rows / KCHUNK), nkc3 = nkc_of(3 * H);
+  gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, 0, w.dhidden + 2 * H, w.dhidden + 3 * H, 4 * H, true, st);
+  // layer-0 outputs transposed once: hprev of layer 0 and the input of layer 1
+  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, st);
+  GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
+      .run((int)rows, 2 * H, w.dx1, 2 * H, nullptr, 0, 1, st);
+  // encoder layer 0
+  gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + H, 2 * H, (long)Bp * 2 * H, w.dhidden, w.dhidden + H, 4 * H, true, st);
+  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, st);      // fills e0.outT_p
+  pack_T(w.x_tb, F, F, (int)rows, (int)rows, w.xT_p, st);
+  for (int dd = 0; dd < 2; ++dd) {
+    // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
+    pack_T(w.e1.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e1.dgiT_p[dd], st);
+    for (int e = 0; e < 2; ++e)
+      GemmB().A(w.e1.dgiT_p[dd], nk, nk).Bm(w.e0.outT_p[e], nk, nk)
+          .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), st);
+    // dW_ih(l0)[dd] = dgi0[dd]^T x
+    pack_T(w.e0.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e0.dgiT_p[dd], st);
+    GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), st);
+  }
+  return check_launch("vame_backward");
+}
+
+int vame_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n, float lr,
+                   const float* hyper, int* step_dev, float* scratch, float beta1, float beta2, float eps, float grad_scale,
+                   void* stream) {
+  VB_REQUIRE(params && grads && exp_avg && exp_avg_sq && max_exp_avg_sq && step_dev && scratch, "vame_adam_step: null pointer");
+  VB_REQUIRE(n > 0, "vame_adam_step: empty");
+  launch_adam(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, hyper, step_dev, scratch, beta1, beta2, eps, grad_scale,
+              (cudaStream_t)stream);
+  return check_launch("vame_adam_step");
+}
+
+/* Re-run one recurrent sweep of encoder layer 1 on the buffers of the last vame_forward(save=1) [+ vame_backward]:
+ * which = 0 forward steps, 1 backward steps.  Used by bench.py to time the dominant kernel with CUDA events. */
+int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* params, const void* packed, void* ws, size_t ws_bytes,
+                         void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && ws, "vame_debug_gru_sweep: null pointer");
+  Ws w = carve_ws(*d, batch, true, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_debug_gru_sweep: workspace too small");
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int H = d->hidden_enc;
+  for (int dd = 0; dd < 2; ++dd) { w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (which == 0) gru_sweep_fwd(W.e1, params + L.e1.bhh[0] + 2 * H, params + L.e1.bhh[1] + 2 * H, w.e1, w.tiles, true, true, st);
+  else gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, 0, w.dhidden + 2 * H, w.dhidden + 3 * H, 4 * H, true, st);
+  return check_launch("vame_debug_gru_sweep");
+}
+
+int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef, double* loss_out,
+                      float* dlatent, void* stream) {
+  VB_REQUIRE(latent && loss_out && batch > 0 && zdims > 0 && zdims <= 64, "vame_cluster_loss: bad arguments (Z <= 64)");
+  // the kernel writes acc[ACC_KMEANS]; give it a pointer such that this slot is loss_out[0]
+  launch_cluster_prior(latent, batch, zdims, kloss, lmbda, bsize, grad_coef, nullptr, dlatent, loss_out - ACC_KMEANS,
+                       (cudaStream_t)stream);
+  return check_launch("vame_cluster_loss");
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// inference entry points: sub-module forwards and the sliding-window embedding
+// ================================================================================================
+namespace vb {
+
+struct EmbedWs {
+  int Bc, Bc_pad, tiles;
+  void* series_p;
+  float* G; long G_rows;
+  float* zeros_f32; void* zeros_p; size_t zeros_p_bytes;
+  GruBuf e0, e1;
+  float* lin; float* scratch_z; float* scratch_lv;
+  double* acc;
+  size_t bytes;
+};
+
+static EmbedWs carve_embed(const vame_dims& d, long n_frames, int chunk, void* base) {
+  EmbedWs w{};
+  Arena A(base);
+  const int T = d.time_window, F = d.num_features, Z = d.zdims, H = d.hidden_enc;
+  w.Bc = chunk; w.Bc_pad = pad128(chunk); w.tiles = w.Bc_pad / 128;
+  const long Np = (n_frames + 127) / 128 * 128;
+  w.series_p = A.raw(p16_bytes((int)Np, F, 128));
+  w.G_rows = Np + w.Bc_pad + T + 128;
+  w.G = A.f32((size_t)w.G_rows * 6 * H);
+  w.zeros_f32 = A.f32((size_t)w.Bc_pad * H);
+  w.zeros_p_bytes = (size_t)w.tiles * nkc_of(H) * p16_tile_bytes(128);
+  w.zeros_p = A.raw(w.zeros_p_bytes);
+  carve_gru(A, w.e0, T, H, F, w.Bc_pad, false, true, /*gi_full=*/false, false, false, false);
+  carve_gru(A, w.e1, T, H, 2 * H, w.Bc_pad, false, false, /*gi_full=*/true, false, false, false);
+  w.lin = A.f32((size_t)w.Bc_pad * 2 * Z);
+  w.scratch_z = A.f32((size_t)w.Bc_pad * Z);
+  w.scratch_lv = A.f32((size_t)w.Bc_pad * Z);
+  w.acc = (double*)A.raw(8 * sizeof(double));
+  w.bytes = (A.off + 1023) & ~(size_t)1023;
+  return w;
+}
+
+}  // namespace vb
+
+extern "C" {
+
+size_t vame_embed_workspace_bytes(const vame_dims* d, long n_frames, int chunk) {
+  if (check_dims(d) || n_frames <= 0 || chunk <= 0) return 0;
+  return carve_embed(*d, n_frames, chunk, nullptr).bytes;
+}
+
+int vame_embed_windows(const vame_dims* d, const float* params, const void* packed, const float* series, long n_frames,
+                       long first_window, long n_windows, int chunk, float* mu_out, void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(params && packed && series && mu_out && ws, "vame_embed_windows: null pointer");
+  const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc;
+  VB_REQUIRE(chunk > 0 && n_windows >= 0 && first_window >= 0, "vame_embed_windows: bad range");
+  VB_REQUIRE(first_window + n_windows + T - 1 <= n_frames, "vame_embed_windows: window range exceeds the series (a window needs T frames)");
+  VB_REQUIRE(n_frames < (1L << 31) - 1024, "vame_embed_windows: series too long for 32-bit row indices");
+  EmbedWs w = carve_embed(*d, n_frames, chunk, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_embed_windows: workspace too small (see vame_embed_workspace_bytes)");
+  if (n_windows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int nkcF = nkc_of(F), nkcH = nkc_of(H);
+  const long Np = (n_frames + 127) / 128 * 128;
+  // once per call: the layer-0 input projection of every FRAME (a window's step t reads row i + t)
+  pack_rows(series, F, (int)Np, F, (int)n_frames, w.series_p, st);
+  cudaMemsetAsync(w.G + (size_t)n_frames * 6 * H, 0, (size_t)(w.G_rows - n_frames) * 6 * H * 4, st);
+  GemmB().A(w.series_p, nkcF, nkcF).Bm(W.e0.wih_p[0], nkcF, nkcF).run((int)n_frames, 6 * H, w.G, 6 * H, W.e0.bias_gi, 0, 1, st);
+  cudaMemsetAsync(w.zeros_f32, 0, (size_t)w.Bc_pad * H * 4, st);
+  cudaMemsetAsync(w.zeros_p, 0, w.zeros_p_bytes, st);
+  for (int dd = 0; dd < 2; ++dd) {
+    w.e0.h0[dd] = w.zeros_f32; w.e0.h0_p[dd] = w.zeros_p;
+    w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
+  }
+  for (long i0 = 0; i0 < n_windows; i0 += w.Bc) {
+    const int Bc = (int)((n_windows - i0 < w.Bc) ? (n_windows - i0) : w.Bc);
+    const int Bp = pad128(Bc), tiles = Bp / 128;
+    // layer 0 reads its projections straight out of G: row(b, t) = first_window + i0 + b + t
+    w.e0.gi = w.G + (size_t)(first_window + i0) * 6 * H;
+    w.e0.gi_bs = 1; w.e0.gi_ts = 1; w.e0.gi_pitch = 6 * H;
+    gru_sweep_fwd(W.e0, params + L.e0.bhh[0] + 2 * H, params + L.e0.bhh[1] + 2 * H, w.e0, tiles, false, true, st);
+    // NOTE: buffers are laid out for Bc_pad rows per time step; a short last chunk uses the first `tiles` tiles of each slot
+    // only if the slot stride matches, so the sweep above is run with the chunk's own tile count and slot strides.
+    w.e1.gi_bs = 1; w.e1.gi_ts = Bp; w.e1.gi_pitch = 6 * H;
+    GemmB().A(w.e0.out_p[0], nkcH, nkcH).A(w.e0.out_p[1], nkcH, nkcH).Bm(W.e1.wih_p[0], nkcH, nkcH).Bm(W.e1.wih_p[1], nkcH, nkcH)
+        .run(T * Bp, 6 * H, w.e1.gi, 6 * H, W.e1.bias_gi, 0, 1, st);
+    gru_sweep_fwd(W.e1, params + L.e1.bhh[0] + 2 * H, params + L.e1.bhh[1] + 2 * H, w.e1, tiles, false, true, st);
+    GemmB gb;
+    gb.A(final_h_p(w.e0, 0, tiles), nkcH, nkcH).A(final_h_p(w.e0, 1, tiles), nkcH, nkcH)
+        .A(final_h_p(w.e1, 0, tiles), nkcH, nkcH).A(final_h_p(w.e1, 1, tiles), nkcH, nkcH);
+    for (int i = 0; i < 4; ++i) gb.Bm(W.lam_p[i], nkcH, nkcH);
+    gb.run(Bc, 2 * Z, w.lin, 2 * Z, params + L.lam_b, 0, 1, st);
+    launch_lambda_fwd(w.lin, 2 * Z, nullptr, Bc, Z, d->softplus, w.scratch_z, mu_out + (size_t)i0 * Z, w.scratch_lv, nullptr, st);
+  }
+  return check_launch("vame_embed_windows");
+}
+
+int vame_encoder_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* x, long x_bs, long x_ts,
+                         float* hidden, void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && x && hidden && ws, "vame_encoder_forward: null pointer");
+  Ws w = carve_ws(*d, batch, false, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_encoder_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int H = d->hidden_enc;
+  encoder_forward(*d, params, L, W, w, x, x_bs, x_ts, false, st);
+  const float* hf[4] = {final_h(w.e0, 0, w.tiles), final_h(w.e0, 1, w.tiles), final_h(w.e1, 0, w.tiles), final_h(w.e1, 1, w.tiles)};
+  for (int i = 0; i < 4; ++i)      // torch.cat((h_n[0], h_n[1], h_n[2], h_n[3]), 1)  (rnn_model.py:43)
+    cudaMemcpy2DAsync(hidden + (size_t)i * H, (size_t)4 * H * 4, hf[i], (size_t)H * 4, (size_t)H * 4, batch, cudaMemcpyDeviceToDevice, st);
+  return check_launch("vame_encoder_forward");
+}
+
+int vame_lambda_forward(const vame_dims* d, int batch, const float* params, const void* packed, const float* hidden, const float* eps,
+                        float* z, float* mu, float* logvar, void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && hidden && z && mu && logvar && ws, "vame_lambda_forward: null pointer");
+  Ws w = carve_ws(*d, batch, false, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_lambda_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  const int H = d->hidden_enc, Z = d->zdims;
+  const void* hp[4];
+  for (int i = 0; i < 4; ++i) {
+    pack_rows(hidden + (size_t)i * H, 4 * H, w.B_pad, H, batch, w.hid_p[i], st);
+    hp[i] = w.hid_p[i];
+  }
+  lambda_linear(*d, params, L, W, w, hp, st);
+  launch_lambda_fwd(w.lin, 2 * Z, eps, batch, Z, d->softplus, z, mu, logvar, nullptr, st);
+  return check_launch("vame_lambda_forward");
+}
+
+int vame_decoder_forward(const vame_dims* d, int batch, int which, const float* params, const void* packed, const float* z, float* pred,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(batch > 0 && params && packed && z && pred && ws, "vame_decoder_forward: null pointer");
+  VB_REQUIRE(which == 0 || (which == 1 && d->future_decoder), "vame_decoder_forward: which must be 0 (decoder) or 1 (decoder_future)");
+  Ws w = carve_ws(*d, batch, false, ws);
+  VB_REQUIRE(ws_bytes >= w.bytes, "vame_decoder_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ParamLayout L = param_layout(*d);
+  const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
+  pack_rows(z, d->zdims, w.B_pad, d->zdims, batch, w.z_p, st);
+  decoder_forward(*d, which, params, L, W, w, false, st);
+  launch_tb_to_bt(w.dec[which].pred_tb, batch, w.dec[which].g.steps, d->num_features, w.B_pad, pred, st);
+  return check_launch("vame_decoder_forward");
+}
+
+}  // extern "C"

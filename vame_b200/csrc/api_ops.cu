@@ -6,6 +6,8 @@
 
 namespace vb {
 thread_local char g_err[512] = {0};
+long g_launch_count = 0;
+int g_opt_pdl = 1;
 }
 
 extern "C" {
@@ -13,6 +15,17 @@ extern "C" {
 const char* vame_last_error(void) { return vb::g_err; }
 
 int vame_abi_version(void) { return VAME_B200_ABI_VERSION; }
+
+long vame_launch_count(void) { return vb::g_launch_count; }
+
+int vame_set_option(const char* name, int value) {
+  VB_REQUIRE(name, "vame_set_option: null name");
+  if (strcmp(name, "pdl") == 0) {
+    vb::g_opt_pdl = value ? 1 : 0;
+    return 0;
+  }
+  return vb::fail("vame_set_option: unknown option");
+}
 
 size_t vame_p16_bytes(int rows, int k, int row_block) { return vb::p16_bytes(rows, k, row_block); }
 

@@ -138,6 +138,7 @@ void launch_gemm_p16(const GemmArgs& g, cudaStream_t st) {
   dim3 grid((g.N + G_BN - 1) / G_BN, (g.M + G_BM - 1) / G_BM, g.splits > 0 ? g.splits : 1);
   GemmArgs a = g;
   if (a.splits < 1) a.splits = 1;
+  count_launch();
   gemm_p16_kernel<<<grid, 128, G_SMEM, st>>>(a);
 }
 

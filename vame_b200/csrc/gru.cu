@@ -205,6 +205,7 @@ void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
+  count_launch();
   cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel, a);
 }
 
@@ -368,6 +369,7 @@ void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
+  count_launch();
   cudaLaunchKernelEx(&cfg, gru_step_bwd_kernel, a);
 }
 

@@ -5,6 +5,11 @@
 
 namespace vb {
 
+// number of kernels this library has enqueued (all streams); bench.py reports the delta over its timed region
+extern long g_launch_count;
+extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
 // ---- pack.cu -------------------------------------------------------------------------------------
 // value(r, k) = src[i * ld + j] with (i, j) = transposed ? (k, r) : (r, k); zero outside i < nrows_src, j < ncols_src
 void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,

@@ -53,6 +53,7 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
   long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
+  count_launch();
   pack_p16_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, ld, transposed, R, K, R_src, K_src, row_map, col_map, RB,
                                                         (__nv_bfloat16*)out);
 }
@@ -104,6 +105,7 @@ __global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __
   }
 }
 void launch_pack_whh(const float* w_hh, int H, int mode, void* out, cudaStream_t st) {
+  count_launch();
   pack_whh_kernel<<<148, 256, 0, st>>>(w_hh, H, mode, (__nv_bfloat16*)out);
 }
 __global__ void bias_fuse_kernel(const float* __restrict__ bi0, const float* __restrict__ bh0, const float* __restrict__ bi1,
@@ -116,6 +118,7 @@ __global__ void bias_fuse_kernel(const float* __restrict__ bi0, const float* __r
   out[i] = bi[r] + (r < 2 * H ? bh[r] : 0.f);
 }
 void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1, const float* b_hh1, int H, float* out, cudaStream_t st) {
+  count_launch();
   bias_fuse_kernel<<<(6 * H + 255) / 256, 256, 0, st>>>(b_ih0, b_hh0, b_ih1, b_hh1, H, out);
 }
 
@@ -162,6 +165,7 @@ void launch_h0_prepare(const float* src, int D, int B, int B_pad, int H, float* 
   int threads = 256;
   long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
   h0_prepare_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, D, B, B_pad, H, h32, (__nv_bfloat16*)hp);
 }
 
@@ -192,6 +196,7 @@ void launch_bt_to_tb(const float* src, int B, int T, int C, long bs, long ts, in
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
+  count_launch();
   bt_to_tb_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, B, T, C, bs, ts, B_pad, dst);
 }
 void launch_tb_to_bt(const float* src, int B, int T, int C, int B_pad, float* dst, cudaStream_t st) {
@@ -199,6 +204,7 @@ void launch_tb_to_bt(const float* src, int B, int T, int C, int B_pad, float* ds
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
+  count_launch();
   tb_to_bt_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, B, T, C, B_pad, dst);
 }
 

@@ -39,6 +39,7 @@ __global__ void lambda_fwd_kernel(const float* __restrict__ lin, long ldl, const
 __global__ void lambda_bwd_kernel(LambdaBwdArgs a) {
   const long total = (long)a.B_pad * a.Z;
   const float c_kl = a.hyper ? a.hyper[HY_BETA] * a.hyper[HY_KLW] / (float)((long)a.B * a.Z) : a.c_kl;
+  const bool use_eps = a.eps && (!a.use_eps_flag || *a.use_eps_flag != 0);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % a.Z);
     const long b = idx / a.Z;
@@ -52,7 +53,7 @@ __global__ void lambda_bwd_kernel(LambdaBwdArgs a) {
       const float m = a.mu[i], lv = a.logvar[i];
       dmu = dz + c_kl * m + (a.dmu_ext ? a.dmu_ext[i] : 0.f);
       dlv = c_kl * 0.5f * (expf(lv) - 1.f) + (a.dlv_ext ? a.dlv_ext[i] : 0.f);
-      if (a.eps) dlv += dz * a.eps[i] * 0.5f * expf(0.5f * lv);
+      if (use_eps) dlv += dz * a.eps[i] * 0.5f * expf(0.5f * lv);
       if (a.softplus) {
         const float x = a.lin[b * a.ldl + a.Z + j];
         dlv *= 1.f / (1.f + expf(-x));
@@ -212,7 +213,10 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
     }
   }
   // ---- eigenvalues, top-k selection (rank bound min(k, B, Z)), loss
-  if (tid < n) ev[tid] = (tid < Z) ? A[tid][tid] : -1e300;
+  if (tid < n) {
+    const double e = (tid < Z) ? A[tid][tid] : -1e300;
+    ev[tid] = (e == e) ? e : -1e300;               // NaN-safe: a total order is needed for the ranking below
+  }
   __syncthreads();
   if (tid < n) {
     int rank = 0;
@@ -372,13 +376,16 @@ static inline unsigned grid_for(long total, int threads, int cap = 148 * 8) {
 }
 void launch_lambda_fwd(const float* lin, long ldl, const float* eps, int B, int Z, int softplus, float* z, float* mu, float* logvar,
                        double* acc, cudaStream_t st) {
+  count_launch();
   lambda_fwd_kernel<<<grid_for((long)B * Z, 256), 256, 0, st>>>(lin, ldl, eps, B, Z, softplus, z, mu, logvar, acc);
 }
 void launch_lambda_bwd(const LambdaBwdArgs& a, cudaStream_t st) {
+  count_launch();
   lambda_bwd_kernel<<<grid_for((long)a.B_pad * a.Z, 256), 256, 0, st>>>(a);
 }
 void launch_mse(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
                 double* acc, int slot, cudaStream_t st) {
+  count_launch();
   mse_kernel<<<grid_for((long)rows * F, 256), 256, 0, st>>>(pred, ldp, target, rows, B, B_pad, F, gscale, dpred, acc, slot);
 }
 void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
@@ -388,27 +395,34 @@ void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda,
     cudaFuncSetAttribute(cluster_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
     attr = true;
   }
+  count_launch();
   cluster_prior_kernel<<<1, 1024, CP_SMEM, st>>>(z, B, Z, kloss, lmbda, bsize, gcoef, hyper, dz, acc);
 }
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st) {
   int ysplit = (int)min((long)64, (rows + 127) / 128);
   if (ysplit < 1) ysplit = 1;
+  count_launch();
   colsum_kernel<<<dim3((N + 127) / 128, ysplit), 128, 0, st>>>(X, ld, rows, N, out);
 }
 void launch_timesum(const float* X, int T, long rowsC, float* out, cudaStream_t st) {
+  count_launch();
   timesum_kernel<<<grid_for(rowsC, 256), 256, 0, st>>>(X, T, rowsC, out);
 }
 void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, int unpadded,
                          cudaStream_t st) {
+  count_launch();
   parts_reduce_kernel<<<grid_for((long)D * B_pad * H, 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out, unpadded);
 }
 void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
                  float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st) {
+  count_launch();
   adam_prepare_kernel<<<1, 32, 0, st>>>(step_dev, scratch2, lr, hyper, b1, b2);
+  count_launch();
   adam_amsgrad_kernel<<<grid_for(n / 4 + 1, 256, 148 * 4), 256, 0, st>>>(p, g, m, v, vmax, n, scratch2, b1, b2, eps, grad_scale);
 }
 void launch_finalize_losses(const double* acc, float* out, double rec_div, double fut_div, double kl_n, double beta, double klw,
                             const float* hyper, int future, cudaStream_t st) {
+  count_launch();
   finalize_losses_kernel<<<1, 32, 0, st>>>(acc, out, rec_div, fut_div, kl_n, beta, klw, hyper, future);
 }
 

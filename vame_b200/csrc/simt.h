@@ -14,6 +14,7 @@ struct LambdaBwdArgs {
   const float* dmu_ext;        // optional external gradient wrt mu / logvar outputs ([B, Z])
   const float* dlv_ext;
   const float* mu; const float* logvar; const float* eps;   // [B, Z]; eps nullptr -> eval (no reparam term)
+  const long long* use_eps_flag;   // optional device flag: 0 -> the forward ran in eval mode, ignore eps
   const float* lin; long ldl;  // forward linear output (needed for softplus')
   const float* hyper;          // device hyper-parameters or nullptr
   float c_kl;                  // used when hyper == nullptr: beta * kl_weight / (B * Z)

@@ -1,0 +1,54 @@
+"""Drop the B200 hot path in behind an UNMODIFIED VAME installation.
+
+``install()`` rebinds, in the already-imported reference modules, exactly the names on the hot path
+(SURVEY.md §8b): the five model classes, the four loss functions, ``train`` / ``test`` and
+``load_model`` / ``embedd_latent_vectors``.  Everything else (config handling, data preparation, train_model's epoch
+loop, checkpoint files, clustering, plotting) keeps running the reference's own code, so existing projects and
+``.pkl`` checkpoints work unchanged.
+"""
+import sys
+
+from . import pose_segmentation as _ps
+from . import rnn_model as _rm
+from . import rnn_vae as _rv
+
+MODEL_NAMES = ("Encoder", "Lambda", "Decoder", "Decoder_Future", "RNN_VAE")
+TRAIN_NAMES = ("reconstruction_loss", "future_reconstruction_loss", "cluster_loss", "kullback_leibler_loss",
+               "kl_annealing", "gaussian", "train", "test")
+CONSUMERS = ("vame.model.rnn_vae", "vame.analysis.pose_segmentation", "vame.model.evaluate",
+             "vame.analysis.generative_functions", "vame.analysis.segment_behavior")
+
+
+def install(verbose=False):
+    """Patch the imported ``vame`` package in place.  Returns the list of (module, name) pairs that were rebound."""
+    if "vame" not in sys.modules:
+        import vame  # noqa: F401  (must be importable; the reference package itself is not modified)
+    done = []
+    ref_rm = sys.modules.get("vame.model.rnn_model")
+    if ref_rm is not None:
+        for n in MODEL_NAMES:
+            setattr(ref_rm, n, getattr(_rm, n))
+            done.append((ref_rm.__name__, n))
+    for modname in CONSUMERS:
+        mod = sys.modules.get(modname)      # NB: vame.analysis.pose_segmentation the ATTRIBUTE is a function; use sys.modules
+        if mod is None:
+            continue
+        for n in MODEL_NAMES:
+            if hasattr(mod, n):
+                setattr(mod, n, getattr(_rm, n))
+                done.append((modname, n))
+    rv = sys.modules.get("vame.model.rnn_vae")
+    if rv is not None:
+        for n in TRAIN_NAMES:
+            setattr(rv, n, getattr(_rv, n))
+            done.append((rv.__name__, n))
+        rv.use_gpu = True
+    ps = sys.modules.get("vame.analysis.pose_segmentation")
+    if ps is not None:
+        for n in ("load_model", "embedd_latent_vectors"):
+            setattr(ps, n, getattr(_ps, n))
+            done.append((ps.__name__, n))
+    if verbose:
+        for m, n in done:
+            print("vame_b200: %s.%s -> B200 path" % (m, n))
+    return done
