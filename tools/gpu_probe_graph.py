@@ -1,0 +1,88 @@
+"""Probe: per-phase timing of the train step in eager / CUDA-graph mode with PDL on/off, each variant in its own
+subprocess under a timeout (a hang in one variant must not take the others down)."""
+import faulthandler
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child(mode, pdl, workload):
+    faulthandler.dump_traceback_later(100, exit=True)
+    import torch
+    from bench import WORKLOADS
+    from oracle import vame_oracle as vo
+    from vame_b200.engine import Engine, TrainStep
+    from vame_b200 import _lib as L
+    F, T, Z, H, fut, S, B = WORKLOADS[workload]
+    lib = L.lib()
+    lib.vame_set_option(b"pdl", int(pdl))
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
+    eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda")
+    eng.load_state_dict(port.state_dict())
+    x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z)
+    cfg = eng.loss_cfg(kmeans_loss=Z, kmeans_lambda=0.1, bsize=B, beta=1.0, kl_weight=1.0)
+    eng.set_hyper(lr=5e-4, kl_weight=1.0, beta=1.0, kmeans_lambda=0.1)
+    ts = TrainStep(eng, B, cfg, world=1, use_graph=(mode == "graph"))
+    print("[%s pdl=%d] capture..." % (mode, pdl), flush=True)
+    ok = ts.capture()
+    print("[%s pdl=%d] captured=%s err=%s" % (mode, pdl, ok, getattr(ts, "capture_error", None)), flush=True)
+    ts.load(x.cuda(), xf[:, :S].cuda() if fut else None, eps.cuda())
+    for i in range(3):
+        ts.run()
+        torch.cuda.synchronize()
+        print("[%s pdl=%d] warm step %d ok" % (mode, pdl, i), flush=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        ts.run()
+    e1.record()
+    torch.cuda.synchronize()
+    print("[%s pdl=%d] RESULT %s ms/step %.3f  windows/s %.0f" % (mode, pdl, workload, e0.elapsed_time(e1) / n, B * n / e0.elapsed_time(e1) * 1e3), flush=True)
+    if mode == "eager":
+        # per-phase breakdown with events
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        tot = [0.0] * 4
+        for _ in range(10):
+            ev[0].record()
+            eng.forward(ts.x, ts.eps, save=True, want=(), ensure_packed=False)
+            ev[1].record()
+            eng.loss(cfg, ts.fut if fut else None, want_grads=True, use_hyper=True, out=ts.losses)
+            ev[2].record()
+            eng.backward(cfg, use_hyper=True)
+            ev[3].record()
+            eng.adam_step(use_hyper=True, repack=True)
+            ev[4].record()
+            torch.cuda.synchronize()
+            for i in range(4):
+                tot[i] += ev[i].elapsed_time(ev[i + 1]) / 10
+        print("[%s pdl=%d] phases ms: forward %.3f loss %.3f backward %.3f adam+repack %.3f" % ((mode, pdl) + tuple(tot)), flush=True)
+        # host-side launch cost
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ts._phase1(); ts._phase2()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        print("[%s pdl=%d] host enqueue time per step %.3f ms" % (mode, pdl, (t1 - t0) / 5 * 1e3), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
+        child(sys.argv[2], int(sys.argv[3]), sys.argv[4])
+        sys.exit(0)
+    workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    for mode, pdl in (("eager", 1), ("eager", 0), ("graph", 0), ("graph", 1)):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload], timeout=150,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            print(r.stdout[-3000:], flush=True)
+            print("variant %s pdl=%d rc=%d" % (mode, pdl, r.returncode), flush=True)
+        except subprocess.TimeoutExpired as ex:
+            out = ex.stdout.decode() if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+            print(out[-3000:], flush=True)
+            print("variant %s pdl=%d TIMEOUT" % (mode, pdl), flush=True)

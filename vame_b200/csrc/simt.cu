@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
     __syncthreads();
     double dmax = 0;
     for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i][i]));
-    if (offmax <= 1e-18 * dmax || offmax == 0) break;
+    if (offmax <= 1e-14 * dmax || offmax == 0) break;      // eigenvalue error ~ off^2 / gap: far below fp32 resolution
     for (int round = 0; round < n - 1; ++round) {
       if (tid < half) {
         // circle method: player n-1 fixed, the others rotate
