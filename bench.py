@@ -88,23 +88,44 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_step_time(F, T, Z, H, fut, S, B, steps, warmup, threads=None):
-    """The reference's CPU arithmetic (oracle torch port: same ATen calls) for the same step, all host cores."""
+def usable_cpus():
+    """Host threads this process can really use: scheduler affinity, capped by the cgroup CPU quota (if any) and by 64
+    (ATen's GRU/GEMM sizes here stop scaling long before that; oversubscribing a quota-limited container is far slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_port_step_time(F, T, Z, H, fut, S, B, steps, warmup, threads=None, budget_s=60.0):
+    """The reference's CPU arithmetic (oracle torch port: same ATen calls) for the same step on the host cores.
+    Bounded: stops early once `budget_s` seconds of CPU work have been spent."""
     import torch
     from oracle import vame_oracle as vo
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cpus()
     torch.set_num_threads(threads)
     torch.manual_seed(19)
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
     opt = vo.make_optimizer(port)
     x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z)
     hp = dict(beta=1.0, kl_weight=1.0, kmeans_loss=Z, kmeans_lambda=0.1, bsize=B)
+    t_start = time.perf_counter()
     for _ in range(warmup):
         vo.train_step(port, x, xf[:, :S] if fut else xf, eps, hp, optimizer=opt)
+        if time.perf_counter() - t_start > budget_s / 2:
+            break
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    for _ in range(max(steps, 1)):
         vo.train_step(port, x, xf[:, :S] if fut else xf, eps, hp, optimizer=opt)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+        done += 1
+        if time.perf_counter() - t_start > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
     return dt, torch.get_num_threads()
 
 

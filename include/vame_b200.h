@@ -22,6 +22,8 @@ int vame_abi_version(void);
 long vame_launch_count(void);
 /* runtime options: "pdl" (default 1) chains the recurrent step kernels with programmatic dependent launch */
 int vame_set_option(const char* name, int value);
+/* measurement hook: device buffer of 16 uint64 that gru_step_fwd_kernel's CTA 0 fills with %globaltimer stamps (NULL = off) */
+int vame_set_debug_buffer(void* device_u64x16);
 
 /* ---- building blocks ------------------------------------------------------------------------ */
 /* bytes of a P16 (bf16 hi/lo split, tensor-core tiled) copy of a [rows, k] matrix */

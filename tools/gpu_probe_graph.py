@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(mode, pdl, workload):
+def child(mode, pdl, workload, streams=1):
     faulthandler.dump_traceback_later(100, exit=True)
     import torch
     from bench import WORKLOADS
@@ -20,6 +20,7 @@ def child(mode, pdl, workload):
     F, T, Z, H, fut, S, B = WORKLOADS[workload]
     lib = L.lib()
     lib.vame_set_option(b"pdl", int(pdl))
+    lib.vame_set_option(b"streams", int(streams))
     torch.manual_seed(19)
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
     eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda")
@@ -69,16 +70,42 @@ def child(mode, pdl, workload):
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         print("[%s pdl=%d] host enqueue time per step %.3f ms" % (mode, pdl, (t1 - t0) / 5 * 1e3), flush=True)
+        # in-kernel timeline of one forward step kernel (CTA 0): globaltimer stamps
+        import ctypes
+        dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+        lib.vame_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+        ws = eng.workspace(B, True)
+        for _ in range(3):
+            lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 0, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
+        torch.cuda.synchronize()
+        lib.vame_set_debug_buffer(None)
+        st = dbg.cpu().tolist()
+        names = ["start", "prologue done", "after pdl_wait", "first chunk landed", "mma issued", "mma done", "epilogue+stores", "end"]
+        print("[%s pdl=%d] fwd step kernel timeline (ns since start of last launch): " % (mode, pdl) +
+              ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
+        e0.record()
+        for _ in range(20):
+            lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 0, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
+        e1.record()
+        torch.cuda.synchronize()
+        print("[%s pdl=%d] fwd sweep: %.2f us per step kernel" % (mode, pdl, e0.elapsed_time(e1) * 1e3 / (20 * T)), flush=True)
+        e0.record()
+        for _ in range(20):
+            lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 1, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
+        e1.record()
+        torch.cuda.synchronize()
+        print("[%s pdl=%d] bwd sweep: %.2f us per step kernel" % (mode, pdl, e0.elapsed_time(e1) * 1e3 / (20 * T)), flush=True)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
-        child(sys.argv[2], int(sys.argv[3]), sys.argv[4])
+        child(sys.argv[2], int(sys.argv[3]), sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 1)
         sys.exit(0)
     workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    for mode, pdl in (("eager", 1), ("eager", 0), ("graph", 0), ("graph", 1)):
+    for mode, pdl, streams in (("eager", 1, 1), ("eager", 1, 0), ("eager", 0, 1), ("graph", 1, 1), ("graph", 1, 0)):
+        print("##### variant mode=%s pdl=%d streams=%d" % (mode, pdl, streams), flush=True)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload], timeout=150,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload, str(streams)], timeout=150,
                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             print(r.stdout[-3000:], flush=True)
             print("variant %s pdl=%d rc=%d" % (mode, pdl, r.returncode), flush=True)

@@ -166,6 +166,34 @@ static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
 }
 
 // ================================================================================================
+// side streams: independent branches of a step (future decoder, k-means prior, weight-gradient GEMMs) run concurrently
+// with the latency-bound recurrent sweeps; fork/join are event edges, so the whole thing stays CUDA-graph capturable.
+// ================================================================================================
+struct Side {
+  cudaStream_t s[2];
+  cudaEvent_t ev[32];
+  int nev;
+};
+static Side& side() {
+  static Side S{};
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
+    init = true;
+  }
+  return S;
+}
+// make `to` wait for everything enqueued on `from` so far
+static inline void edge(cudaStream_t from, cudaStream_t to) {
+  if (from == to) return;
+  Side& S = side();
+  cudaEvent_t e = S.ev[S.nev++ & 31];
+  cudaEventRecord(e, from);
+  cudaStreamWaitEvent(to, e, 0);
+}
+
+// ================================================================================================
 // small host helpers
 // ================================================================================================
 static inline GemmSeg seg(const void* p, long rb_stride, int nkc) { return GemmSeg{p, rb_stride, nkc}; }
@@ -335,13 +363,16 @@ static inline const float* final_parts(const GruBuf& L, int d, int tiles) {
 
 // weight / bias gradients of the recurrent part of one bi-GRU layer after its backward sweep:
 //   dW_hh[d] = dgh[d]^T hprev[d],  db_hh[d] = colsum(dgh[d]),  db_ih[d] = colsum(dgi[d])
+static void pack_outT(GruBuf& L, int Bp, cudaStream_t st) {      // forward activations only: can run any time after the forward
+  const long rows = (long)L.steps * Bp;
+  for (int d = 0; d < 2; ++d) pack_T(L.out[d], L.H, L.H, (int)rows, (int)rows, L.outT_p[d], st);
+}
 static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st) {
   const int H = L.H;
   const long rows = (long)L.steps * Bp;
   const int cB = Bp / KCHUNK, nk = (int)(rows / KCHUNK);
   for (int d = 0; d < 2; ++d) {
     pack_T(L.dgh[d], 3 * H, 3 * H, (int)rows, (int)rows, L.dghT_p[d], st);
-    pack_T(L.out[d], H, H, (int)rows, (int)rows, L.outT_p[d], st);
     const void* h0T = d == 0 ? h0T0 : h0T1;
     GemmB gb;
     gb.A(L.dghT_p[d], nk, nk);
@@ -504,8 +535,13 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
   if (eps) cudaMemcpyAsync(w.eps, eps, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
   launch_lambda_fwd(w.lin, 2 * Z, eps ? w.eps : nullptr, batch, Z, d->softplus, w.z, w.mu, w.logvar, w.acc, st);
   pack_rows(w.z, Z, w.B_pad, Z, batch, w.z_p, st);
+  cudaStream_t sA = (d->future_decoder && g_opt_streams) ? side().s[0] : st;
+  if (d->future_decoder) {
+    edge(st, sA);
+    decoder_forward(*d, 1, params, L, W, w, save, sA);
+  }
   decoder_forward(*d, 0, params, L, W, w, save, st);
-  if (d->future_decoder) decoder_forward(*d, 1, params, L, W, w, save, st);
+  edge(sA, st);
   if (pred) launch_tb_to_bt(w.dec[0].pred_tb, batch, T, F, w.B_pad, pred, st);
   if (future && d->future_decoder) launch_tb_to_bt(w.dec[1].pred_tb, batch, d->future_steps, F, w.B_pad, future, st);
   if (z) cudaMemcpyAsync(z, w.z, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
@@ -528,6 +564,10 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
   const bool with_fut = d->future_decoder && cfg->with_future;
   VB_REQUIRE(!with_fut || fut, "vame_loss: future target missing");
   const double nrec = (double)batch * T * F;
+  cudaStream_t sA = g_opt_streams ? side().s[0] : st;
+  edge(st, sA);
+  launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
+                       training ? w.dz_km : nullptr, w.acc, sA);
   launch_mse(w.dec[0].pred_tb, F, w.x_tb, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
              training ? w.dec[0].dpred_tb : nullptr, w.acc, ACC_REC, st);
   double nfut = 1.0;
@@ -538,8 +578,7 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
     launch_mse(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f,
                training ? w.dec[1].dpred_tb : nullptr, w.acc, ACC_FUT, st);
   }
-  launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
-                       training ? w.dz_km : nullptr, w.acc, st);
+  edge(sA, st);
   launch_finalize_losses(w.acc, losses_out, cfg->mse_red_mean ? nrec : 1.0, cfg->mse_pred_mean ? nfut : 1.0, (double)batch * Z,
                          cfg->beta, cfg->kl_weight, hyper, with_fut ? 1 : 0, st);
   return check_launch("vame_loss");
@@ -554,6 +593,9 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   Ws w = carve_ws(*d, batch, true, ws);
   VB_REQUIRE(ws_bytes >= w.bytes, "vame_backward: workspace too small (forward must have used save_for_backward)");
   cudaStream_t st = (cudaStream_t)stream;
+  // sA: the future decoder's backward; sB: weight-gradient work that is not on the data-gradient chain
+  cudaStream_t sA = g_opt_streams ? side().s[0] : st;
+  cudaStream_t sB = g_opt_streams ? side().s[1] : st;
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc, Bp = w.B_pad, B = batch;
@@ -565,54 +607,65 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
   }
   pack_T(w.z, Z, Z, Bp, B, w.zT_p, st);                                   // [Z rows, K = B_pad]
+  edge(st, sB);
+  // operands that only depend on the forward pass: transposed activations for the weight-gradient GEMMs
+  pack_outT(w.e0, Bp, sB);
+  pack_outT(w.e1, Bp, sB);
+  pack_T(w.x_tb, F, F, T * Bp, T * Bp, w.xT_p, sB);
 
   const int ndec = d->future_decoder ? 2 : 1;
   const float* dz_dec[2] = {nullptr, nullptr};
-  for (int i = 0; i < ndec; ++i) {
+  for (int i = ndec - 1; i >= 0; --i) {      // the future decoder (i = 1) is enqueued first, on its own stream
     DecBuf& D = w.dec[i];
     const float* ext = i == 0 ? dpred : dfuture;
     const bool have_grad = use_loss_grads ? (i == 0 || cfg->with_future) : (ext != nullptr);
     if (!have_grad) continue;                                             // this decoder received no gradient
+    cudaStream_t sd = i == 0 ? st : sA;      // data-gradient chain of this decoder
+    cudaStream_t sw = i == 0 ? sB : sA;      // its weight-gradient work
+    if (i == 1) edge(st, sA);
     const int Hd = D.g.H, steps = D.g.steps;
     const long rows = (long)steps * Bp;
     const int nk = (int)(rows / KCHUNK), nkcF = nkc_of(F), nkc3 = nkc_of(3 * Hd), nkc2H = nkc_of(2 * Hd);
     const GruOff& o = i == 0 ? L.dec : L.fut;
     const GruPacked& Wg = i == 0 ? W.dec : W.fut;
-    if (!use_loss_grads) launch_bt_to_tb(ext, B, steps, F, (long)steps * F, F, Bp, D.dpred_tb, st);
-    // hidden_to_output backward
-    pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, st);
-    GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run((int)rows, 2 * Hd, D.ddec, 2 * Hd, nullptr, 0, 1, st);
-    pack_T(D.dpred_tb, F, F, (int)rows, (int)rows, D.dpredT_p, st);
-    launch_colsum(D.dpred_tb, F, rows, F, G + L.h2o_b[i], st);
-    // BPTT
-    gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + Hd, 2 * Hd, (long)Bp * 2 * Hd, nullptr, nullptr, 0, true, st);
-    for (int dd = 0; dd < 2; ++dd) pack_T(D.g.h0[dd], Hd, Hd, Bp, Bp, D.g.h0T_p[dd], st);
-    gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, st);       // also fills outT_p
-    for (int dd = 0; dd < 2; ++dd)                                        // dW_out[:, dd*H:(dd+1)*H] = dpred^T out_dd
-      GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
-          .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), st);
-    // input projection: the input is z at every step -> reduce dgi over time first
-    for (int dd = 0; dd < 2; ++dd) {
-      launch_timesum(D.g.dgi[dd], steps, (long)Bp * 3 * Hd, D.dgi_sum[dd], st);
-      pack_rows(D.dgi_sum[dd], 3 * Hd, Bp, 3 * Hd, Bp, D.dgi_sum_p[dd], st);
-      pack_T(D.dgi_sum[dd], 3 * Hd, 3 * Hd, Bp, Bp, D.dgi_sumT_p[dd], st);
-      GemmB().A(D.dgi_sumT_p[dd], nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB)
-          .run(3 * Hd, Z, G + o.wih[dd], Z, nullptr, 1, splits_for(3 * Hd, Z, nkcB), st);
+    if (!use_loss_grads) launch_bt_to_tb(ext, B, steps, F, (long)steps * F, F, Bp, D.dpred_tb, sd);
+    // ---- data-gradient chain: hidden_to_output backward, BPTT, dz
+    pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);
+    GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run((int)rows, 2 * Hd, D.ddec, 2 * Hd, nullptr, 0, 1, sd);
+    gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + Hd, 2 * Hd, (long)Bp * 2 * Hd, nullptr, nullptr, 0, true, sd);
+    for (int dd = 0; dd < 2; ++dd) {         // the input is z at every step -> reduce dgi over time first
+      launch_timesum(D.g.dgi[dd], steps, (long)Bp * 3 * Hd, D.dgi_sum[dd], sd);
+      pack_rows(D.dgi_sum[dd], 3 * Hd, Bp, 3 * Hd, Bp, D.dgi_sum_p[dd], sd);
     }
     GemmB().A(D.dgi_sum_p[0], nkc3, nkc3).A(D.dgi_sum_p[1], nkc3, nkc3).Bm(Wg.wihT_p[0], nkc3, nkc3).Bm(Wg.wihT_p[1], nkc3, nkc3)
-        .run(B, Z, D.dz, Z, nullptr, 0, 1, st);
+        .run(B, Z, D.dz, Z, nullptr, 0, 1, sd);
     // latent_to_hidden backward through the inverse of the .view(2,B,H) quirk
     launch_parts_reduce(final_parts(D.g, 0, w.tiles), Hd / 32 + 1, (long)(final_parts(D.g, 1, w.tiles) - final_parts(D.g, 0, w.tiles)), 2, B,
-                        Bp, Hd, D.dhid, 1, st);
-    pack_rows(D.dhid, 2 * Hd, Bp, 2 * Hd, B, D.dhid_p, st);
-    pack_T(D.dhid, 2 * Hd, 2 * Hd, Bp, B, D.dhidT_p, st);
-    GemmB().A(D.dhidT_p, nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB).run(2 * Hd, Z, G + L.l2h_w[i], Z, nullptr, 1, splits_for(2 * Hd, Z, nkcB), st);
-    launch_colsum(D.dhid, 2 * Hd, B, 2 * Hd, G + L.l2h_b[i], st);
-    GemmB().A(D.dhid_p, nkc2H, nkc2H).Bm(W.l2hT_p[i], nkc2H, nkc2H).run(B, Z, D.dz, Z, nullptr, 1, 1, st);
+                        Bp, Hd, D.dhid, 1, sd);
+    pack_rows(D.dhid, 2 * Hd, Bp, 2 * Hd, B, D.dhid_p, sd);
+    GemmB().A(D.dhid_p, nkc2H, nkc2H).Bm(W.l2hT_p[i], nkc2H, nkc2H).run(B, Z, D.dz, Z, nullptr, 1, 1, sd);
     dz_dec[i] = D.dz;
+    // ---- weight gradients of this decoder (off the critical path)
+    edge(sd, sw);
+    if (i == 1) edge(sA, st);                // main needs dz of the future decoder, not its weight gradients
+    pack_T(D.dpred_tb, F, F, (int)rows, (int)rows, D.dpredT_p, sw);
+    launch_colsum(D.dpred_tb, F, rows, F, G + L.h2o_b[i], sw);
+    for (int dd = 0; dd < 2; ++dd) pack_T(D.g.h0[dd], Hd, Hd, Bp, Bp, D.g.h0T_p[dd], sw);
+    pack_outT(D.g, Bp, sw);
+    gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, sw);
+    for (int dd = 0; dd < 2; ++dd) {                                      // dW_out[:, dd*H:(dd+1)*H] = dpred^T out_dd
+      GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
+          .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), sw);
+      pack_T(D.dgi_sum[dd], 3 * Hd, 3 * Hd, Bp, Bp, D.dgi_sumT_p[dd], sw);
+      GemmB().A(D.dgi_sumT_p[dd], nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB)
+          .run(3 * Hd, Z, G + o.wih[dd], Z, nullptr, 1, splits_for(3 * Hd, Z, nkcB), sw);
+    }
+    pack_T(D.dhid, 2 * Hd, 2 * Hd, Bp, B, D.dhidT_p, sw);
+    GemmB().A(D.dhidT_p, nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB).run(2 * Hd, Z, G + L.l2h_w[i], Z, nullptr, 1, splits_for(2 * Hd, Z, nkcB), sw);
+    launch_colsum(D.dhid, 2 * Hd, B, 2 * Hd, G + L.l2h_b[i], sw);
   }
 
-  // Lambda backward
+  // ---- Lambda backward (main chain: dlin -> dhidden)
   {
     LambdaBwdArgs a{};
     a.dz[0] = use_loss_grads ? w.dz_km : nullptr;
@@ -628,42 +681,45 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     a.dlin = w.dlin; a.ldd = 2 * Z;
     launch_lambda_bwd(a, st);
   }
-  const int nkc2Z = nkc_of(2 * Z), nkcH = nkc_of(H);
+  const int nkc2Z = nkc_of(2 * Z);
+  edge(st, sB);
   pack_rows(w.dlin, 2 * Z, Bp, 2 * Z, Bp, w.dlin_p, st);
-  pack_T(w.dlin, 2 * Z, 2 * Z, Bp, Bp, w.dlinT_p, st);
-  launch_colsum(w.dlin, 2 * Z, Bp, 2 * Z, G + L.lam_b, st);
-  {
+  GemmB().A(w.dlin_p, nkc2Z, nkc2Z).Bm(W.lamT_p, nkc2Z, nkc2Z).run(Bp, 4 * H, w.dhidden, 4 * H, nullptr, 0, 1, st);
+  {   // Lambda weight gradients on sB
+    pack_T(w.dlin, 2 * Z, 2 * Z, Bp, Bp, w.dlinT_p, sB);
+    launch_colsum(w.dlin, 2 * Z, Bp, 2 * Z, G + L.lam_b, sB);
     const float* hf[4] = {final_h(w.e0, 0, w.tiles), final_h(w.e0, 1, w.tiles), final_h(w.e1, 0, w.tiles), final_h(w.e1, 1, w.tiles)};
     for (int i = 0; i < 4; ++i) {
-      pack_T(hf[i], H, H, Bp, Bp, w.hidT_p[i], st);
+      pack_T(hf[i], H, H, Bp, Bp, w.hidT_p[i], sB);
       GemmB().A(w.dlinT_p, nkcB, nkcB).Bm(w.hidT_p[i], nkcB, nkcB)
-          .run(2 * Z, H, G + L.lam_w + (long)i * H, 4 * H, nullptr, 1, splits_for(2 * Z, H, nkcB), st);
+          .run(2 * Z, H, G + L.lam_w + (long)i * H, 4 * H, nullptr, 1, splits_for(2 * Z, H, nkcB), sB);
     }
   }
-  GemmB().A(w.dlin_p, nkc2Z, nkc2Z).Bm(W.lamT_p, nkc2Z, nkc2Z).run(Bp, 4 * H, w.dhidden, 4 * H, nullptr, 0, 1, st);
 
-  // encoder layer 1 (only h_n is used downstream, rnn_model.py:41-43: no per-step output gradient)
+  // ---- encoder layer 1 (only h_n is used downstream, rnn_model.py:41-43: no per-step output gradient)
   const long rows = (long)T * Bp;
   const int nk = (int)(rows / KCHUNK), nkc3 = nkc_of(3 * H);
   gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, 0, w.dhidden + 2 * H, w.dhidden + 3 * H, 4 * H, true, st);
-  // layer-0 outputs transposed once: hprev of layer 0 and the input of layer 1
-  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, st);
+  edge(st, sB);
   GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
       .run((int)rows, 2 * H, w.dx1, 2 * H, nullptr, 0, 1, st);
-  // encoder layer 0
-  gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + H, 2 * H, (long)Bp * 2 * H, w.dhidden, w.dhidden + H, 4 * H, true, st);
-  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, st);      // fills e0.outT_p
-  pack_T(w.x_tb, F, F, (int)rows, (int)rows, w.xT_p, st);
-  for (int dd = 0; dd < 2; ++dd) {
-    // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
-    pack_T(w.e1.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e1.dgiT_p[dd], st);
+  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB);
+  for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
+    pack_T(w.e1.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e1.dgiT_p[dd], sB);
     for (int e = 0; e < 2; ++e)
       GemmB().A(w.e1.dgiT_p[dd], nk, nk).Bm(w.e0.outT_p[e], nk, nk)
-          .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), st);
-    // dW_ih(l0)[dd] = dgi0[dd]^T x
-    pack_T(w.e0.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e0.dgiT_p[dd], st);
-    GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), st);
+          .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sB);
   }
+  // ---- encoder layer 0
+  gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + H, 2 * H, (long)Bp * 2 * H, w.dhidden, w.dhidden + H, 4 * H, true, st);
+  edge(st, sB);
+  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB);
+  for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
+    pack_T(w.e0.dgi[dd], 3 * H, 3 * H, (int)rows, (int)rows, w.e0.dgiT_p[dd], sB);
+    GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sB);
+  }
+  edge(sB, st);
+  edge(sA, st);
   return check_launch("vame_backward");
 }
 

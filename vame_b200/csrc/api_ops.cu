@@ -8,6 +8,8 @@ namespace vb {
 thread_local char g_err[512] = {0};
 long g_launch_count = 0;
 int g_opt_pdl = 1;
+int g_opt_streams = 1;
+unsigned long long* g_dbg_buffer = nullptr;
 }
 
 extern "C" {
@@ -18,10 +20,19 @@ int vame_abi_version(void) { return VAME_B200_ABI_VERSION; }
 
 long vame_launch_count(void) { return vb::g_launch_count; }
 
+int vame_set_debug_buffer(void* device_u64x16) {
+  vb::g_dbg_buffer = (unsigned long long*)device_u64x16;
+  return 0;
+}
+
 int vame_set_option(const char* name, int value) {
   VB_REQUIRE(name, "vame_set_option: null name");
   if (strcmp(name, "pdl") == 0) {
     vb::g_opt_pdl = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "streams") == 0) {
+    vb::g_opt_streams = value ? 1 : 0;
     return 0;
   }
   return vb::fail("vame_set_option: unknown option");

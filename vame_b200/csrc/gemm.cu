@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
   const uint32_t tmem = *tmem_slot;
 
   if (nk > 0) {
-    if (threadIdx.x == 0) {
+    // warp 0 = producer, warp 1 = MMA issuer: one elected lane works, its siblings are parked at __syncwarp (a sibling
+    // spinning on an mbarrier would put the whole warp to sleep and starve the working lane)
+    if (warp == 0) {
+     if (lane == 0) {
       // ===== producer: TMA-engine bulk copies of whole P16 tiles =====
       for (int i = 0; i < nk; ++i) {
         const int s = i % G_STAGES;
@@ -66,7 +69,10 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
         bulk_g2s(sa, seg_tile(g.a, mb, kc_begin + i), G_TILE_BYTES, &full[s]);
         bulk_g2s(sa + G_TILE_BYTES, seg_tile(g.b, nb, kc_begin + i), G_TILE_BYTES, &full[s]);
       }
-    } else if (threadIdx.x == 32) {
+     }
+     __syncwarp();
+    } else if (warp == 1) {
+     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = make_idesc_bf16(G_BM, G_BN);
       for (int i = 0; i < nk; ++i) {
@@ -89,6 +95,8 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
         umma_commit(&empty[s]);          // frees the smem stage once these MMAs retire
       }
       umma_commit(done);
+     }
+     __syncwarp();
     }
     // ===== epilogue: all 4 warps, warp w owns TMEM lanes 32w..32w+31 (= rows of the tile) =====
     mbar_wait(done, 0);

@@ -53,6 +53,21 @@ __device__ __forceinline__ void st16_p16(__nv_bfloat16* tile, int rows_in_tile, 
   *reinterpret_cast<uint4*>(lo + off + 64) = lo1;
 }
 
+// optional in-kernel timeline (vame_set_debug_buffer): CTA (0,0,0) thread 0 records %globaltimer at fixed points
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_STAMP(i)                                                                              \
+  do {                                                                                            \
+    if (a.dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[(i)] = gtime(); \
+  } while (0)
+#define DBG_STAMP0(i)                                                                             \
+  do {                                                                                            \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[(i)] = gtime();     \
+  } while (0)
+
 // =================================================================================================
 // forward step
 // =================================================================================================
@@ -89,12 +104,19 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   const uint32_t tmem = *tmem_slot;
 
   // ---- prologue: everything that does not depend on the previous time step ----
-  if (tid == 0) {
-    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
-    for (int kc = 0; kc < nkc; ++kc) {
-      mbar_expect_tx(&wbar[kc], F_WTILE);
-      bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+  // NOTE on warp roles: the TMA / MMA issuing thread is lane 0 of warp 0 and its 31 sibling lanes are parked at a
+  // __syncwarp() — if they spun on an mbarrier instead, the divergent try_wait path would put the whole warp to sleep
+  // and starve the issuing lane.
+  DBG_STAMP(0);
+  if (warp == 0) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_expect_tx(&wbar[kc], F_WTILE);
+        bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+      }
     }
+    __syncwarp();
   }
   const int r_in = q * 32 + lane;
   const long b = (long)tile * 128 + r_in;
@@ -109,33 +131,40 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     ld16(d.b_hn + u0, bhn);
   }
 
+  DBG_STAMP(1);
   if (a.pdl) pdl_wait();               // previous step's h is now complete and visible
   if (a.pdl) pdl_launch_dependents();  // let the next step start its prologue
+  DBG_STAMP(2);
 
-  if (tid == 0) {
-    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(d.h_in_p) + (size_t)tile * nkc * p16_tile_elems(128);
-    for (int kc = 0; kc < nkc; ++kc) {
-      mbar_expect_tx(&abar[kc], F_ATILE);
-      bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
-    }
-    const uint32_t idesc = make_idesc_bf16(128, 96);
-    const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
-    for (int kc = 0; kc < nkc; ++kc) {
-      mbar_wait(&wbar[kc], 0);
-      mbar_wait(&abar[kc], 0);
-      tc_fence_after();
-      const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
-      const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t ko = ks * 2 * ATOM_BYTES;
-        const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
-        const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-        umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-        umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-        umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(d.h_in_p) + (size_t)tile * nkc * p16_tile_elems(128);
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_expect_tx(&abar[kc], F_ATILE);
+        bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
       }
+      const uint32_t idesc = make_idesc_bf16(128, 96);
+      const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_wait(&wbar[kc], 0);
+        mbar_wait(&abar[kc], 0);
+        if (kc == 0) DBG_STAMP0(3);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
+        const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t ko = ks * 2 * ATOM_BYTES;
+          const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
+          const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+          umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+          umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+          umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+        }
+      }
+      umma_commit(done);
+      DBG_STAMP0(4);
     }
-    umma_commit(done);
+    __syncwarp();
   }
 
   float hprev[16];
@@ -143,6 +172,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
 
   mbar_wait(done, 0);
   __syncwarp();
+  DBG_STAMP(5);
   tc_fence_after();
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
   float ar[16], az[16], an[16];
@@ -173,9 +203,11 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     st16(d.sv_n + b * H + u0, an);
     st16(d.sv_ghn + b * H + u0, bhn);
   }
+  DBG_STAMP(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 128);
+  DBG_STAMP(7);
 }
 
 static void launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int threads, size_t smem, cudaStream_t st,
@@ -194,7 +226,9 @@ static void launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 
   }
 }
 
-void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st) {
+void launch_gru_step_fwd(const GruFwdArgs& a_in, cudaStream_t st) {
+  GruFwdArgs a = a_in;
+  a.dbg = g_dbg_buffer;
   const int nkc = (a.H + KCHUNK - 1) / KCHUNK;
   const size_t smem = (size_t)nkc * (F_WTILE + F_ATILE) + 256;
   static size_t attr_smem = 0;
@@ -243,16 +277,19 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   const uint32_t tmem = *tmem_slot;
 
   // ---- prologue independent of the previous BPTT step: weights + saved forward activations ----
-  if (tid == 0) {
-    // global layout: [slice c][rb][kc(2)][plane(2)][128x64]; shared layout per kc: hi[rb0..], lo[rb0..]
-    const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
-    mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
-    for (int kc = 0; kc < 2; ++kc)
-      for (int rb = 0; rb < nrb; ++rb) {
-        const __nv_bfloat16* t = wp + ((size_t)rb * 2 + kc) * p16_tile_elems(128);
-        bulk_g2s(sW + kc * wchunk + (size_t)rb * B_APLANE, t, B_APLANE, wbar);                                    // hi
-        bulk_g2s(sW + kc * wchunk + (size_t)(nrb + rb) * B_APLANE, t + 128 * KCHUNK, B_APLANE, wbar);             // lo
-      }
+  if (warp == 0) {
+    if (lane == 0) {
+      // global layout: [slice c][rb][kc(2)][plane(2)][128x64]; shared layout per kc: hi[rb0..], lo[rb0..]
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
+      mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
+      for (int kc = 0; kc < 2; ++kc)
+        for (int rb = 0; rb < nrb; ++rb) {
+          const __nv_bfloat16* t = wp + ((size_t)rb * 2 + kc) * p16_tile_elems(128);
+          bulk_g2s(sW + kc * wchunk + (size_t)rb * B_APLANE, t, B_APLANE, wbar);                                    // hi
+          bulk_g2s(sW + kc * wchunk + (size_t)(nrb + rb) * B_APLANE, t + 128 * KCHUNK, B_APLANE, wbar);             // lo
+        }
+    }
+    __syncwarp();
   }
   const int r_in = q * 32 + lane;
   const long b = (long)tile * 128 + r_in;
@@ -302,25 +339,28 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   fence_proxy_async_smem();
   __syncthreads();
 
-  if (tid == 0) {
-    mbar_wait(wbar, 0);
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, H);
-    for (int kc = 0; kc < 2; ++kc) {
-      const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
-      const uint32_t sw = smem_u32(sW + kc * wchunk);
-      const uint32_t wplane = (uint32_t)nrb * B_APLANE;
-      const int ksteps = kc == 0 ? 4 : 2;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t ko = ks * 2 * ATOM_BYTES;
-        const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
-        const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-        umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-        umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-        umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, H);
+      for (int kc = 0; kc < 2; ++kc) {
+        const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
+        const uint32_t sw = smem_u32(sW + kc * wchunk);
+        const uint32_t wplane = (uint32_t)nrb * B_APLANE;
+        const int ksteps = kc == 0 ? 4 : 2;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t ko = ks * 2 * ATOM_BYTES;
+          const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
+          const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+          umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+          umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+          umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+        }
       }
+      umma_commit(done);
     }
-    umma_commit(done);
+    __syncwarp();
   }
 
   // outputs that do not need the MMA

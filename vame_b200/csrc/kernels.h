@@ -8,6 +8,8 @@ namespace vb {
 // number of kernels this library has enqueued (all streams); bench.py reports the delta over its timed region
 extern long g_launch_count;
 extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
+extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
+extern int g_opt_streams;   // 1: run independent branches of a step on internal side streams
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 // ---- pack.cu -------------------------------------------------------------------------------------
@@ -58,6 +60,7 @@ struct GruFwdArgs {
   GruDirFwd d[2];
   int ndir, H, tiles;
   int pdl;                // launch with programmatic stream serialization
+  unsigned long long* dbg;   // optional device buffer for %globaltimer stamps (filled in by the launcher)
 };
 void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
 
