@@ -110,7 +110,20 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
       const int col = nb * G_BN + c0;
-      if (row < g.M && col < g.N) {
+      if (g.c_fm) {                       // feature-major output: C[n*ldc + m]; lanes (= rows m) are contiguous -> coalesced
+        if (row < g.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (col + j < g.N) {
+              float x = v[j];
+              if (g.bias && split == 0) x += g.bias[col + j];
+              float* dst = g.C + (long)(col + j) * g.ldc + row;
+              if (g.atomic) atomicAdd(dst, x);
+              else *dst = x;
+            }
+          }
+        }
+      } else if (row < g.M && col < g.N) {
         float* crow = g.C + (long)row * g.ldc + col;
         if (g.bias && split == 0) {
 #pragma unroll

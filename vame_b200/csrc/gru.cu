@@ -40,6 +40,15 @@ __device__ __forceinline__ void st16(float* p, const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+// feature-major access: 16 consecutive features of one row (lane = row -> each access is coalesced across the warp)
+__device__ __forceinline__ void ldf16(const float* p, long ld, float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = p[i * ld];
+}
+__device__ __forceinline__ void stf16(float* p, long ld, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) p[i * ld] = v[i];
+}
 // write 16 consecutive k-values of one row into a P16 tile (two atoms), hi and lo planes; generic pointer (smem or global)
 __device__ __forceinline__ void st16_p16(__nv_bfloat16* tile, int rows_in_tile, int r, int k, const float* v) {
   uint4 hi0, lo0, hi1, lo1;
@@ -124,10 +133,10 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   const int u0 = c * 32 + j0;          // first hidden unit handled by this thread
   float gir[16], giz[16], gin[16], bhn[16];
   {
-    const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts) * d.gi_pitch;
-    ld16(gi_row + u0, gir);
-    ld16(gi_row + H + u0, giz);
-    ld16(gi_row + 2 * H + u0, gin);
+    const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts);
+    ldf16(gi_row + (long)u0 * d.gi_ld, d.gi_ld, gir);
+    ldf16(gi_row + (long)(H + u0) * d.gi_ld, d.gi_ld, giz);
+    ldf16(gi_row + (long)(2 * H + u0) * d.gi_ld, d.gi_ld, gin);
     ld16(d.b_hn + u0, bhn);
   }
 
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   }
 
   float hprev[16];
-  ld16(d.h_in + b * H + u0, hprev);
+  ldf16(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);
 
   mbar_wait(done, 0);
   __syncwarp();
@@ -191,17 +200,18 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     hn[i] = (1.0f - z) * n + z * hprev[i];
     ar[i] = r; az[i] = z; an[i] = n; bhn[i] = ghn;
   }
-  st16(d.h_out + b * H + u0, hn);
+  stf16(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
   {
     const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
     st16_p16(t, 128, r_in, kk, hn);
   }
   if (d.sv_r) {
-    st16(d.sv_r + b * H + u0, ar);
-    st16(d.sv_z + b * H + u0, az);
-    st16(d.sv_n + b * H + u0, an);
-    st16(d.sv_ghn + b * H + u0, bhn);
+    const long so = (long)u0 * d.sv_ld + b;
+    stf16(d.sv_r + so, d.sv_ld, ar);
+    stf16(d.sv_z + so, d.sv_ld, az);
+    stf16(d.sv_n + so, d.sv_ld, an);
+    stf16(d.sv_ghn + so, d.sv_ld, bhn);
   }
   DBG_STAMP(6);
   tc_fence_before();
@@ -295,12 +305,15 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   const long b = (long)tile * 128 + r_in;
   const int j0 = half * 16, u0 = c * 32 + j0;
   float r[16], z[16], n[16], ghn[16], hp[16], dh[16];
-  ld16(d.sv_r + b * H + u0, r);
-  ld16(d.sv_z + b * H + u0, z);
-  ld16(d.sv_n + b * H + u0, n);
-  ld16(d.sv_ghn + b * H + u0, ghn);
-  ld16(d.h_prev + b * H + u0, hp);
-  if (d.dout) ld16(d.dout + b * d.dout_pitch + u0, dh);
+  {
+    const long so = (long)u0 * d.sv_ld + b;
+    ldf16(d.sv_r + so, d.sv_ld, r);
+    ldf16(d.sv_z + so, d.sv_ld, z);
+    ldf16(d.sv_n + so, d.sv_ld, n);
+    ldf16(d.sv_ghn + so, d.sv_ld, ghn);
+  }
+  ldf16(d.h_prev + (long)u0 * d.h_prev_ld + b, d.h_prev_ld, hp);
+  if (d.dout) ldf16(d.dout + (long)u0 * d.dout_ld + b, d.dout_ld, dh);
   else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) dh[i] = 0.f;
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   const long bpad = (long)a.tiles * 128;
   for (int p = 0; p < d.n_parts; ++p) {
     float t[16];
-    ld16(d.parts + (long)p * d.parts_stride + b * d.parts_pitch + u0, t);
+    ldf16(d.parts + (long)p * d.parts_stride + (long)u0 * d.parts_ld + b, d.parts_ld, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) dh[i] += t[i];
   }
@@ -364,13 +377,13 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   }
 
   // outputs that do not need the MMA
-  st16(d.parts_out + ((long)nsl * bpad + b) * H + u0, dh);            // carry slot
-  st16(d.dgi + b * 3 * H + u0, dar);
-  st16(d.dgi + b * 3 * H + H + u0, daz);
-  st16(d.dgi + b * 3 * H + 2 * H + u0, dan);
-  st16(d.dgh + b * 3 * H + u0, dar);
-  st16(d.dgh + b * 3 * H + H + u0, daz);
-  st16(d.dgh + b * 3 * H + 2 * H + u0, dgn);
+  stf16(d.parts_out + ((long)nsl * H + u0) * bpad + b, bpad, dh);     // carry slot
+  stf16(d.dgi + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
+  stf16(d.dgi + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
+  stf16(d.dgi + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dan);
+  stf16(d.dgh + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
+  stf16(d.dgh + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
+  stf16(d.dgh + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dgn);
   if (d.dgi_p) {
     const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
@@ -385,13 +398,13 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   __syncwarp();
   tc_fence_after();
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-  float* prow = d.parts_out + ((long)c * bpad + b) * H;
+  float* pbase = d.parts_out + (long)c * H * bpad + b;                 // part c, feature-major [H][B_pad]
   const int hh = H / 2;
   for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
     float v[16];
     tmem_ld16(taddr + c0, v);
     tmem_ld_wait();
-    st16(prow + c0, v);
+    stf16(pbase + (long)c0 * bpad, bpad, v);
   }
   tc_fence_before();
   __syncthreads();

@@ -35,8 +35,9 @@ struct GemmSeg {
 struct GemmArgs {
   GemmSeg a[4], b[4];   // A: [M, K] , B: [N, K]; K = concatenation of up to 4 segments (A and B split independently)
   int M, N;             // logical output extent (rows >= M / cols >= N are masked)
-  float* C;             // fp32 row-major
+  float* C;             // fp32 row-major (C[m*ldc + n]) or, with c_fm, feature-major (C[n*ldc + m])
   long ldc;
+  int c_fm;
   const float* bias;    // [N] or nullptr (added only by split 0)
   int atomic;           // 1: red.add into C (split-K / accumulation), 0: plain store
   int splits;           // gridDim.z
@@ -44,17 +45,22 @@ struct GemmArgs {
 void launch_gemm_p16(const GemmArgs& g, cudaStream_t st);
 
 // ---- gru.cu --------------------------------------------------------------------------------------
+// fp32 interchange arrays of the step kernels are FEATURE-MAJOR: element (feature f, row r) lives at base + f*ld + r with
+// r = slot*B_pad + b.  A TMEM lane is a batch row, so for a fixed feature the 32 lanes of a warp touch 128 contiguous bytes.
 struct GruDirFwd {
   const void* w_p;        // P16 (RB=96) W_hh slices: [H/32][KC][2][96x64], slice rows = r,z,n gates of 32 units
   const float* b_hn;      // [H] hidden bias of the n gate (b_hr, b_hz are folded into gi)
-  const float* gi;        // input projections incl. biases; row(b,t) = gi + (b*gi_bs + t*gi_ts) * gi_pitch, gates at 0,H,2H
-  long gi_bs, gi_ts, gi_pitch;
+  const float* gi;        // input projections incl. biases, feature-major [3H][gi_ld]; row of (b, t) = b*gi_bs + t*gi_ts
+  long gi_ld, gi_bs, gi_ts;
   int t;                  // time index of this step for this direction
   const void* h_in_p;     // P16 (RB=128) [tiles][KC][2][128x64]
-  const float* h_in;      // fp32 [B_pad][H]
+  const float* h_in;      // fp32 feature-major [H][h_in_ld], already offset to the slot
+  long h_in_ld;
   void* h_out_p;          // P16 like h_in_p
-  float* h_out;           // fp32 [B_pad][H]
-  float* sv_r; float* sv_z; float* sv_n; float* sv_ghn;   // saved gates for BPTT, each fp32 [B_pad][H] slot of this t (or nullptr)
+  float* h_out;           // fp32 feature-major [H][h_out_ld], already offset to the slot
+  long h_out_ld;
+  float* sv_r; float* sv_z; float* sv_n; float* sv_ghn;   // saved gates for BPTT, feature-major [H][sv_ld] at this t's slot (or nullptr)
+  long sv_ld;
 };
 struct GruFwdArgs {
   GruDirFwd d[2];
@@ -66,15 +72,19 @@ void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
 
 struct GruDirBwd {
   const void* wT_p;       // P16 (RB=128) [H/32 slices][rb: H_pad/128][KC=2][2][128x64]: B[n=u, k=g*32+j] = W_hh[g*H+32c+j, u]
-  const float* parts;     // incoming dh pieces: part p, row b at parts + p*parts_stride + b*parts_pitch (H wide); their sum is
-  int n_parts;            //   the dh flowing into this step
-  long parts_stride, parts_pitch;
-  const float* dout;      // upstream gradient of this step's output: row b at dout + b*dout_pitch (H wide) or nullptr
-  long dout_pitch;
-  const float* sv_r; const float* sv_z; const float* sv_n; const float* sv_ghn; const float* h_prev;   // [B_pad][H] slots of this t
-  float* parts_out;       // [H/32 + 1][B_pad][H]: slice partial sums of dgh @ W_hh, last slot = carry dh*z
-  float* dgi;             // [B_pad][3H] slot of this t (dgi_r, dgi_z, dgi_n)
-  float* dgh;             // [B_pad][3H] slot of this t (dgi_r, dgi_z, dgi_n * r)
+  const float* parts;     // incoming dh pieces, feature-major: part p, unit u, row b at parts + p*parts_stride + u*parts_ld + b;
+  int n_parts;            //   their sum is the dh flowing into this step
+  long parts_stride, parts_ld;
+  const float* dout;      // upstream gradient of this step's output, feature-major [H][dout_ld] at this t's slot, or nullptr
+  long dout_ld;
+  const float* sv_r; const float* sv_z; const float* sv_n; const float* sv_ghn;   // [H][sv_ld] at this t's slot
+  long sv_ld;
+  const float* h_prev;    // [H][h_prev_ld]
+  long h_prev_ld;
+  float* parts_out;       // [H/32 + 1][H][B_pad]: slice partial sums of dgh @ W_hh, last slot = carry dh*z
+  float* dgi;             // feature-major [3H][dg_ld] at this t's slot (dgi_r, dgi_z, dgi_n)
+  float* dgh;             // same layout (dgi_r, dgi_z, dgi_n * r)
+  long dg_ld;
   void* dgi_p;            // optional P16 (RB=128) A-operand copy of dgi for the dx GEMM: [tiles][KC3H][2][128x64] slot of this t
 };
 struct GruBwdArgs {

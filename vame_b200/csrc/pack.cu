@@ -125,7 +125,7 @@ void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1
 // ------------------------------------------------------------------------------------------------
 // h0 preparation: src is a flat fp32 buffer viewed as [D][B][H] (for the decoder this is the raw
 // reinterpretation of the (B, 2H) latent_to_hidden output, vame/model/rnn_model.py:104,137); src == nullptr -> zeros.
-// Writes fp32 [D][B_pad][H] and packed P16 [D][tiles][KC][2][128x64].
+// Writes fp32 feature-major [D][H][B_pad] and packed P16 [D][tiles][KC][2][128x64].
 // ------------------------------------------------------------------------------------------------
 __global__ void h0_prepare_kernel(const float* __restrict__ src, int D, int B, int B_pad, int H, float* __restrict__ h32,
                                   __nv_bfloat16* __restrict__ hp) {
@@ -142,11 +142,10 @@ __global__ void h0_prepare_kernel(const float* __restrict__ src, int D, int B, i
       const int k = kbase + i;
       v[i] = (src && b < B && k < H) ? src[((long)d * B + b) * H + k] : 0.f;
     }
-    if (h32 && kbase < H) {
-      float* o = h32 + ((long)d * B_pad + b) * H + kbase;
+    if (h32 && kbase < H) {              // feature-major [D][H][B_pad]
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (kbase + i < H) o[i] = v[i];
+        if (kbase + i < H) h32[((long)d * H + kbase + i) * B_pad + b] = v[i];
     }
     uint4 hi, lo;
     split8(v, hi, lo);

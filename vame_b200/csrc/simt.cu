@@ -273,31 +273,58 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, long rows, i
   atomicAdd(out + n, s);
 }
 
-// out[b, :] = sum_t X[t][b][:]   (X: [T][rows][C])
-__global__ void timesum_kernel(const float* __restrict__ X, int T, long rowsC, float* __restrict__ out) {
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < rowsC; idx += (long)gridDim.x * blockDim.x) {
+// feature-major time reduction: out[c*Bp + b] = sum_t X[c*ld + t*Bp + b]
+__global__ void timesum_fm_kernel(const float* __restrict__ X, long ld, int T, int Bp, int C, float* __restrict__ out) {
+  const long total = (long)C * Bp;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx % Bp);
+    const long c = idx / Bp;
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += X[(long)t * rowsC + idx];
+    for (int t = 0; t < T; ++t) s += X[c * ld + (long)t * Bp + b];
     out[idx] = s;
   }
 }
 
-// sum of the dh pieces left by the last BPTT step -> dense dh0; optionally written in the UNPADDED [D][B][H] order
-// (the flat buffer that the reference's hidden.view(2,B,H) aliases, rnn_model.py:104)
+// row sums of a feature-major matrix (bias gradients): out[f] += sum_r X[f*ld + r]; one warp per feature
+__global__ void rowsum_fm_kernel(const float* __restrict__ X, long ld, long ncols, int nfeat, float* __restrict__ out) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= nfeat) return;
+  const float* row = X + (long)f * ld;
+  float s = 0.f;
+  for (long r = threadIdx.x & 31; r < ncols; r += 32) s += row[r];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out + f, s);
+}
+
+// feature-major [H][ld] -> row-major dst[b*dst_ld + u] (b < B)
+__global__ void fm_to_rows_kernel(const float* __restrict__ src, long ld, int H, int B, float* __restrict__ dst, long dst_ld) {
+  __shared__ float tile[32][33];
+  const int u0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  for (int i = ty; i < 32; i += 8) {
+    const int u = u0 + i, b = b0 + tx;
+    tile[i][tx] = (u < H && b < B) ? src[(long)u * ld + b] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int b = b0 + i, u = u0 + tx;
+    if (b < B && u < H) dst[(long)b * dst_ld + u] = tile[tx][i];
+  }
+}
+
+// sum of the dh pieces left by the last BPTT step (feature-major parts [p][H][B_pad]) -> dh0 written in the UNPADDED
+// [D][B][H] order, i.e. the flat buffer that the reference's hidden.view(2,B,H) aliases (rnn_model.py:104)
 __global__ void parts_reduce_kernel(const float* __restrict__ parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H,
-                                    float* __restrict__ out, int unpadded) {
-  const long total = (long)D * B_pad * H;
+                                    float* __restrict__ out) {
+  const long total = (long)D * H * B_pad;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % H);
-    const long r = idx / H;
-    const int b = (int)(r % B_pad), d = (int)(r / B_pad);
+    const int b = (int)(idx % B_pad);
+    const long r = idx / B_pad;
+    const int u = (int)(r % H), d = (int)(r / H);
+    if (b >= B) continue;
     float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += parts[d * dir_stride + ((long)p * B_pad + b) * H + k];
-    if (unpadded) {
-      if (b < B) out[((long)d * B + b) * H + k] = s;
-    } else {
-      out[idx] = s;
-    }
+    for (int p = 0; p < n_parts; ++p) s += parts[d * dir_stride + ((long)p * H + u) * B_pad + b];
+    out[((long)d * B + b) * H + u] = s;
   }
 }
 
@@ -404,14 +431,21 @@ void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaSt
   count_launch();
   colsum_kernel<<<dim3((N + 127) / 128, ysplit), 128, 0, st>>>(X, ld, rows, N, out);
 }
-void launch_timesum(const float* X, int T, long rowsC, float* out, cudaStream_t st) {
+void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out, cudaStream_t st) {
   count_launch();
-  timesum_kernel<<<grid_for(rowsC, 256), 256, 0, st>>>(X, T, rowsC, out);
+  timesum_fm_kernel<<<grid_for((long)C * Bp, 256), 256, 0, st>>>(X, ld, T, Bp, C, out);
 }
-void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, int unpadded,
-                         cudaStream_t st) {
+void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st) {
   count_launch();
-  parts_reduce_kernel<<<grid_for((long)D * B_pad * H, 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out, unpadded);
+  rowsum_fm_kernel<<<(nfeat + 7) / 8, 256, 0, st>>>(X, ld, ncols, nfeat, out);
+}
+void launch_fm_to_rows(const float* src, long ld, int H, int B, float* dst, long dst_ld, cudaStream_t st) {
+  count_launch();
+  fm_to_rows_kernel<<<dim3((B + 31) / 32, (H + 31) / 32), 256, 0, st>>>(src, ld, H, B, dst, dst_ld);
+}
+void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, cudaStream_t st) {
+  count_launch();
+  parts_reduce_kernel<<<grid_for((long)D * B_pad * H, 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out);
 }
 void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
                  float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st) {

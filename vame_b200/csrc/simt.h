@@ -31,9 +31,10 @@ void launch_mse(const float* pred, long ldp, const float* target, int rows, int 
 void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
                           float* dz, double* acc, cudaStream_t st);
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st);
-void launch_timesum(const float* X, int T, long rowsC, float* out, cudaStream_t st);
-void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, int unpadded,
-                         cudaStream_t st);
+void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out, cudaStream_t st);
+void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st);
+void launch_fm_to_rows(const float* src, long ld, int H, int B, float* dst, long dst_ld, cudaStream_t st);
+void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, cudaStream_t st);
 // step_dev: device int32 step counter (incremented by the kernel chain); lr from hyper[HY_LR] when hyper != nullptr
 void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
                  float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st);
