@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvame_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math" if os.environ.get("VAME_FAST_MATH") else "-DVAME_ACCURATE_MATH=1"]
+              "-Xcompiler", "-fPIC"] + (["-DVAME_ACCURATE_MATH=1"] if os.environ.get("VAME_ACCURATE_MATH") else [])
 
 
 def _sources():

@@ -284,6 +284,25 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
                           cudaStream_t st) {
   const int H = L.H;
   zero_p16_padding(L, tiles, true, st);
+  if (g_opt_persistent) {                       // one cluster kernel for the whole sweep
+    GruSeqFwdArgs a{};
+    a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
+    const long Bp = (long)tiles * 128;
+    for (int d = 0; d < 2; ++d) {
+      GruSeqDirFwd& D = a.d[d];
+      D.w_p = W.whh_p[d]; D.b_hn = d == 0 ? b_hn0 : b_hn1;
+      D.gi = L.gi + (size_t)d * 3 * H * L.gi_ld; D.gi_ld = L.gi_ld; D.gi_bs = L.gi_bs; D.gi_ts = L.gi_ts;
+      D.h0 = L.h0[d]; D.h0_ld = Bp; D.h0_p = L.h0_p[d];
+      D.out = L.out[d]; D.out_ld = (long)L.out_slots * Bp; D.out_slots = L.out_slots;
+      D.out_p = L.out_p[d]; D.out_p_slots = L.out_p_slots;
+      D.out_p_slot_elems = (long)tiles * nkc_of(H) * (long)p16_tile_elems(128);
+      for (int i = 0; i < 4; ++i) D.sv[i] = save ? L.sv[d][i] : nullptr;
+      D.sv_ld = (long)L.steps * Bp;
+      D.reverse = d;
+    }
+    launch_gru_seq_fwd(a, st);
+    return;
+  }
   const size_t slotp = (size_t)tiles * nkc_of(H) * p16_tile_elems(128);
   for (int s = 0; s < L.steps; ++s) {
     GruFwdArgs a{};
@@ -337,6 +356,27 @@ static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
   const size_t slotf = (size_t)Bp * H;
   const size_t pslot = (size_t)(nsl + 1) * slotf;
   zero_p16_padding(L, tiles, false, st);
+  if (g_opt_persistent) {                       // one cluster kernel for the whole BPTT sweep
+    GruSeqBwdArgs a{};
+    a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
+    const long seq_ld = (long)L.steps * Bp;
+    for (int d = 0; d < 2; ++d) {
+      GruSeqDirBwd& D = a.d[d];
+      D.wT_p = W.whhT_p[d];
+      D.dh_last = d == 0 ? dhl0 : dhl1; D.dh_last_ld = dhl_ld;
+      D.dout = d == 0 ? dout0 : dout1; D.dout_ld = dout_ld;
+      for (int i = 0; i < 4; ++i) D.sv[i] = L.sv[d][i];
+      D.sv_ld = seq_ld;
+      D.out = L.out[d]; D.out_ld = seq_ld;
+      D.h0 = L.h0[d]; D.h0_ld = Bp;
+      D.parts = L.parts[d];
+      D.dgi = L.dgi[d]; D.dgh = L.dgh[d]; D.dg_ld = seq_ld;
+      D.dgi_p = L.dgi_p[d]; D.dgi_p_slot_elems = (long)tiles * nkc3 * (long)p16_tile_elems(128);
+      D.reverse = d;
+    }
+    launch_gru_seq_bwd(a, st);
+    return;
+  }
   for (int s = 0; s < L.steps; ++s) {
     GruBwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;

@@ -9,6 +9,7 @@ thread_local char g_err[512] = {0};
 long g_launch_count = 0;
 int g_opt_pdl = 1;
 int g_opt_streams = 1;
+int g_opt_persistent = 1;
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -29,6 +30,10 @@ int vame_set_option(const char* name, int value) {
   VB_REQUIRE(name, "vame_set_option: null name");
   if (strcmp(name, "pdl") == 0) {
     vb::g_opt_pdl = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "persistent") == 0) {
+    vb::g_opt_persistent = value;
     return 0;
   }
   if (strcmp(name, "streams") == 0) {

@@ -25,8 +25,10 @@ namespace vb {
 __device__ __forceinline__ float gate_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gate_tanh(float x) { return tanhf(x); }
 #else
-__device__ __forceinline__ float gate_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gate_tanh(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
+// default: MUFU-based gates (ex2.approx + rcp.approx, ~2 ulp each).  The absolute error (<3e-7) is far inside the
+// stated parity tolerances and keeps the serial gate epilogue short; -DVAME_ACCURATE_MATH selects expf/tanhf.
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 #endif
 
 __device__ __forceinline__ void ld16(const float* p, float* v) {
@@ -254,6 +256,178 @@ void launch_gru_step_fwd(const GruFwdArgs& a_in, cudaStream_t st) {
 }
 
 // =================================================================================================
+// persistent forward sweep: all `steps` time steps of one (batch tile, direction) in ONE kernel.
+// A thread-block cluster of H/32 CTAs owns the tile; CTA c keeps its 96 x H slice of W_hh in shared memory for the
+// whole sweep, TMEM is allocated once, h_{t-1} of the CTA's own units stays in registers.  After each step every CTA
+// publishes its 128 x 32 slice of h_t (fp32 + P16) to global memory, the cluster synchronises (barrier.cluster with
+// release/acquire + generic->async proxy fences), and each CTA re-fetches the full 128 x H tile with the TMA engine.
+// This removes the per-step kernel boundary (launch gap + prologue + teardown, ~4 us of the ~11 us step).
+// =================================================================================================
+__global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int H = a.H, nkc = (H + KCHUNK - 1) / KCHUNK;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + (size_t)nkc * F_WTILE;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + (size_t)nkc * F_ATILE);
+  uint64_t* abar = wbar + 4;
+  uint64_t* done = abar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int c = blockIdx.x, tile = blockIdx.y;          // cluster = all CTAs with the same (y, z): c is the cluster rank
+  const GruSeqDirFwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const long Bp = (long)a.tiles * 128;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&wbar[i], 1);
+      mbar_init(&abar[i], 1);
+    }
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
+      for (int kc = 0; kc < nkc; ++kc) {
+        mbar_expect_tx(&wbar[kc], F_WTILE);
+        bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+      }
+    }
+    __syncwarp();
+  }
+  const int r_in = q * 32 + lane;
+  const long b = (long)tile * 128 + r_in;
+  const int j0 = half * 16, u0 = c * 32 + j0;
+  float bhn[16], hprev[16];
+  ld16(d.b_hn + u0, bhn);
+  ldf16(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hprev);
+  const uint32_t idesc = make_idesc_bf16(128, 96);
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+
+  for (int s = 0; s < a.steps; ++s) {
+    const int t = d.reverse ? a.steps - 1 - s : s;
+    const int so = (d.out_slots == a.steps) ? t : (s & 1);
+    const int sp = (d.out_p_slots == a.steps) ? t : (s & 1);
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    const int sp_prev = (d.out_p_slots == a.steps) ? tprev : ((s - 1) & 1);
+    // input projections of this step (independent of the recurrence): issue before waiting for the cluster
+    float gir[16], giz[16], gin[16];
+    {
+      const float* gi_row = d.gi + (b * d.gi_bs + (long)t * d.gi_ts);
+      ldf16(gi_row + (long)u0 * d.gi_ld, d.gi_ld, gir);
+      ldf16(gi_row + (long)(H + u0) * d.gi_ld, d.gi_ld, giz);
+      ldf16(gi_row + (long)(2 * H + u0) * d.gi_ld, d.gi_ld, gin);
+    }
+    if (s > 0) cluster_wait_acquire();          // every CTA of the cluster has published its slice of h_{t-1}
+    const uint32_t ph = s & 1;
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();
+        const __nv_bfloat16* hp = (s == 0 ? reinterpret_cast<const __nv_bfloat16*>(d.h0_p)
+                                          : reinterpret_cast<const __nv_bfloat16*>(d.out_p) + (size_t)sp_prev * d.out_p_slot_elems) +
+                                  (size_t)tile * nkc * p16_tile_elems(128);
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_expect_tx(&abar[kc], F_ATILE);
+          bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
+        }
+        const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
+        for (int kc = 0; kc < nkc; ++kc) {
+          if (s == 0) mbar_wait(&wbar[kc], 0);
+          mbar_wait(&abar[kc], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
+          const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ko = ks * 2 * ATOM_BYTES;
+            const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
+            const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+            umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+            umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+            umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+          }
+        }
+        umma_commit(done);
+      }
+      __syncwarp();
+    }
+    mbar_wait(done, ph);
+    __syncwarp();
+    tc_fence_after();
+    float ar[16], az[16], an[16];
+    tmem_ld16(taddr + j0, ar);
+    tmem_ld16(taddr + 32 + j0, az);
+    tmem_ld16(taddr + 64 + j0, an);
+    tmem_ld_wait();
+    float ghn[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float r = gate_sigmoid(gir[i] + ar[i]);
+      const float z = gate_sigmoid(giz[i] + az[i]);
+      ghn[i] = an[i] + bhn[i];
+      const float n = gate_tanh(gin[i] + r * ghn[i]);
+      hprev[i] = (1.0f - z) * n + z * hprev[i];
+      ar[i] = r; az[i] = z; an[i] = n;
+    }
+    // publish: P16 slice first (it is what the other CTAs of the cluster wait for), then the fp32 / BPTT copies
+    {
+      const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
+      __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                          ((size_t)tile * nkc + kc) * p16_tile_elems(128);
+      st16_p16(tl, 128, r_in, kk, hprev);
+    }
+    tc_fence_before();                           // TMEM reads of this step are ordered before the next step's MMAs
+    if (s + 1 < a.steps) {
+      __threadfence();
+      fence_proxy_async_all();
+      cluster_arrive_release();
+    }
+    stf16(d.out + (long)u0 * d.out_ld + (long)so * Bp + b, d.out_ld, hprev);
+    if (d.sv[0]) {
+      const long o = (long)u0 * d.sv_ld + (long)t * Bp + b;
+      stf16(d.sv[0] + o, d.sv_ld, ar);
+      stf16(d.sv[1] + o, d.sv_ld, az);
+      stf16(d.sv[2] + o, d.sv_ld, an);
+      stf16(d.sv[3] + o, d.sv_ld, ghn);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
+  const int nkc = (a.H + KCHUNK - 1) / KCHUNK;
+  const size_t smem = (size_t)nkc * (F_WTILE + F_ATILE) + 256;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(a.H / 32, a.tiles, a.ndir);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.H / 32;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  cudaLaunchKernelEx(&cfg, gru_seq_fwd_kernel, a);
+}
+
+// =================================================================================================
 // backward step
 // =================================================================================================
 constexpr int B_APLANE = 128 * KCHUNK * 2;        // 16 KB: one plane of a 128-row K chunk
@@ -409,6 +583,204 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+// =================================================================================================
+// persistent backward sweep (BPTT over all steps in one cluster kernel).  CTA c owns hidden units [32c, 32c+32): it keeps
+// its 96 x H slice of W_hh (as the [H, 96] B operand) in shared memory, the carry dh*z of its own units in registers, and
+// exchanges the H/32 partial products dgh_c W_hh[c-rows, :] with the other CTAs of the cluster through global memory
+// (L2-coherent loads) between steps.
+// =================================================================================================
+__global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int H = a.H, nrb = (H + 127) / 128, nsl = H / 32;
+  const size_t wchunk = (size_t)nrb * 2 * B_APLANE;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + 2 * wchunk;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + 4 * B_APLANE);
+  uint64_t* done = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int c = blockIdx.x, tile = blockIdx.y;
+  const GruSeqDirBwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const uint32_t tmem_cols = (H <= 32) ? 32 : (H <= 64) ? 64 : (H <= 128) ? 128 : 256;
+  const long bpad = (long)a.tiles * 128;
+  const size_t slotf = (size_t)bpad * H, pslot = (size_t)(nsl + 1) * slotf;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
+      mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
+      for (int kc = 0; kc < 2; ++kc)
+        for (int rb = 0; rb < nrb; ++rb) {
+          const __nv_bfloat16* t = wp + ((size_t)rb * 2 + kc) * p16_tile_elems(128);
+          bulk_g2s(sW + kc * wchunk + (size_t)rb * B_APLANE, t, B_APLANE, wbar);
+          bulk_g2s(sW + kc * wchunk + (size_t)(nrb + rb) * B_APLANE, t + 128 * KCHUNK, B_APLANE, wbar);
+        }
+    }
+    __syncwarp();
+  }
+  const int r_in = q * 32 + lane;
+  const long b = (long)tile * 128 + r_in;
+  const int j0 = half * 16, u0 = c * 32 + j0;
+  const uint32_t idesc = make_idesc_bf16(128, H);
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  const int hh = H / 2;
+  float carry[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) carry[i] = 0.f;
+  if (d.dh_last) ldf16(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
+
+  for (int s = 0; s < a.steps; ++s) {
+    const int t = d.reverse ? s : a.steps - 1 - s;                       // BPTT order = reverse of the forward order
+    const bool first_fwd = d.reverse ? (t == a.steps - 1) : (t == 0);
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    float r[16], z[16], n[16], ghn[16], hp[16], dh[16];
+    {
+      const long so = (long)u0 * d.sv_ld + (long)t * bpad + b;
+      ldf16(d.sv[0] + so, d.sv_ld, r);
+      ldf16(d.sv[1] + so, d.sv_ld, z);
+      ldf16(d.sv[2] + so, d.sv_ld, n);
+      ldf16(d.sv[3] + so, d.sv_ld, ghn);
+    }
+    if (first_fwd) ldf16(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hp);
+    else ldf16(d.out + (long)u0 * d.out_ld + (long)tprev * bpad + b, d.out_ld, hp);
+    if (d.dout) ldf16(d.dout + (long)u0 * d.dout_ld + (long)t * bpad + b, d.dout_ld, dh);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dh[i] += carry[i];
+    if (s > 0) {
+      cluster_wait_acquire();                                            // all partial products of the previous step are published
+      const float* pin = d.parts + ((s - 1) & 1) * pslot + (long)u0 * bpad + b;
+      for (int p = 0; p < nsl; ++p) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dh[i] += ld_cg(pin + (long)p * slotf + (long)i * bpad);
+      }
+    }
+    float dar[16], daz[16], dan[16], dgn[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float dn = dh[i] * (1.0f - z[i]);
+      const float dz = dh[i] * (hp[i] - n[i]);
+      dan[i] = dn * (1.0f - n[i] * n[i]);
+      daz[i] = dz * z[i] * (1.0f - z[i]);
+      dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
+      dgn[i] = dan[i] * r[i];
+      carry[i] = dh[i] * z[i];
+    }
+    {
+      __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(sA);
+      __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sA + 2 * B_APLANE);
+      st16_p16(a0, 128, r_in, j0, dar);
+      st16_p16(a0, 128, r_in, 32 + j0, daz);
+      st16_p16(a1, 128, r_in, j0, dgn);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    const uint32_t ph = s & 1;
+    if (warp == 0) {
+      if (lane == 0) {
+        if (s == 0) mbar_wait(wbar, 0);
+        tc_fence_after();
+        for (int kc = 0; kc < 2; ++kc) {
+          const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
+          const uint32_t sw = smem_u32(sW + kc * wchunk);
+          const uint32_t wplane = (uint32_t)nrb * B_APLANE;
+          const int ksteps = kc == 0 ? 4 : 2;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ko = ks * 2 * ATOM_BYTES;
+            const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
+            const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
+            umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
+            umma_bf16(tmem, a_hi, w_lo, idesc, 1);
+            umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+          }
+        }
+        umma_commit(done);
+      }
+      __syncwarp();
+    }
+    // outputs that do not need the MMA
+    {
+      const long o = (long)t * bpad + b;
+      stf16(d.dgi + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stf16(d.dgi + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stf16(d.dgi + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dan);
+      stf16(d.dgh + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stf16(d.dgh + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stf16(d.dgh + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dgn);
+    }
+    if (d.dgi_p) {
+      const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
+                            (size_t)tile * nkc3 * p16_tile_elems(128);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int k = g * H + u0;
+        st16_p16(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+      }
+    }
+    float* pout = d.parts + (s & 1) * pslot;
+    if (s == a.steps - 1) stf16(pout + ((long)nsl * H + u0) * bpad + b, bpad, carry);   // final carry -> dh0 reduction
+
+    mbar_wait(done, ph);
+    __syncwarp();
+    tc_fence_after();
+    float* pbase = pout + (long)c * H * bpad + b;
+    for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
+      float v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      stf16(pbase + (long)c0 * bpad, bpad, v);
+    }
+    tc_fence_before();
+    if (s + 1 < a.steps) {
+      __threadfence();
+      cluster_arrive_release();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
+  const int nrb = (a.H + 127) / 128;
+  const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * B_APLANE + 256;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(a.H / 32, a.tiles, a.ndir);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.H / 32;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel, a);
 }
 
 void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st) {

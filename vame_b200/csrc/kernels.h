@@ -9,7 +9,8 @@ namespace vb {
 extern long g_launch_count;
 extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
 extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
-extern int g_opt_streams;   // 1: run independent branches of a step on internal side streams
+extern int g_opt_streams;
+extern int g_opt_persistent; // 1: run each recurrent sweep as one persistent cluster kernel instead of one kernel per step   // 1: run independent branches of a step on internal side streams
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 // ---- pack.cu -------------------------------------------------------------------------------------
@@ -69,6 +70,41 @@ struct GruFwdArgs {
   unsigned long long* dbg;   // optional device buffer for %globaltimer stamps (filled in by the launcher)
 };
 void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
+
+// ---- persistent (whole-sweep) forward kernel: one thread-block cluster of H/32 CTAs per (batch tile, direction) ----
+struct GruSeqDirFwd {
+  const void* w_p; const float* b_hn;
+  const float* gi; long gi_ld, gi_bs, gi_ts;
+  const float* h0; long h0_ld; const void* h0_p;       // initial state: fp32 feature-major + P16
+  float* out; long out_ld; int out_slots;               // fp32 h sequence, slot offset = slot*B_pad (slots = steps or 2)
+  void* out_p; int out_p_slots; long out_p_slot_elems;  // P16 h sequence
+  float* sv[4]; long sv_ld;                             // saved gates r,z,n,ghn (slot t) or nullptr
+  int reverse;                                          // 1: processes t = steps-1 .. 0
+};
+struct GruSeqFwdArgs {
+  GruSeqDirFwd d[2];
+  int ndir, H, tiles, steps;
+};
+void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
+
+// ---- persistent (whole-sweep) backward kernel, same cluster decomposition ----
+struct GruSeqDirBwd {
+  const void* wT_p;
+  const float* dh_last; long dh_last_ld;       // gradient of the final hidden state, feature-major [H][ld], or nullptr
+  const float* dout; long dout_ld;             // per-step output gradients, feature-major [H][dout_ld] (slot t at + t*B_pad) or nullptr
+  const float* sv[4]; long sv_ld;              // saved gates r,z,n,ghn, [H][sv_ld]
+  const float* out; long out_ld;               // forward h sequence [H][out_ld] (h_prev of step t = slot t -/+ 1)
+  const float* h0; long h0_ld;                 // initial state [H][h0_ld]
+  float* parts;                                // [2 slots][H/32 + 1][H][B_pad] partial sums exchanged between the CTAs
+  float* dgi; float* dgh; long dg_ld;          // outputs, feature-major [3H][dg_ld] (slot t at + t*B_pad)
+  void* dgi_p; long dgi_p_slot_elems;          // optional P16 copy of dgi per t
+  int reverse;                                 // direction of the FORWARD recurrence (0: t ascending) -> BPTT runs the other way
+};
+struct GruSeqBwdArgs {
+  GruSeqDirBwd d[2];
+  int ndir, H, tiles, steps;
+};
+void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 
 struct GruDirBwd {
   const void* wT_p;       // P16 (RB=128) [H/32 slices][rb: H_pad/128][KC=2][2][128x64]: B[n=u, k=g*32+j] = W_hh[g*H+32c+j, u]
