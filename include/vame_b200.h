@@ -62,6 +62,8 @@ typedef struct {
   float beta;            /* used when hyper == NULL */
   float kl_weight;       /* used when hyper == NULL */
   int with_future;       /* include the future-reconstruction term (train) or not (test, rnn_vae.py:186-190) */
+  int defer_prior_join;  /* 1: the k-means-prior branch (internal side stream) is joined by the following vame_backward
+                            instead of by vame_loss; losses_out is then valid only after that vame_backward */
 } vame_loss_cfg;
 
 /* Number of parameter tensors (44 with the future decoder, 32 without) and their placement in the flat fp32 buffer.

@@ -81,7 +81,8 @@ def child(mode, pdl, workload, streams=1, persistent=1):
         torch.cuda.synchronize()
         lib.vame_set_debug_buffer(None)
         st = dbg.cpu().tolist()
-        names = ["start", "prologue done", "after pdl_wait", "first chunk landed", "mma issued", "mma done", "epilogue+stores", "end"]
+        names = ["start", "prologue done", "after pdl_wait", "first chunk landed", "mma issued", "mma done", "epilogue+stores", "end",
+                 "tmem loaded", "math done", "h stores issued"]
         print("[%s pdl=%d] fwd step kernel timeline (ns since start of last launch): " % (mode, pdl) +
               ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
         e0.record()
@@ -104,7 +105,7 @@ if __name__ == "__main__":
               int(sys.argv[6]) if len(sys.argv) > 6 else 1)
         sys.exit(0)
     workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    for mode, pdl, streams, pers in (("eager", 1, 1, 0), ("eager", 1, 1, 1), ("graph", 1, 1, 0), ("graph", 1, 1, 1)):
+    for mode, pdl, streams, pers in (("eager", 0, 1, 0), ("graph", 1, 1, 0)):
         print("##### variant mode=%s pdl=%d streams=%d persistent=%d" % (mode, pdl, streams, pers), flush=True)
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload, str(streams), str(pers)], timeout=150,

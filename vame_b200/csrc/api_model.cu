@@ -170,7 +170,7 @@ static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
 // with the latency-bound recurrent sweeps; fork/join are event edges, so the whole thing stays CUDA-graph capturable.
 // ================================================================================================
 struct Side {
-  cudaStream_t s[2];
+  cudaStream_t s[3];       // [0] future decoder, [1] weight-gradient work, [2] k-means prior
   cudaEvent_t ev[32];
   int nev;
 };
@@ -178,7 +178,7 @@ static Side& side() {
   static Side S{};
   static bool init = false;
   if (!init) {
-    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
     for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
     init = true;
   }
@@ -618,7 +618,7 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
   const bool with_fut = d->future_decoder && cfg->with_future;
   VB_REQUIRE(!with_fut || fut, "vame_loss: future target missing");
   const double nrec = (double)batch * T * F;
-  cudaStream_t sA = g_opt_streams ? side().s[0] : st;
+  cudaStream_t sA = g_opt_streams ? side().s[2] : st;   // the prior's own side stream
   edge(st, sA);
   launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
                        training ? w.dz_km : nullptr, w.acc, sA);
@@ -632,9 +632,17 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
     launch_mse(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f,
                training ? w.dec[1].dpred_tb : nullptr, w.acc, ACC_FUT, st);
   }
-  edge(sA, st);
-  launch_finalize_losses(w.acc, losses_out, cfg->mse_red_mean ? nrec : 1.0, cfg->mse_pred_mean ? nfut : 1.0, (double)batch * Z,
-                         cfg->beta, cfg->kl_weight, hyper, with_fut ? 1 : 0, st);
+  if (training && cfg->defer_prior_join && g_opt_streams) {
+    // the prior keeps running on sA while the caller's stream proceeds into vame_backward (which joins sA before the
+    // Lambda backward); the loss vector is finalised on sA once the MSE sums of the main stream are in
+    edge(st, sA);
+    launch_finalize_losses(w.acc, losses_out, cfg->mse_red_mean ? nrec : 1.0, cfg->mse_pred_mean ? nfut : 1.0, (double)batch * Z,
+                           cfg->beta, cfg->kl_weight, hyper, with_fut ? 1 : 0, sA);
+  } else {
+    edge(sA, st);
+    launch_finalize_losses(w.acc, losses_out, cfg->mse_red_mean ? nrec : 1.0, cfg->mse_pred_mean ? nfut : 1.0, (double)batch * Z,
+                           cfg->beta, cfg->kl_weight, hyper, with_fut ? 1 : 0, st);
+  }
   return check_launch("vame_loss");
 }
 
@@ -720,6 +728,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   }
 
   // ---- Lambda backward (main chain: dlin -> dhidden)
+  if (use_loss_grads && g_opt_streams) edge(side().s[2], st);   // k-means prior gradient (vame_loss may have left it running)
   {
     LambdaBwdArgs a{};
     a.dz[0] = use_loss_grads ? w.dz_km : nullptr;

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
     } else if (warp == 1) {
      if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = make_idesc_bf16(G_BM, G_BN);
+      const uint32_t idesc = make_idesc_bf16(G_BM, 2 * G_BN);          // one descriptor spans [B_hi ; B_lo]
       for (int i = 0; i < nk; ++i) {
         const int s = i % G_STAGES;
         const uint32_t ph = (i / G_STAGES) & 1;
@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
 #pragma unroll
         for (int ks = 0; ks < KCHUNK / 16; ++ks) {
           const uint32_t ko = ks * 2 * ATOM_BYTES;                   // 16 k-elements = 2 atoms
+          // D[:, 0:128] += a * b_hi, D[:, 128:256] += a * b_lo (summed in the epilogue); a tcgen05.mma costs ~100 cycles
+          // for any N <= 128 and 128 cycles for N = 256 (tools/bench_mma), so two N=256 MMAs beat three N=128 ones
           const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + plane + ko);
-          const uint64_t b_hi = make_desc(sb + ko), b_lo = make_desc(sb + plane + ko);
-          umma_bf16(tmem, a_lo, b_hi, idesc, (i | ks) != 0);
-          umma_bf16(tmem, a_hi, b_lo, idesc, 1);
-          umma_bf16(tmem, a_hi, b_hi, idesc, 1);
+          const uint64_t b_hl = make_desc(sb + ko);
+          umma_bf16(tmem, a_lo, b_hl, idesc, (i | ks) != 0);
+          umma_bf16(tmem, a_hi, b_hl, idesc, 1);
         }
         umma_commit(&empty[s]);          // frees the smem stage once these MMAs retire
       }
@@ -106,9 +107,12 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < G_BN; c0 += 16) {
-      float v[16];
+      float v[16], v2[16];
       tmem_ld16(taddr + c0, v);
+      tmem_ld16(taddr + G_BN + c0, v2);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += v2[j];
       const int col = nb * G_BN + c0;
       if (g.c_fm) {                       // feature-major output: C[n*ldc + m]; lanes (= rows m) are contiguous -> coalesced
         if (row < g.M) {
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 void launch_gemm_p16(const GemmArgs& g, cudaStream_t st) {

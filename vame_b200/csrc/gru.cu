@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
         mbar_expect_tx(&abar[kc], F_ATILE);
         bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
       }
-      const uint32_t idesc = make_idesc_bf16(128, 96);
-      const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
+      const uint32_t idesc = make_idesc_bf16(128, 192);
+      const uint32_t aplane = 128 * KCHUNK * 2;
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_wait(&wbar[kc], 0);
         mbar_wait(&abar[kc], 0);
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
         const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t ko = ks * 2 * ATOM_BYTES;
+          // one descriptor covers [W_hi ; W_lo] (192 rows): D[:, 0:96] += a*w_hi, D[:, 96:192] += a*w_lo
           const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
-          const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-          umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-          umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-          umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+          const uint64_t w_hl = make_desc(sw + ko);
+          umma_bf16(tmem, a_lo, w_hl, idesc, (kc | ks) != 0);
+          umma_bf16(tmem, a_hi, w_hl, idesc, 1);
         }
       }
       umma_commit(done);
@@ -187,10 +187,19 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   tc_fence_after();
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
   float ar[16], az[16], an[16];
-  tmem_ld16(taddr + j0, ar);
-  tmem_ld16(taddr + 32 + j0, az);
-  tmem_ld16(taddr + 64 + j0, an);
-  tmem_ld_wait();
+  {
+    float br[16], bz[16], bn[16];                 // columns 96.. hold the (* w_lo) products
+    tmem_ld16(taddr + j0, ar);
+    tmem_ld16(taddr + 32 + j0, az);
+    tmem_ld16(taddr + 64 + j0, an);
+    tmem_ld16(taddr + 96 + j0, br);
+    tmem_ld16(taddr + 128 + j0, bz);
+    tmem_ld16(taddr + 160 + j0, bn);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
+  }
+  DBG_STAMP(8);
 
   float hn[16];
 #pragma unroll
@@ -202,12 +211,14 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     hn[i] = (1.0f - z) * n + z * hprev[i];
     ar[i] = r; az[i] = z; an[i] = n; bhn[i] = ghn;
   }
+  DBG_STAMP(9);
   stf16(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
   {
     const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
     st16_p16(t, 128, r_in, kk, hn);
   }
+  DBG_STAMP(10);
   if (d.sv_r) {
     const long so = (long)u0 * d.sv_ld + b;
     stf16(d.sv_r + so, d.sv_ld, ar);
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   DBG_STAMP(6);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
   DBG_STAMP(7);
 }
 
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
     mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
   float bhn[16], hprev[16];
   ld16(d.b_hn + u0, bhn);
   ldf16(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hprev);
-  const uint32_t idesc = make_idesc_bf16(128, 96);
+  const uint32_t idesc = make_idesc_bf16(128, 192);
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
 
   for (int s = 0; s < a.steps; ++s) {
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
           mbar_expect_tx(&abar[kc], F_ATILE);
           bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
         }
-        const uint32_t aplane = 128 * KCHUNK * 2, wplane = 96 * KCHUNK * 2;
+        const uint32_t aplane = 128 * KCHUNK * 2;
         for (int kc = 0; kc < nkc; ++kc) {
           if (s == 0) mbar_wait(&wbar[kc], 0);
           mbar_wait(&abar[kc], ph);
@@ -348,10 +359,9 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t ko = ks * 2 * ATOM_BYTES;
             const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
-            const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-            umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-            umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-            umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+            const uint64_t w_hl = make_desc(sw + ko);            // [W_hi ; W_lo], N = 192
+            umma_bf16(tmem, a_lo, w_hl, idesc, (kc | ks) != 0);
+            umma_bf16(tmem, a_hi, w_hl, idesc, 1);
           }
         }
         umma_commit(done);
@@ -362,10 +372,18 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
     __syncwarp();
     tc_fence_after();
     float ar[16], az[16], an[16];
-    tmem_ld16(taddr + j0, ar);
-    tmem_ld16(taddr + 32 + j0, az);
-    tmem_ld16(taddr + 64 + j0, an);
-    tmem_ld_wait();
+    {
+      float br[16], bz[16], bn[16];
+      tmem_ld16(taddr + j0, ar);
+      tmem_ld16(taddr + 32 + j0, az);
+      tmem_ld16(taddr + 64 + j0, an);
+      tmem_ld16(taddr + 96 + j0, br);
+      tmem_ld16(taddr + 128 + j0, bz);
+      tmem_ld16(taddr + 160 + j0, bn);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
+    }
     float ghn[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -385,9 +403,8 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
     }
     tc_fence_before();                           // TMEM reads of this step are ordered before the next step's MMAs
     if (s + 1 < a.steps) {
-      __threadfence();
-      fence_proxy_async_all();
-      cluster_arrive_release();
+      fence_proxy_async_all();                   // generic-proxy stores above -> visible to the peers' TMA (async proxy) reads
+      cluster_arrive_release();                  // release at cluster scope publishes them to the other CTAs
     }
     stf16(d.out + (long)u0 * d.out_ld + (long)so * Bp + b, d.out_ld, hprev);
     if (d.sv[0]) {
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 128);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
@@ -750,10 +767,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
       stf16(pbase + (long)c0 * bpad, bpad, v);
     }
     tc_fence_before();
-    if (s + 1 < a.steps) {
-      __threadfence();
-      cluster_arrive_release();
-    }
+    if (s + 1 < a.steps) cluster_arrive_release();   // release at cluster scope publishes the partial sums to the peers
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);

@@ -94,7 +94,7 @@ __global__ void mse_kernel(const float* __restrict__ pred, long ldp, const float
 // One CTA of 1024 threads.
 // -------------------------------------------------------------------------------------------------
 constexpr int CP_MAXZ = 64;
-constexpr size_t CP_SMEM = 2 * CP_MAXZ * (CP_MAXZ + 1) * 8 + (CP_MAXZ + CP_MAXZ + 1) * 8 + (CP_MAXZ * 2) * 4 + 64 * (CP_MAXZ + 1) * 4 + 64;
+constexpr size_t CP_SMEM = 4 * CP_MAXZ * (CP_MAXZ + 1) * 8 + (3 * CP_MAXZ + 1) * 8 + (CP_MAXZ * 2) * 4 + 64 * (CP_MAXZ + 1) * 4 + 64;
 
 __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __restrict__ z, int B, int Z, int kloss,
                                                                 double lmbda, double bsize, double gcoef,
@@ -108,13 +108,14 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
   typedef double Row[CP_MAXZ + 1];
   Row* A = reinterpret_cast<Row*>(cp_smem);
   Row* V = A + CP_MAXZ;
-  double* cs = reinterpret_cast<double*>(V + CP_MAXZ);
-  double* sn = cs + CP_MAXZ / 2;
-  double* ev = sn + CP_MAXZ / 2;
+  Row* A2 = V + CP_MAXZ;
+  Row* V2 = A2 + CP_MAXZ;
+  double* own = reinterpret_cast<double*>(V2 + CP_MAXZ);
+  double* oth = own + CP_MAXZ;
+  double* ev = oth + CP_MAXZ;
   double* offmax_p = ev + CP_MAXZ;
-  int* pp = reinterpret_cast<int*>(offmax_p + 1);
-  int* qq = pp + CP_MAXZ / 2;
-  int* order = qq + CP_MAXZ / 2;
+  int* part = reinterpret_cast<int*>(offmax_p + 1);
+  int* order = part + CP_MAXZ;
   typedef float ZRow[CP_MAXZ + 1];
   ZRow* zs = reinterpret_cast<ZRow*>(order + CP_MAXZ);
 #define offmax (*offmax_p)
@@ -151,8 +152,12 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
   }
   __syncthreads();
 
-  // ---- parallel cyclic Jacobi (round-robin tournament ordering: n-1 rounds of n/2 disjoint rotations)
+  // ---- parallel cyclic Jacobi (round-robin tournament ordering: n-1 rounds of n/2 disjoint rotations).
+  // Each round is two phases: (A) the n/2 rotations are computed from the current matrix, (B) every element of
+  // A' = J^T A J and V' = V J is produced from the OLD matrices (double buffering), so a round costs two barriers.
   const int half = n / 2;
+  Row* Acur = A; Row* Anew = A2;
+  Row* Vcur = V; Row* Vnew = V2;
   for (int sweep = 0; sweep < 30; ++sweep) {
     if (tid == 0) offmax = 0;
     __syncthreads();
@@ -160,14 +165,14 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
       double m = 0;
       for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, j = e % n;
-        if (i != j) m = fmax(m, fabs(A[i][j]));
+        if (i != j) m = fmax(m, fabs(Acur[i][j]));
       }
       for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
       if ((tid & 31) == 0 && m > 0) atomicMax(reinterpret_cast<unsigned long long*>(&offmax), (unsigned long long)__double_as_longlong(m));
     }
     __syncthreads();
     double dmax = 0;
-    for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(A[i][i]));
+    for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(Acur[i][i]));
     if (offmax <= 1e-14 * dmax || offmax == 0) break;      // eigenvalue error ~ off^2 / gap: far below fp32 resolution
     for (int round = 0; round < n - 1; ++round) {
       if (tid < half) {
@@ -175,43 +180,33 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
         const int a0 = (tid == 0) ? n - 1 : (round + tid) % (n - 1);
         const int b0 = (tid == 0) ? round : (round - tid + (n - 1)) % (n - 1);
         const int p = min(a0, b0), q = max(a0, b0);
-        pp[tid] = p; qq[tid] = q;
-        const double apq = A[p][q];
-        double c = 1.0, s = 0.0;
+        const double apq = Acur[p][q];
+        double c = 1.0, sn_ = 0.0;
         if (fabs(apq) > 1e-300) {
-          const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+          const double tau = (Acur[q][q] - Acur[p][p]) / (2.0 * apq);
           const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
           c = 1.0 / sqrt(1.0 + t * t);
-          s = t * c;
+          sn_ = t * c;
         }
-        cs[tid] = c; sn[tid] = s;
+        // new_p = c*old_p - s*old_q ; new_q = s*old_p + c*old_q
+        part[p] = q; part[q] = p;
+        own[p] = c; own[q] = c;
+        oth[p] = -sn_; oth[q] = sn_;
       }
       __syncthreads();
-      // columns: A <- A J, V <- V J
-      for (int e = tid; e < half * n; e += nt) {
-        const int k = e / n, i = e % n;
-        const int p = pp[k], q = qq[k];
-        const double c = cs[k], s = sn[k];
-        const double aip = A[i][p], aiq = A[i][q];
-        A[i][p] = c * aip - s * aiq;
-        A[i][q] = s * aip + c * aiq;
-        const double vip = V[i][p], viq = V[i][q];
-        V[i][p] = c * vip - s * viq;
-        V[i][q] = s * vip + c * viq;
+      for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e % n;
+        const int pi = part[i], pj = part[j];
+        const double oi = own[i], xi = oth[i], oj = own[j], xj = oth[j];
+        Anew[i][j] = oi * (oj * Acur[i][j] + xj * Acur[i][pj]) + xi * (oj * Acur[pi][j] + xj * Acur[pi][pj]);
+        Vnew[i][j] = oj * Vcur[i][j] + xj * Vcur[i][pj];
       }
       __syncthreads();
-      // rows: A <- J^T A
-      for (int e = tid; e < half * n; e += nt) {
-        const int k = e / n, j = e % n;
-        const int p = pp[k], q = qq[k];
-        const double c = cs[k], s = sn[k];
-        const double apj = A[p][j], aqj = A[q][j];
-        A[p][j] = c * apj - s * aqj;
-        A[q][j] = s * apj + c * aqj;
-      }
-      __syncthreads();
+      Row* tA = Acur; Acur = Anew; Anew = tA;
+      Row* tV = Vcur; Vcur = Vnew; Vnew = tV;
     }
   }
+  A = Acur; V = Vcur;
   // ---- eigenvalues, top-k selection (rank bound min(k, B, Z)), loss
   if (tid < n) {
     const double e = (tid < Z) ? A[tid][tid] : -1e300;

@@ -19,7 +19,7 @@ class VameDims(ctypes.Structure):
 class VameLossCfg(ctypes.Structure):
     _fields_ = [("mse_red_mean", ctypes.c_int), ("mse_pred_mean", ctypes.c_int), ("kmeans_loss", ctypes.c_int),
                 ("kmeans_lambda", ctypes.c_float), ("bsize", ctypes.c_float), ("beta", ctypes.c_float),
-                ("kl_weight", ctypes.c_float), ("with_future", ctypes.c_int)]
+                ("kl_weight", ctypes.c_float), ("with_future", ctypes.c_int), ("defer_prior_join", ctypes.c_int)]
 
 
 HY_LR, HY_KLW, HY_BETA, HY_KMLAMBDA = 0, 1, 2, 3
@@ -184,7 +184,7 @@ class Engine:
         d = self.dims
         return VameLossCfg(int(mse_red == "mean"), int(mse_pred == "mean"), int(d.zdims if kmeans_loss is None else kmeans_loss),
                            float(kmeans_lambda), float(bsize if bsize is not None else 0), float(beta), float(kl_weight),
-                           int(bool(with_future) and bool(d.future_decoder)))
+                           int(bool(with_future) and bool(d.future_decoder)), 0)
 
     def loss(self, cfg, fut=None, want_grads=True, use_hyper=False, out=None):
         """Loss terms of the last forward -> device float tensor [rec, fut, kl, kmeans, total, ...]."""
@@ -341,8 +341,10 @@ class TrainStep:
     def _phase1(self):
         e = self.eng
         e.forward(self.x, self.eps, save=True, want=(), ensure_packed=False)
+        self.cfg.defer_prior_join = 1        # the k-means prior overlaps the decoder BPTT; vame_backward joins it
         e.loss(self.cfg, self.fut if self.cfg.with_future else None, want_grads=True, use_hyper=True, out=self.losses)
         e.backward(self.cfg, use_hyper=True)
+        self.cfg.defer_prior_join = 0
 
     def _phase2(self):
         self.eng.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=True)
