@@ -20,7 +20,9 @@ const char* vame_last_error(void);
 int vame_abi_version(void);
 /* number of kernels enqueued by this library so far (host counter) */
 long vame_launch_count(void);
-/* runtime options: "pdl" (default 1) chains the recurrent step kernels with programmatic dependent launch */
+/* runtime options: "pdl" (default 1) chains the per-step recurrent kernels with programmatic dependent launch;
+ * "streams" (default 1) runs independent branches on internal side streams; "persistent" (default 2) bit0/bit1 select the
+ * persistent cluster kernel for the forward/backward sweeps */
 int vame_set_option(const char* name, int value);
 /* measurement hook: device buffer of 16 uint64 that gru_step_fwd_kernel's CTA 0 fills with %globaltimer stamps (NULL = off) */
 int vame_set_debug_buffer(void* device_u64x16);

@@ -284,7 +284,7 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
                           cudaStream_t st) {
   const int H = L.H;
   zero_p16_padding(L, tiles, true, st);
-  if (g_opt_persistent) {                       // one cluster kernel for the whole sweep
+  if (g_opt_persistent & 1) {                   // one cluster kernel for the whole sweep
     GruSeqFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
     const long Bp = (long)tiles * 128;
@@ -356,7 +356,7 @@ static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
   const size_t slotf = (size_t)Bp * H;
   const size_t pslot = (size_t)(nsl + 1) * slotf;
   zero_p16_padding(L, tiles, false, st);
-  if (g_opt_persistent) {                       // one cluster kernel for the whole BPTT sweep
+  if (g_opt_persistent & 2) {                   // one cluster kernel for the whole BPTT sweep
     GruSeqBwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
     const long seq_ld = (long)L.steps * Bp;
@@ -595,7 +595,7 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
     decoder_forward(*d, 1, params, L, W, w, save, sA);
   }
   decoder_forward(*d, 0, params, L, W, w, save, st);
-  edge(sA, st);
+  if (d->future_decoder) edge(sA, st);
   if (pred) launch_tb_to_bt(w.dec[0].pred_tb, batch, T, F, w.B_pad, pred, st);
   if (future && d->future_decoder) launch_tb_to_bt(w.dec[1].pred_tb, batch, d->future_steps, F, w.B_pad, future, st);
   if (z) cudaMemcpyAsync(z, w.z, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
@@ -677,6 +677,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
 
   const int ndec = d->future_decoder ? 2 : 1;
   const float* dz_dec[2] = {nullptr, nullptr};
+  bool used_sA = false;
   for (int i = ndec - 1; i >= 0; --i) {      // the future decoder (i = 1) is enqueued first, on its own stream
     DecBuf& D = w.dec[i];
     const float* ext = i == 0 ? dpred : dfuture;
@@ -684,7 +685,10 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     if (!have_grad) continue;                                             // this decoder received no gradient
     cudaStream_t sd = i == 0 ? st : sA;      // data-gradient chain of this decoder
     cudaStream_t sw = i == 0 ? sB : sA;      // its weight-gradient work
-    if (i == 1) edge(st, sA);
+    if (i == 1) {
+      edge(st, sA);
+      used_sA = true;
+    }
     const int Hd = D.g.H, steps = D.g.steps;
     const long rows = (long)steps * Bp;
     const int nk = (int)(rows / KCHUNK), nkcF = nkc_of(F), nkc3 = nkc_of(3 * Hd), nkc2H = nkc_of(2 * Hd);
@@ -783,7 +787,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sB);
   }
   edge(sB, st);
-  edge(sA, st);
+  if (used_sA) edge(sA, st);                 // only streams that were forked into this call may be joined (graph capture isolation)
   return check_launch("vame_backward");
 }
 

@@ -10,7 +10,8 @@ extern long g_launch_count;
 extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
 extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
 extern int g_opt_streams;
-extern int g_opt_persistent; // 1: run each recurrent sweep as one persistent cluster kernel instead of one kernel per step   // 1: run independent branches of a step on internal side streams
+extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
+                             // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 // ---- pack.cu -------------------------------------------------------------------------------------

@@ -183,9 +183,12 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
         const double apq = Acur[p][q];
         double c = 1.0, sn_ = 0.0;
         if (fabs(apq) > 1e-300) {
-          const double tau = (Acur[q][q] - Acur[p][p]) / (2.0 * apq);
-          const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
+          // the rotation ANGLE is computed in fp32 with MUFU ops (it only steers convergence: an angle that is off by
+          // 1e-7 leaves a 1e-7 residue that the next sweep removes), the rotation itself (c, s) is orthonormal in fp64
+          const float tau = __fdividef((float)(Acur[q][q] - Acur[p][p]), (float)(2.0 * apq));
+          const float tf = __fdividef(tau >= 0.f ? 1.f : -1.f, fabsf(tau) + sqrtf(1.f + tau * tau));
+          const double t = (tf == tf) ? (double)tf : 0.0;
+          c = rsqrt(1.0 + t * t);
           sn_ = t * c;
         }
         // new_p = c*old_p - s*old_q ; new_q = s*old_p + c*old_q
