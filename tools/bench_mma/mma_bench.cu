@@ -36,20 +36,21 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int iters, int mode, 
     if (lane == 0) {
       const uint32_t sa = smem_u32(smem), sb = sa + 64 * 1024;
       const uint32_t idesc = make_idesc_bf16(128, N);
+      // tight issue loop: descriptors precomputed, 4 k-steps unrolled, constant predicates (like the production kernels)
+      uint64_t da[4], db[4];
+      for (int ks = 0; ks < 4; ++ks) {
+        if (mode == 0) { da[ks] = desc_generic(sa + ks * 256, 128, 1024, 0); db[ks] = desc_generic(sb + ks * 256, 128, 1024, 0); }
+        else           { da[ks] = desc_generic(sa + ks * 32, 16, 1024, 2);   db[ks] = desc_generic(sb + ks * 32, 16, 1024, 2); }
+      }
+      const uint32_t d1 = tmem + (nacc > 1 ? N : 0);
       t0 = clock64();
-      for (int i = 0; i < iters; ++i) {
-        const int ks = same_k ? 0 : (i & 15);
-        uint64_t da, db;
-        if (mode == 0) {          // SWIZZLE_NONE: atoms 128 B, LBO 128, SBO 1024 (tile = 64 k wide: chunk stride 16/32 KB)
-          const uint32_t ko = (ks & 3) * 256, kc = ks >> 2;
-          da = desc_generic(sa + kc * 16384 + ko, 128, 1024, 0);
-          db = desc_generic(sb + kc * 32768 + ko, 128, 1024, 0);
-        } else {                  // SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart, K advance = 32 B
-          const uint32_t ko = (ks & 3) * 32, kc = ks >> 2;
-          da = desc_generic(sa + kc * 16384 + ko, 16, 1024, 2);
-          db = desc_generic(sb + kc * 32768 + ko, 16, 1024, 2);
-        }
-        umma_bf16(tmem + (uint32_t)((i % nacc) * N), da, db, idesc, i >= nacc);
+      umma_bf16_c<0>(tmem, da[0], db[0], idesc);
+      umma_bf16_c<0>(d1, da[0], db[0], idesc);
+      for (int i = 0; i < iters; i += 4) {
+        umma_bf16_c<1>(tmem, da[0], db[0], idesc);
+        umma_bf16_c<1>(d1, da[1], db[1], idesc);
+        umma_bf16_c<1>(tmem, da[2], db[2], idesc);
+        umma_bf16_c<1>(d1, da[3], db[3], idesc);
       }
       t1 = clock64();
       umma_commit(&done);
@@ -83,19 +84,14 @@ void run(int mode, int same_k, long long* d_out, int nacc = 1) {
 int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
-  for (int mode = 0; mode < 2; ++mode) {
-    run<48>(mode, 0, d_out);
-    run<96>(mode, 0, d_out);
-    run<128>(mode, 0, d_out);
-    run<192>(mode, 0, d_out);
-    run<256>(mode, 0, d_out);
-  }
-  // independent accumulators (round-robin over nacc TMEM regions): is the ~100-cycle floor a dependency latency?
-  for (int nacc = 2; nacc <= 4; nacc *= 2) {
-    run<48>(0, 0, d_out, nacc);
-    run<96>(0, 0, d_out, nacc);
-    run<128>(0, 0, d_out, nacc);
-    if (nacc == 2) run<192>(0, 0, d_out, nacc);
-  }
+  for (int nacc = 1; nacc <= 2; ++nacc)
+    for (int mode = 0; mode < 2; ++mode) {
+      run<32>(mode, 0, d_out, nacc);
+      run<48>(mode, 0, d_out, nacc);
+      run<96>(mode, 0, d_out, nacc);
+      run<128>(mode, 0, d_out, nacc);
+      run<192>(mode, 0, d_out, nacc);
+      run<256>(mode, 0, d_out, nacc);
+    }
   return 0;
 }

@@ -75,23 +75,21 @@ __global__ void __launch_bounds__(128, 1) gemm_p16_kernel(const GemmArgs g) {
      if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = make_idesc_bf16(G_BM, 2 * G_BN);          // one descriptor spans [B_hi ; B_lo]
+      const uint64_t dA0 = make_desc(smem_u32(smem));
       for (int i = 0; i < nk; ++i) {
         const int s = i % G_STAGES;
         const uint32_t ph = (i / G_STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * G_STAGE_BYTES);
-        const uint32_t sb = sa + G_TILE_BYTES;
-        const uint32_t plane = 128 * KCHUNK * 2;                      // bytes between hi and lo planes
+        const uint64_t dA = desc_advance(dA0, s * G_STAGE_BYTES), dB = desc_advance(dA0, s * G_STAGE_BYTES + G_TILE_BYTES);
+        constexpr uint32_t plane = 128 * KCHUNK * 2;                  // bytes between hi and lo planes
 #pragma unroll
         for (int ks = 0; ks < KCHUNK / 16; ++ks) {
+          // D[:, 0:128] += a * b_hi, D[:, 128:256] += a * b_lo (summed in the epilogue)
           const uint32_t ko = ks * 2 * ATOM_BYTES;                   // 16 k-elements = 2 atoms
-          // D[:, 0:128] += a * b_hi, D[:, 128:256] += a * b_lo (summed in the epilogue); a tcgen05.mma costs ~100 cycles
-          // for any N <= 128 and 128 cycles for N = 256 (tools/bench_mma), so two N=256 MMAs beat three N=128 ones
-          const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + plane + ko);
-          const uint64_t b_hl = make_desc(sb + ko);
-          umma_bf16(tmem, a_lo, b_hl, idesc, (i | ks) != 0);
-          umma_bf16(tmem, a_hi, b_hl, idesc, 1);
+          if (ks == 0 && i == 0) umma_bf16_c<0>(tmem, desc_advance(dA, plane + ko), desc_advance(dB, ko), idesc);
+          else umma_bf16_c<1>(tmem, desc_advance(dA, plane + ko), desc_advance(dB, ko), idesc);
+          umma_bf16_c<1>(tmem, desc_advance(dA, ko), desc_advance(dB, ko), idesc);
         }
         umma_commit(&empty[s]);          // frees the smem stage once these MMAs retire
       }

@@ -155,21 +155,26 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
         bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
       }
       const uint32_t idesc = make_idesc_bf16(128, 192);
-      const uint32_t aplane = 128 * KCHUNK * 2;
-      for (int kc = 0; kc < nkc; ++kc) {
-        mbar_wait(&wbar[kc], 0);
-        mbar_wait(&abar[kc], 0);
-        if (kc == 0) DBG_STAMP0(3);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
-        const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t ko = ks * 2 * ATOM_BYTES;
-          // one descriptor covers [W_hi ; W_lo] (192 rows): D[:, 0:96] += a*w_hi, D[:, 96:192] += a*w_lo
-          const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
-          const uint64_t w_hl = make_desc(sw + ko);
-          umma_bf16(tmem, a_lo, w_hl, idesc, (kc | ks) != 0);
-          umma_bf16(tmem, a_hi, w_hl, idesc, 1);
+      // the issue loop is the critical resource (one thread): descriptors are precomputed, the k-steps fully unrolled
+      const uint64_t dA = make_desc(smem_u32(sA)), dAl = make_desc(smem_u32(sA) + 128 * KCHUNK * 2), dW = make_desc(smem_u32(sW));
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        if (kc < nkc) {
+          mbar_wait(&wbar[kc], 0);
+          mbar_wait(&abar[kc], 0);
+          if (kc == 0) DBG_STAMP0(3);
+          tc_fence_after();
+          const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps) {
+              // one descriptor covers [W_hi ; W_lo] (192 rows): D[:, 0:96] += a*w_hi, D[:, 96:192] += a*w_lo
+              const uint32_t ao = kc * F_ATILE + ks * 2 * ATOM_BYTES, wo = kc * F_WTILE + ks * 2 * ATOM_BYTES;
+              if (kc == 0 && ks == 0) umma_bf16_c<0>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
+              else umma_bf16_c<1>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
+              umma_bf16_c<1>(tmem, desc_advance(dA, ao), desc_advance(dW, wo), idesc);
+            }
+          }
         }
       }
       umma_commit(done);
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
   ldf16(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hprev);
   const uint32_t idesc = make_idesc_bf16(128, 192);
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  const uint64_t dA = make_desc(smem_u32(sA)), dAl = make_desc(smem_u32(sA) + 128 * KCHUNK * 2), dW = make_desc(smem_u32(sW));
 
   for (int s = 0; s < a.steps; ++s) {
     const int t = d.reverse ? a.steps - 1 - s : s;
@@ -349,19 +355,22 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
           mbar_expect_tx(&abar[kc], F_ATILE);
           bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
         }
-        const uint32_t aplane = 128 * KCHUNK * 2;
-        for (int kc = 0; kc < nkc; ++kc) {
-          if (s == 0) mbar_wait(&wbar[kc], 0);
-          mbar_wait(&abar[kc], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(sA + (size_t)kc * F_ATILE), sw = smem_u32(sW + (size_t)kc * F_WTILE);
-          const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t ko = ks * 2 * ATOM_BYTES;
-            const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + aplane + ko);
-            const uint64_t w_hl = make_desc(sw + ko);            // [W_hi ; W_lo], N = 192
-            umma_bf16(tmem, a_lo, w_hl, idesc, (kc | ks) != 0);
-            umma_bf16(tmem, a_hi, w_hl, idesc, 1);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          if (kc < nkc) {
+            if (s == 0) mbar_wait(&wbar[kc], 0);
+            mbar_wait(&abar[kc], ph);
+            tc_fence_after();
+            const int ksteps = min(KCHUNK, H - kc * KCHUNK) / 16;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint32_t ao = kc * F_ATILE + ks * 2 * ATOM_BYTES, wo = kc * F_WTILE + ks * 2 * ATOM_BYTES;
+                if (kc == 0 && ks == 0) umma_bf16_c<0>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
+                else umma_bf16_c<1>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
+                umma_bf16_c<1>(tmem, desc_advance(dA, ao), desc_advance(dW, wo), idesc);
+              }
+            }
           }
         }
         umma_commit(done);
@@ -548,18 +557,17 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
       mbar_wait(wbar, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, H);
-      for (int kc = 0; kc < 2; ++kc) {
-        const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
-        const uint32_t sw = smem_u32(sW + kc * wchunk);
-        const uint32_t wplane = (uint32_t)nrb * B_APLANE;
-        const int ksteps = kc == 0 ? 4 : 2;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t ko = ks * 2 * ATOM_BYTES;
-          const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
-          const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-          umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-          umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-          umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+      {
+        const uint64_t dA0 = make_desc(smem_u32(sA)), dW0 = make_desc(smem_u32(sW));
+        const uint32_t wplane = (uint32_t)nrb * B_APLANE, wch = (uint32_t)wchunk;
+#pragma unroll
+        for (int kk = 0; kk < 6; ++kk) {                 // k-steps 0..3 in chunk 0, 4..5 in chunk 1
+          const uint32_t kc = kk >> 2, ko = (kk & 3) * 2 * ATOM_BYTES;
+          const uint32_t ao = kc * 2 * B_APLANE + ko, wo = kc * wch + ko;
+          if (kk == 0) umma_bf16_c<0>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
+          else umma_bf16_c<1>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
+          umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo + wplane), idesc);
+          umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo), idesc);
         }
       }
       umma_commit(done);
@@ -715,18 +723,17 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
       if (lane == 0) {
         if (s == 0) mbar_wait(wbar, 0);
         tc_fence_after();
-        for (int kc = 0; kc < 2; ++kc) {
-          const uint32_t sa = smem_u32(sA + (size_t)kc * 2 * B_APLANE);
-          const uint32_t sw = smem_u32(sW + kc * wchunk);
-          const uint32_t wplane = (uint32_t)nrb * B_APLANE;
-          const int ksteps = kc == 0 ? 4 : 2;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t ko = ks * 2 * ATOM_BYTES;
-            const uint64_t a_hi = make_desc(sa + ko), a_lo = make_desc(sa + B_APLANE + ko);
-            const uint64_t w_hi = make_desc(sw + ko), w_lo = make_desc(sw + wplane + ko);
-            umma_bf16(tmem, a_lo, w_hi, idesc, (kc | ks) != 0);
-            umma_bf16(tmem, a_hi, w_lo, idesc, 1);
-            umma_bf16(tmem, a_hi, w_hi, idesc, 1);
+        {
+          const uint64_t dA0 = make_desc(smem_u32(sA)), dW0 = make_desc(smem_u32(sW));
+          const uint32_t wplane = (uint32_t)nrb * B_APLANE, wch = (uint32_t)wchunk;
+#pragma unroll
+          for (int kk = 0; kk < 6; ++kk) {                 // k-steps 0..3 in chunk 0, 4..5 in chunk 1
+            const uint32_t kc = kk >> 2, ko = (kk & 3) * 2 * ATOM_BYTES;
+            const uint32_t ao = kc * 2 * B_APLANE + ko, wo = kc * wch + ko;
+            if (kk == 0) umma_bf16_c<0>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
+            else umma_bf16_c<1>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
+            umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo + wplane), idesc);
+            umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo), idesc);
           }
         }
         umma_commit(done);

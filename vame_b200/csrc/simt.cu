@@ -287,9 +287,20 @@ __global__ void timesum_fm_kernel(const float* __restrict__ X, long ld, int T, i
 __global__ void rowsum_fm_kernel(const float* __restrict__ X, long ld, long ncols, int nfeat, float* __restrict__ out) {
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= nfeat) return;
+  const long per = ((ncols + gridDim.y - 1) / gridDim.y + 3) & ~3L;       // column split (gridDim.y) for parallelism
+  const long c0 = blockIdx.y * per, c1 = min(ncols, c0 + per);
   const float* row = X + (long)f * ld;
   float s = 0.f;
-  for (long r = threadIdx.x & 31; r < ncols; r += 32) s += row[r];
+  if ((((uintptr_t)(row + c0)) & 15) == 0) {
+    long r = c0 + (threadIdx.x & 31) * 4;
+    for (; r + 3 < c1; r += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(row + r);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    for (; r < c1; ++r) s += row[r];
+  } else {
+    for (long r = c0 + (threadIdx.x & 31); r < c1; r += 32) s += row[r];
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) atomicAdd(out + f, s);
 }
@@ -435,7 +446,10 @@ void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out
 }
 void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st) {
   count_launch();
-  rowsum_fm_kernel<<<(nfeat + 7) / 8, 256, 0, st>>>(X, ld, ncols, nfeat, out);
+  int ysplit = (int)((ncols + 2047) / 2048);
+  if (ysplit > 8) ysplit = 8;
+  if (ysplit < 1) ysplit = 1;
+  rowsum_fm_kernel<<<dim3((nfeat + 7) / 8, ysplit), 256, 0, st>>>(X, ld, ncols, nfeat, out);
 }
 void launch_fm_to_rows(const float* src, long ld, int H, int B, float* dst, long dst_ld, cudaStream_t st) {
   count_launch();
