@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(mode, pdl, workload, streams=1, persistent=1):
+def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
     faulthandler.dump_traceback_later(100, exit=True)
     import torch
     from bench import WORKLOADS
@@ -22,6 +22,7 @@ def child(mode, pdl, workload, streams=1, persistent=1):
     lib.vame_set_option(b"pdl", int(pdl))
     lib.vame_set_option(b"streams", int(streams))
     lib.vame_set_option(b"persistent", int(persistent))
+    lib.vame_set_option(b"flags", int(flags))
     torch.manual_seed(19)
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
     eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda")
@@ -102,13 +103,13 @@ def child(mode, pdl, workload, streams=1, persistent=1):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child(sys.argv[2], int(sys.argv[3]), sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 1,
-              int(sys.argv[6]) if len(sys.argv) > 6 else 1)
+              int(sys.argv[6]) if len(sys.argv) > 6 else 1, int(sys.argv[7]) if len(sys.argv) > 7 else 1)
         sys.exit(0)
     workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    for mode, pdl, streams, pers in (("eager", 0, 1, 0), ("graph", 1, 1, 0)):
-        print("##### variant mode=%s pdl=%d streams=%d persistent=%d" % (mode, pdl, streams, pers), flush=True)
+    for mode, pdl, streams, pers, flags in (("eager", 1, 1, 0, 1), ("eager", 1, 1, 2, 1), ("eager", 1, 1, 0, 0), ("graph", 1, 1, 0, 1), ("graph", 1, 1, 2, 1), ("graph", 1, 1, 2, 0)):
+        print("##### variant mode=%s pdl=%d streams=%d persistent=%d flags=%d" % (mode, pdl, streams, pers, flags), flush=True)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload, str(streams), str(pers)], timeout=150,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload, str(streams), str(pers), str(flags)], timeout=150,
                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             print(r.stdout[-3000:], flush=True)
             print("variant %s pdl=%d rc=%d" % (mode, pdl, r.returncode), flush=True)

@@ -24,6 +24,7 @@ struct GruBuf {
   float* dgi[2]; float* dgh[2]; void* dgi_p[2];
   float* parts[2];
   void* dghT_p[2]; void* dgiT_p[2]; void* outT_p[2]; void* h0T_p[2];
+  unsigned int* flags;                  // [2 dirs][steps][tiles] hand-over counters of the per-step kernels
 };
 
 struct DecBuf {
@@ -77,6 +78,7 @@ static void carve_gru(Arena& A, GruBuf& g, int steps, int H, int In, int B_pad, 
   }
   g.out_slots = training ? steps : 2;
   g.out_p_slots = per_t_p16 ? steps : 2;
+  g.flags = (unsigned int*)A.raw((size_t)2 * steps * tiles * sizeof(unsigned int));
   for (int d = 0; d < 2; ++d) {
     g.out[d] = A.f32(slotf * g.out_slots);
     g.out_p[d] = A.raw(slotp * g.out_p_slots);
@@ -304,13 +306,22 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
     return;
   }
   const size_t slotp = (size_t)tiles * nkc_of(H) * p16_tile_elems(128);
+  const bool use_flags = pdl && g_opt_pdl && g_opt_flags;
+  if (use_flags) cudaMemsetAsync(L.flags, 0, (size_t)2 * L.steps * tiles * sizeof(unsigned int), st);
   for (int s = 0; s < L.steps; ++s) {
     GruFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
+    a.flags = use_flags ? 1 : 0;
+    a.flag_expected = (unsigned int)(H / 32) * 8u;            // every warp of every slice CTA signals once
     for (int d = 0; d < 2; ++d) {
       const int t = d == 0 ? s : L.steps - 1 - s;
       const int tprev = d == 0 ? t - 1 : t + 1;
       GruDirFwd& D = a.d[d];
+      if (use_flags) {
+        unsigned int* f = L.flags + (size_t)d * L.steps * tiles;
+        D.flag_in = s == 0 ? nullptr : f + (size_t)(s - 1) * tiles;
+        D.flag_out = f + (size_t)s * tiles;
+      }
       D.w_p = W.whh_p[d];
       D.b_hn = d == 0 ? b_hn0 : b_hn1;
       D.gi = L.gi + (size_t)d * 3 * H * L.gi_ld;
@@ -377,14 +388,23 @@ static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
     launch_gru_seq_bwd(a, st);
     return;
   }
+  const bool use_flags = pdl && g_opt_pdl && g_opt_flags;
+  if (use_flags) cudaMemsetAsync(L.flags, 0, (size_t)2 * L.steps * tiles * sizeof(unsigned int), st);
   for (int s = 0; s < L.steps; ++s) {
     GruBwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
+    a.flags = use_flags ? 1 : 0;
+    a.flag_expected = (unsigned int)(H / 32) * 8u;
     for (int d = 0; d < 2; ++d) {
       const int t = d == 0 ? L.steps - 1 - s : s;           // reverse of the forward order
       const bool first_fwd = d == 0 ? (t == 0) : (t == L.steps - 1);
       const int tprev = d == 0 ? t - 1 : t + 1;
       GruDirBwd& D = a.d[d];
+      if (use_flags) {
+        unsigned int* f = L.flags + (size_t)d * L.steps * tiles;
+        D.flag_in = s == 0 ? nullptr : f + (size_t)(s - 1) * tiles;
+        D.flag_out = f + (size_t)s * tiles;
+      }
       D.wT_p = W.whhT_p[d];
       const float* dhl = d == 0 ? dhl0 : dhl1;
       if (s == 0) {

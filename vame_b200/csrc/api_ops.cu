@@ -9,6 +9,7 @@ thread_local char g_err[512] = {0};
 long g_launch_count = 0;
 int g_opt_pdl = 1;
 int g_opt_streams = 1;
+int g_opt_flags = 1;
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
 unsigned long long* g_dbg_buffer = nullptr;
 }
@@ -34,6 +35,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "persistent") == 0) {
     vb::g_opt_persistent = value;
+    return 0;
+  }
+  if (strcmp(name, "flags") == 0) {
+    vb::g_opt_flags = value ? 1 : 0;
     return 0;
   }
   if (strcmp(name, "streams") == 0) {

@@ -96,6 +96,15 @@ __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.c
 // orders this thread's generic-proxy accesses (st.global / ld.global) against async-proxy accesses (TMA bulk copies)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }   // L2-coherent load (bypasses the non-coherent L1)
+// inter-kernel hand-over flags (PDL chains without griddepcontrol.wait): release-increment / acquire-poll at gpu scope
+__device__ __forceinline__ void flag_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int flag_acquire_load(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM

@@ -143,12 +143,21 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   }
 
   DBG_STAMP(1);
-  if (a.pdl) pdl_wait();               // previous step's h is now complete and visible
-  if (a.pdl) pdl_launch_dependents();  // let the next step start its prologue
+  if (a.pdl && !a.flags) pdl_wait();   // previous step's h is now complete and visible
+  if (a.pdl && !a.flags) pdl_launch_dependents();  // let the next step start its prologue
   DBG_STAMP(2);
 
   if (warp == 0) {
     if (lane == 0) {
+      if (a.flags) {
+        // flag hand-over: the previous step's CTAs (a still-running kernel) publish h and then bump the counter
+        if (d.flag_in) {
+          while (flag_acquire_load(d.flag_in + tile) < a.flag_expected) {
+          }
+        }
+        fence_proxy_async_all();
+        pdl_launch_dependents();       // at most one successor is resident (prologue + spin) while this step works
+      }
       const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(d.h_in_p) + (size_t)tile * nkc * p16_tile_elems(128);
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_expect_tx(&abar[kc], F_ATILE);
@@ -184,10 +193,13 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   }
 
   float hprev[16];
-  ldf16(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);
-
-  mbar_wait(done, 0);
+  if (!a.flags) ldf16(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);     // complete + visible after griddepcontrol.wait
+  mbar_wait(done, 0);                   // (with flags this also orders the h_in read below after the producer's release)
   __syncwarp();
+  if (a.flags) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hprev[i] = ld_cg(d.h_in + (long)(u0 + i) * d.h_in_ld + b);
+  }
   DBG_STAMP(5);
   tc_fence_after();
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
@@ -223,6 +235,12 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
     st16_p16(t, 128, r_in, kk, hn);
   }
+  if (a.flags) {                        // publish: everything the next step reads is written above
+    fence_proxy_async_all();
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) flag_release_add(d.flag_out + tile, 1u);
+  }
   DBG_STAMP(10);
   if (d.sv_r) {
     const long so = (long)u0 * d.sv_ld + b;
@@ -232,6 +250,9 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     stf16(d.sv_ghn + so, d.sv_ld, bhn);
   }
   DBG_STAMP(6);
+  // flag mode: kernels complete in launch order (each waits here for its predecessor), so the completion of the last step
+  // kernel implies that every step's stores have landed — what a following normal launch / graph edge relies on
+  if (a.pdl && a.flags) pdl_wait();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
@@ -519,13 +540,26 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
     for (int i = 0; i < 16; ++i) dh[i] = 0.f;
   }
 
-  if (a.pdl) pdl_wait();
-  if (a.pdl) pdl_launch_dependents();
+  if (a.pdl && !a.flags) pdl_wait();
+  if (a.pdl && !a.flags) pdl_launch_dependents();
+  if (a.flags) {
+    if (d.flag_in && lane == 0) {
+      while (flag_acquire_load(d.flag_in + tile) < a.flag_expected) {
+      }
+    }
+    __syncwarp();
+    if (tid == 0) pdl_launch_dependents();
+  }
 
   const long bpad = (long)a.tiles * 128;
   for (int p = 0; p < d.n_parts; ++p) {
     float t[16];
-    ldf16(d.parts + (long)p * d.parts_stride + (long)u0 * d.parts_ld + b, d.parts_ld, t);
+    if (a.flags) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] = ld_cg(d.parts + (long)p * d.parts_stride + (long)(u0 + i) * d.parts_ld + b);
+    } else {
+      ldf16(d.parts + (long)p * d.parts_stride + (long)u0 * d.parts_ld + b, d.parts_ld, t);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) dh[i] += t[i];
   }
@@ -575,23 +609,26 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
     __syncwarp();
   }
 
-  // outputs that do not need the MMA
+  // the carry is part of what the next step reads; the gate gradients are not (they feed the GEMMs after the sweep)
   stf16(d.parts_out + ((long)nsl * H + u0) * bpad + b, bpad, dh);     // carry slot
-  stf16(d.dgi + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
-  stf16(d.dgi + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
-  stf16(d.dgi + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dan);
-  stf16(d.dgh + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
-  stf16(d.dgh + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
-  stf16(d.dgh + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dgn);
-  if (d.dgi_p) {
-    const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
-    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
+  auto store_gate_grads = [&]() {
+    stf16(d.dgi + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
+    stf16(d.dgi + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
+    stf16(d.dgi + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dan);
+    stf16(d.dgh + (long)u0 * d.dg_ld + b, d.dg_ld, dar);
+    stf16(d.dgh + (long)(H + u0) * d.dg_ld + b, d.dg_ld, daz);
+    stf16(d.dgh + (long)(2 * H + u0) * d.dg_ld + b, d.dg_ld, dgn);
+    if (d.dgi_p) {
+      const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const int k = g * H + u0;
-      st16_p16(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+      for (int g = 0; g < 3; ++g) {
+        const int k = g * H + u0;
+        st16_p16(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+      }
     }
-  }
+  };
+  if (!a.flags) store_gate_grads();     // overlap with the MMA when the next step waits for kernel completion anyway
 
   mbar_wait(done, 0);
   __syncwarp();
@@ -604,6 +641,13 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
     tmem_ld16(taddr + c0, v);
     tmem_ld_wait();
     stf16(pbase + (long)c0 * bpad, bpad, v);
+  }
+  if (a.flags) {                        // publish the partial sums + carry, then write what only later kernels read
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) flag_release_add(d.flag_out + tile, 1u);
+    store_gate_grads();
+    if (a.pdl) pdl_wait();              // in-order completion of the chain (see the forward kernel)
   }
   tc_fence_before();
   __syncthreads();

@@ -9,6 +9,7 @@ namespace vb {
 extern long g_launch_count;
 extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
 extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
+extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through release/acquire flags (tail of step t overlaps t+1)
 extern int g_opt_streams;
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
@@ -63,11 +64,17 @@ struct GruDirFwd {
   long h_out_ld;
   float* sv_r; float* sv_z; float* sv_n; float* sv_ghn;   // saved gates for BPTT, feature-major [H][sv_ld] at this t's slot (or nullptr)
   long sv_ld;
+  // hand-over flags (a.flags != 0): per (tile) counters; this step waits until flag_in[tile] == flag_expected (nullptr: no wait)
+  // and adds 1 per warp to flag_out[tile] once its slice of h is published
+  const unsigned int* flag_in; unsigned int* flag_out;
 };
 struct GruFwdArgs {
   GruDirFwd d[2];
   int ndir, H, tiles;
   int pdl;                // launch with programmatic stream serialization
+  int flags;              // 1: the recurrence dependency is carried by flag_in/flag_out instead of griddepcontrol.wait, so the
+                          //    tail of step t (saved-gate stores, teardown) overlaps step t+1
+  unsigned int flag_expected;
   unsigned long long* dbg;   // optional device buffer for %globaltimer stamps (filled in by the launcher)
 };
 void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
@@ -123,11 +130,14 @@ struct GruDirBwd {
   float* dgh;             // same layout (dgi_r, dgi_z, dgi_n * r)
   long dg_ld;
   void* dgi_p;            // optional P16 (RB=128) A-operand copy of dgi for the dx GEMM: [tiles][KC3H][2][128x64] slot of this t
+  const unsigned int* flag_in; unsigned int* flag_out;   // as in GruDirFwd
 };
 struct GruBwdArgs {
   GruDirBwd d[2];
   int ndir, H, tiles;
   int pdl;
+  int flags;
+  unsigned int flag_expected;
 };
 void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st);
 
