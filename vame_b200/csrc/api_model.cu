@@ -235,34 +235,64 @@ static inline int splits_for(int M, int N, int nkc) {
 // ================================================================================================
 // weights
 // ================================================================================================
-static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, cudaStream_t st) {
+// All weight re-packs of one optimizer step are queued as jobs and executed by 2-3 launches of pack_jobs_kernel.
+struct JobQ {
+  PackJobs jobs{};
+  cudaStream_t st;
+  explicit JobQ(cudaStream_t s) : st(s) { jobs.n = 0; }
+  void push(const PackJob& j) {
+    if (jobs.n == 40) launch_pack_jobs(jobs, st);
+    jobs.j[jobs.n++] = j;
+  }
+  void rows(const float* src, long ld, int R, int K, int R_src, void* out) {           // like pack_rows
+    PackJob j{}; j.src = src; j.out = out; j.ld = ld; j.kind = 0; j.transposed = 0; j.R = R; j.K = K; j.R_src = R_src; j.K_src = K; j.RB = 128;
+    push(j);
+  }
+  void T(const float* src, long ld, int R, int K, int K_src, void* out) {               // like pack_T
+    PackJob j{}; j.src = src; j.out = out; j.ld = ld; j.kind = 0; j.transposed = 1; j.R = R; j.K = K; j.R_src = R; j.K_src = K_src; j.RB = 128;
+    push(j);
+  }
+  void whh(const float* w, int H, int mode, void* out) {
+    PackJob j{}; j.src = w; j.out = out; j.kind = 1 + mode; j.R = H;
+    push(j);
+  }
+  void bias(const float* b_ih, const float* b_hh, int H, float* out) {
+    PackJob j{}; j.src = b_ih; j.src2 = b_hh; j.out = out; j.kind = 3; j.R = H;
+    push(j);
+  }
+  void flush() { launch_pack_jobs(jobs, st); }
+};
+
+static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
   const int H = o.H, In = o.In;
   for (int d = 0; d < 2; ++d) {
-    launch_pack_whh(P + o.whh[d], H, 0, W.whh_p[d], st);
-    launch_pack_whh(P + o.whh[d], H, 1, W.whhT_p[d], st);
-    pack_T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d], st);           // [In rows, K = 3H]
+    q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
+    q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
+    q.T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d]);                 // [In rows, K = 3H]
+    q.bias(P + o.bih[d], P + o.bhh[d], H, W.bias_gi + (size_t)d * 3 * H);
   }
   // both directions' W_ih are adjacent in the flat buffer -> one [6H, In] matrix; K split in wih_nseg column blocks
   const int Ks = In / W.wih_nseg;
-  for (int s = 0; s < W.wih_nseg; ++s) pack_rows(P + o.wih[0] + (long)s * Ks, In, 6 * H, Ks, 6 * H, W.wih_p[s], st);
-  launch_bias_fuse(P + o.bih[0], P + o.bhh[0], P + o.bih[1], P + o.bhh[1], H, W.bias_gi, st);
+  for (int s = 0; s < W.wih_nseg; ++s) q.rows(P + o.wih[0] + (long)s * Ks, In, 6 * H, Ks, 6 * H, W.wih_p[s]);
 }
 
 static void pack_all_weights(const vame_dims& d, const float* P, const PackedWeights& W, cudaStream_t st) {
   const ParamLayout L = param_layout(d);
   const int H = d.hidden_enc, F = d.num_features, Z = d.zdims;
-  pack_gru_weights(P, L.e0, W.e0, st);
-  pack_gru_weights(P, L.e1, W.e1, st);
-  for (int i = 0; i < 4; ++i) pack_rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i], st);
-  pack_T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p, st);
+  JobQ q(st);
+  pack_gru_weights(P, L.e0, W.e0, q);
+  pack_gru_weights(P, L.e1, W.e1, q);
+  for (int i = 0; i < 4; ++i) q.rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i]);
+  q.T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p);
   for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
     const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
-    pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, st);
-    pack_rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i], st);
-    pack_T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i], st);
-    for (int dd = 0; dd < 2; ++dd) pack_rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd], st);
-    pack_T(P + L.h2o_w[i], 2 * Hd, 2 * Hd, F, F, W.h2oT_p[i], st);
+    pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, q);
+    q.rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i]);
+    q.T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i]);
+    for (int dd = 0; dd < 2; ++dd) q.rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd]);
+    q.T(P + L.h2o_w[i], 2 * Hd, 2 * Hd, F, F, W.h2oT_p[i]);
   }
+  q.flush();
 }
 
 // ================================================================================================

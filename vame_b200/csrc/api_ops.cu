@@ -9,7 +9,7 @@ thread_local char g_err[512] = {0};
 long g_launch_count = 0;
 int g_opt_pdl = 1;
 int g_opt_streams = 1;
-int g_opt_flags = 1;
+int g_opt_flags = 0;           // measured: no gain (the gpu-scope publish costs what the kernel-completion flush costs)
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
 unsigned long long* g_dbg_buffer = nullptr;
 }

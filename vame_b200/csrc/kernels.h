@@ -9,7 +9,8 @@ namespace vb {
 extern long g_launch_count;
 extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic dependent launch
 extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
-extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through release/acquire flags (tail of step t overlaps t+1)
+extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through release/acquire flags (tail of step t overlaps t+1);
+                            //    default 0: measured equal to griddepcontrol.wait (tools/gpu_probe_graph.py, profiles/)
 extern int g_opt_streams;
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
@@ -19,6 +20,18 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
 // value(r, k) = src[i * ld + j] with (i, j) = transposed ? (k, r) : (r, k); zero outside i < nrows_src, j < ncols_src
 void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
                      const int* col_map, int RB, void* out, cudaStream_t st);
+// batched pack jobs (one launch): kind 0 = generic pack_p16, 1 / 2 = W_hh forward / backward slices (R = H), 3 = fused bias (R = H)
+struct PackJob {
+  const float* src; const float* src2; void* out;
+  long ld;
+  int kind, transposed, R, K, R_src, K_src, RB, block_begin;
+};
+struct PackJobs {
+  PackJob j[40];
+  int n;
+};
+void launch_pack_jobs(PackJobs& jobs, cudaStream_t st);   // resets jobs.n to 0
+
 // W_hh [3H, H] -> forward-step slices (mode 0: P16 RB=96, rows (slice c, gate g, unit j) = W_hh[g*H + 32c + j, :], K = H)
 //               or backward-step slices (mode 1: per slice c a P16 RB=128 matrix [rows = unit u, K = 128]:
 //                                        value(u, k = g*32 + j) = W_hh[g*H + 32c + j, u], zero for k >= 96)

@@ -7,13 +7,13 @@ namespace vb {
 // One thread produces one 16-byte atom row (8 consecutive k) of both planes.
 // value(r, k) = src[rm * ld + km]  (or src[km * ld + rm] when transposed), rm = row_map ? row_map[r] : r, idem km;
 // out-of-range / negative map entries give 0.
-__global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src, int K_src,
-                                const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
-                                __nv_bfloat16* __restrict__ out) {
+__device__ __forceinline__ void pack_p16_body(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src,
+                                              int K_src, const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
+                                              __nv_bfloat16* __restrict__ out, long bid, long nb) {
   const int nkc = (K + KCHUNK - 1) / KCHUNK;
   const int nrb = (R + RB - 1) / RB;
   const long total = (long)nrb * RB * nkc * 8;           // atom rows
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+  for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
     // transposed sources are contiguous along r, others along k: pick the thread order that coalesces the reads
     long r, k8g;
     if (transposed) {
@@ -44,6 +44,11 @@ __global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int tran
     *reinterpret_cast<uint4*>(tile + (size_t)RB * KCHUNK + off) = lo;
   }
 }
+__global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src, int K_src,
+                                const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
+                                __nv_bfloat16* __restrict__ out) {
+  pack_p16_body(src, ld, transposed, R, K, R_src, K_src, row_map, col_map, RB, out, blockIdx.x, gridDim.x);
+}
 
 void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
                      const int* col_map, int RB, void* out, cudaStream_t st) {
@@ -61,12 +66,13 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
 // ------------------------------------------------------------------------------------------------
 // W_hh slices for the recurrent step kernels (see kernels.h)
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out) {
+__device__ __forceinline__ void pack_whh_body(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out, long bid,
+                                              long nb) {
   const int nsl = H / 32;
   if (mode == 0) {
     const int nkc = (H + KCHUNK - 1) / KCHUNK;
     const long total = (long)nsl * 96 * nkc * 8;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
       const int k8g = (int)(idx % (nkc * 8));
       const int p = (int)(idx / (nkc * 8));            // packed row
       const int c = p / 96, g = (p % 96) / 32, j = p % 32;
@@ -84,7 +90,7 @@ __global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __
   } else {
     const int nrb = (H + 127) / 128;
     const long total = (long)nsl * nrb * 128 * 2 * 8;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
       const int u = (int)(idx % (nrb * 128));          // coalesced along u (source columns)
       const long rest = idx / (nrb * 128);
       const int k8g = (int)(rest % 16), c = (int)(rest / 16);
@@ -104,6 +110,9 @@ __global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __
     }
   }
 }
+__global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out) {
+  pack_whh_body(w, H, mode, out, blockIdx.x, gridDim.x);
+}
 void launch_pack_whh(const float* w_hh, int H, int mode, void* out, cudaStream_t st) {
   count_launch();
   pack_whh_kernel<<<148, 256, 0, st>>>(w_hh, H, mode, (__nv_bfloat16*)out);
@@ -120,6 +129,47 @@ __global__ void bias_fuse_kernel(const float* __restrict__ bi0, const float* __r
 void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1, const float* b_hh1, int H, float* out, cudaStream_t st) {
   count_launch();
   bias_fuse_kernel<<<(6 * H + 255) / 256, 256, 0, st>>>(b_ih0, b_hh0, b_ih1, b_hh1, H, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched packing: one launch executes a table of independent pack jobs (the ~50 weight re-packs after every optimizer
+// step would otherwise be ~50 serial 3-us launches)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_jobs_kernel(const PackJobs jobs) {
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.j[j + 1].block_begin) ++j;
+  const PackJob& J = jobs.j[j];
+  const long bid = blockIdx.x - J.block_begin;
+  const long nb = (j + 1 < jobs.n ? jobs.j[j + 1].block_begin : (int)gridDim.x) - J.block_begin;
+  if (J.kind == 0) {
+    pack_p16_body(J.src, J.ld, J.transposed, J.R, J.K, J.R_src, J.K_src, nullptr, nullptr, J.RB, (__nv_bfloat16*)J.out, bid, nb);
+  } else if (J.kind == 1 || J.kind == 2) {
+    pack_whh_body(J.src, J.R, J.kind - 1, (__nv_bfloat16*)J.out, bid, nb);
+  } else {                                         // fused projection bias: out[i] = b_ih[i] + (i < 2H ? b_hh[i] : 0), R = H
+    const int H = J.R;
+    for (long i = bid * blockDim.x + threadIdx.x; i < 3L * H; i += nb * blockDim.x)
+      ((float*)J.out)[i] = J.src[i] + (i < 2 * H ? J.src2[i] : 0.f);
+  }
+}
+void launch_pack_jobs(PackJobs& jobs, cudaStream_t st) {
+  if (jobs.n == 0) return;
+  int total = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    PackJob& J = jobs.j[i];
+    long work;
+    if (J.kind == 0) work = (long)((J.R + J.RB - 1) / J.RB) * J.RB * ((J.K + KCHUNK - 1) / KCHUNK) * 8;
+    else if (J.kind == 1) work = (long)(J.R / 32) * 96 * ((J.R + KCHUNK - 1) / KCHUNK) * 8;
+    else if (J.kind == 2) work = (long)(J.R / 32) * ((J.R + 127) / 128) * 128 * 16;
+    else work = 3L * J.R;
+    long nb = (work + 255) / 256;
+    if (nb > 96) nb = 96;
+    if (nb < 1) nb = 1;
+    J.block_begin = total;
+    total += (int)nb;
+  }
+  count_launch();
+  pack_jobs_kernel<<<total, 256, 0, st>>>(jobs);
+  jobs.n = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
