@@ -90,7 +90,10 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
  * gradients wrt pred / future / z (kept in the workspace for vame_backward).
  * hyper: device float[8] {lr, kl_weight, beta, kmeans_lambda, ...} or NULL to use the cfg scalars.
  * losses_out: device float[8] = {rec, fut, kl, kmeans, total, 0, 0, 0}. */
-int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts, const float* hyper, float* losses_out, int want_grads, void* ws,
+/* target: optional [B, T, F] reconstruction target when it differs from the forward input (cfg['noise'], rnn_vae.py:116-124:
+ * the model sees x + noise, the loss compares against the clean x); NULL = the forward input. */
+int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts,
+              const float* target, long t_bs, long t_ts, const float* hyper, float* losses_out, int want_grads, void* ws,
               size_t ws_bytes, void* stream);
 
 /* Backward of the last vame_forward (replaces loss.backward(), rnn_vae.py:142).  If use_loss_grads != 0 the upstream

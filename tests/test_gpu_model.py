@@ -214,3 +214,56 @@ def test_module_surface_and_autograd(golden_dir):
     with torch.no_grad():
         p2 = model(x)[0]
     assert rel(p2, pred) > 1e-5
+
+
+def test_noisy_input_clean_target(golden_dir):
+    """cfg['noise']: the model sees x + noise, the reconstruction loss compares against the clean x (rnn_vae.py:116-124)."""
+    g = np.load(os.path.join(golden_dir, "step_small_nofut.npz"))
+    B, T, F, Z, H, fut, S = (int(v) for v in g["cfg"])
+    port, eng = make(T, Z, F, fut, S, H)
+    x, eps = torch.from_numpy(g["x"]), torch.from_numpy(g["eps"])
+    torch.manual_seed(3)
+    xn = x + 0.3 * torch.randn_like(x)
+    port.zero_grad()
+    pred, z, mu, lv = port.forward(xn, eps)
+    ref = vo.reconstruction_loss(x, pred, "sum") + 0.7 * vo.kullback_leibler_loss(mu, lv) + 0.7 * vo.cluster_loss(z.T, Z, 0.1, B)
+    ref.backward()
+    eng.forward(xn.cuda(), eps.cuda(), save=True, want=())
+    cfg = eng.loss_cfg(kmeans_loss=Z, kmeans_lambda=0.1, bsize=B, beta=1.0, kl_weight=0.7)
+    ls = eng.loss(cfg, None, want_grads=True, target=x.cuda()).cpu().tolist()
+    assert abs(ls[4] - ref.item()) <= LOSS_TOL * abs(ref.item())
+    eng.backward(cfg)
+    gv = eng.views(eng.grad)
+    for k, p in port.named_parameters():
+        assert rel(gv[k], p.grad) <= GRAD_TOL, k
+
+
+def test_device_window_sampler_and_train_epoch(tmp_path):
+    """on-device sampler feeding the drop-in train()/test(); statistics files and batch shapes follow the
+    reference dataset, the loss goes down over a few epochs."""
+    from vame_b200.dataloader import DeviceWindowSampler
+    from vame_b200.rnn_model import RNN_VAE
+    from vame_b200 import rnn_vae as rv
+    T, F, Z, H, S, B = 10, 6, 5, 32, 4, 64
+    rng = np.random.default_rng(0)
+    series = np.cumsum(rng.standard_normal((F, 3000)), axis=1)
+    d = str(tmp_path) + os.sep
+    np.save(d + "train_seq.npy", series)
+    np.save(d + "test_seq.npy", series[:, :600])
+    tr = DeviceWindowSampler(d, "train_seq.npy", True, 2 * T, B, seed=1)
+    te = DeviceWindowSampler(d, "test_seq.npy", False, 2 * T, B // 4, seed=2)
+    assert abs(float(np.load(d + "seq_mean.npy")) - series.mean()) < 1e-12 and len(tr) == 3000 // B
+    batch = next(iter(tr))
+    assert tuple(batch.shape) == (B, F, 2 * T) and batch.is_cuda
+    torch.manual_seed(19)
+    model = RNN_VAE(2 * T, Z, F, True, S, H, H, H, H, 0, 0, 0, False).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3, amsgrad=True)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=1)
+    first = last = None
+    for epoch in range(1, 5):
+        r = rv.train(tr, epoch, model, opt, "linear", 1, 0, 4, 2 * T, True, S, sched, "sum", "sum", Z, 0.1, B, epoch == 4)
+        first = r[4] if first is None else first
+        last = r[4]
+    assert last < 0.8 * first, (first, last)
+    mse, loss, km = rv.test(te, 4, model, opt, 1, 1.0, 2 * T, "sum", Z, 0.1, True, B // 4)
+    assert np.isfinite(mse) and np.isfinite(loss)

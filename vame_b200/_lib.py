@@ -28,7 +28,8 @@ SIGNATURES = {
     "vame_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vame_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "vame_loss": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "vame_loss": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_void_p, c_int,
+                          c_void_p, c_size_t, c_void_p]),
     "vame_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vame_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_void_p, c_void_p, c_void_p,

@@ -40,7 +40,7 @@ struct DecBuf {
   float* dhid;       // [B, 2H]
   void* dhid_p; void* dhidT_p;
   float* dz;         // [B, Z]
-  float* target_tb;  // [steps*B_pad, F]  (future decoder only; the reconstruction target is x_tb)
+  float* target_tb;  // [steps*B_pad, F]  future target / optional clean reconstruction target (default: x_tb)
 };
 
 struct Ws {
@@ -136,7 +136,7 @@ static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
     carve_gru(A, D.g, steps, Hd, Z, Bp, training, true, /*gi_full=*/false, false, false, /*own_h0=*/true);
     D.hid = A.f32((size_t)B * 2 * Hd);
     D.pred_tb = A.f32((size_t)r * F);
-    D.target_tb = i == 1 ? A.f32((size_t)r * F) : nullptr;
+    D.target_tb = A.f32((size_t)r * F);
     if (training) {
       D.dpred_tb = A.f32((size_t)r * F);
       D.dpred_p = A.raw(p16_bytes((int)r, F, 128));
@@ -656,8 +656,8 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
   return check_launch("vame_forward");
 }
 
-int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts, const float* hyper,
-              float* losses_out, int want_grads, void* ws, size_t ws_bytes, void* stream) {
+int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts, const float* target,
+              long t_bs, long t_ts, const float* hyper, float* losses_out, int want_grads, void* ws, size_t ws_bytes, void* stream) {
   if (check_dims(d)) return -1;
   VB_REQUIRE(cfg && ws && losses_out && batch > 0, "vame_loss: null pointer");
   const bool training = want_grads != 0;
@@ -672,7 +672,12 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
   edge(st, sA);
   launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
                        training ? w.dz_km : nullptr, w.acc, sA);
-  launch_mse(w.dec[0].pred_tb, F, w.x_tb, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
+  const float* rec_target = w.x_tb;
+  if (target) {                              // clean target of a noisy forward input
+    launch_bt_to_tb(target, batch, T, F, t_bs, t_ts, Bp, w.dec[0].target_tb, st);
+    rec_target = w.dec[0].target_tb;
+  }
+  launch_mse(w.dec[0].pred_tb, F, rec_target, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
              training ? w.dec[0].dpred_tb : nullptr, w.acc, ACC_REC, st);
   double nfut = 1.0;
   if (with_fut) {

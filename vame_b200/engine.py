@@ -186,7 +186,7 @@ class Engine:
                            float(kmeans_lambda), float(bsize if bsize is not None else 0), float(beta), float(kl_weight),
                            int(bool(with_future) and bool(d.future_decoder)), 0)
 
-    def loss(self, cfg, fut=None, want_grads=True, use_hyper=False, out=None):
+    def loss(self, cfg, fut=None, want_grads=True, use_hyper=False, out=None, target=None):
         """Loss terms of the last forward -> device float tensor [rec, fut, kl, kmeans, total, ...]."""
         B, save = self._last
         assert (not want_grads) or save, "loss gradients need forward(save=True)"
@@ -199,7 +199,12 @@ class Engine:
             if fut.stride(2) != 1:
                 fut = fut.contiguous()
             fs0, fs1 = fut.stride(0), fut.stride(1)
-        L.check(self.lib.vame_loss(ctypes.byref(self.dims), B, ctypes.byref(cfg), L.ptr(fut), fs0, fs1,
+        ts0 = ts1 = 0
+        if target is not None:
+            if target.stride(2) != 1:
+                target = target.contiguous()
+            ts0, ts1 = target.stride(0), target.stride(1)
+        L.check(self.lib.vame_loss(ctypes.byref(self.dims), B, ctypes.byref(cfg), L.ptr(fut), fs0, fs1, L.ptr(target), ts0, ts1,
                                    L.ptr(self.hyper) if use_hyper else None, L.ptr(out), int(want_grads), L.ptr(ws), ws.numel(),
                                    L.cur_stream()), "vame_loss")
         return out

@@ -96,6 +96,22 @@ def _engine_of(model):
     return model.engine
 
 
+def _train_step(model, eng, batch, cfg, world, betas, adam_eps):
+    """Cached engine.TrainStep (captured CUDA graphs) for this batch size / loss configuration; hyper-parameters that change
+    between epochs (lr, kl_weight, beta, lambda) are read from device memory, so the graphs stay valid."""
+    from .engine import TrainStep
+    key = (int(batch), cfg.mse_red_mean, cfg.mse_pred_mean, cfg.kmeans_loss, float(cfg.bsize), cfg.with_future, int(world),
+           tuple(betas), float(adam_eps))
+    cache = model.__dict__.setdefault("_b200_steps", {})
+    ts = cache.get(key)
+    if ts is None:
+        import copy
+        ts = TrainStep(eng, batch, copy.copy(cfg), world=world, betas=betas, eps=adam_eps)
+        ts.capture()
+        cache[key] = ts
+    return ts
+
+
 def _to_device(data_item, seq_len_half, future_steps, device):
     """rnn_vae.py:107-112: (B, F, 2T) float64 loader item -> data (B,T,F), fut (B,S,F) float32 on the GPU."""
     data_item = data_item.permute(0, 2, 1)
@@ -120,17 +136,22 @@ def train(train_loader, epoch, model, optimizer, anneal_function, BETA, kl_start
     world = _world()
     idx = -1
     loss_last = None
+    eng.set_hyper(lr=lr, kl_weight=kl_weight, beta=BETA, kmeans_lambda=klmbda)
     for idx, data_item in enumerate(train_loader):
         data, fut = _to_device(data_item, seq_len_half, future_steps, eng.device)
-        data_in = gaussian(data, True, seq_len_half) if noise == True else data      # noqa: E712
         eps = torch.randn(data.shape[0], eng.dims.zdims, device=eng.device)
-        eng.forward(data_in, eps, save=True, want=())
-        if noise == True:   # noqa: E712  the loss target is the clean data (rnn_vae.py:124): overwrite the saved target
-            raise NotImplementedError("vame_b200: cfg['noise']=True is not supported by the fused step yet")
-        losses = eng.loss(cfg, fut if future_decoder else None, want_grads=True)
-        eng.backward(cfg)
-        allreduce_gradients(eng)
-        eng.adam_step(lr=lr, betas=betas, eps=adam_eps, grad_scale=1.0 / world)
+        if noise == True:   # noqa: E712
+            # with input noise the model sees data_gaussian but the loss target stays the clean data (rnn_vae.py:116-124)
+            eng.forward(gaussian(data, True, seq_len_half), eps, save=True, want=())
+            losses = eng.loss(cfg, fut if future_decoder else None, want_grads=True, target=data)
+            eng.backward(cfg)
+            allreduce_gradients(eng)
+            eng.adam_step(lr=lr, betas=betas, eps=adam_eps, grad_scale=1.0 / world)
+        else:
+            # steady state: the whole step is two CUDA-graph replays around the (optional) NCCL allreduce
+            ts = _train_step(model, eng, data.shape[0], cfg, world, betas, adam_eps)
+            ts.load(data, fut if future_decoder else None, eps)
+            losses = ts.run()
         acc += losses.double()
         loss_last = losses
     if idx < 0:
