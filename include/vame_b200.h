@@ -135,6 +135,10 @@ int vame_decoder_forward(const vame_dims* d, int batch, int which, const float* 
 int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* params, const void* packed, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* measurement hook: per-section timeline of vame_forward / vame_backward (eager mode only, not graph-capturable) */
+int vame_debug_timeline(int enable);
+int vame_debug_timeline_read(const char** names, float* ms, int max);
+
 /* k-means prior on its own (cluster_loss, rnn_vae.py:45-50): loss_out device double[1], dlatent [B, Z] or NULL */
 int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef,
                       double* loss_out, float* dlatent, void* stream);

@@ -65,6 +65,17 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
             for i in range(4):
                 tot[i] += ev[i].elapsed_time(ev[i + 1]) / 10
         print("[%s pdl=%d] phases ms: forward %.3f loss %.3f backward %.3f adam+repack %.3f" % ((mode, pdl) + tuple(tot)), flush=True)
+        # section timeline of one eager step (cudaEvents at section boundaries on the main stream)
+        import ctypes as _ct
+        lib.vame_debug_timeline(1)
+        eng.forward(ts.x, ts.eps, save=True, want=(), ensure_packed=False)
+        eng.loss(cfg, ts.fut if fut else None, want_grads=True, use_hyper=True, out=ts.losses)
+        eng.backward(cfg, use_hyper=True)
+        names = (_ct.c_char_p * 64)()
+        msv = (_ct.c_float * 64)()
+        nsec = lib.vame_debug_timeline_read(names, msv, 64)
+        lib.vame_debug_timeline(0)
+        print("[%s pdl=%d] SECTIONS " % (mode, pdl) + " | ".join("%s %.0fus" % (names[i].decode(), msv[i] * 1e3) for i in range(nsec)), flush=True)
         # host-side launch cost
         t0 = time.perf_counter()
         for _ in range(5):
@@ -106,7 +117,7 @@ if __name__ == "__main__":
               int(sys.argv[6]) if len(sys.argv) > 6 else 1, int(sys.argv[7]) if len(sys.argv) > 7 else 1)
         sys.exit(0)
     workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    for mode, pdl, streams, pers, flags in (("eager", 1, 1, 0, 1), ("eager", 1, 1, 2, 1), ("eager", 1, 1, 0, 0), ("graph", 1, 1, 0, 1), ("graph", 1, 1, 2, 1), ("graph", 1, 1, 2, 0)):
+    for mode, pdl, streams, pers, flags in (("eager", 1, 1, 2, 0), ("graph", 1, 1, 2, 0)):
         print("##### variant mode=%s pdl=%d streams=%d persistent=%d flags=%d" % (mode, pdl, streams, pers, flags), flush=True)
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", mode, str(pdl), workload, str(streams), str(pers), str(flags)], timeout=150,

@@ -17,6 +17,8 @@ SIGNATURES = {
     "vame_launch_count": (c_long, []),
     "vame_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "vame_set_debug_buffer": (c_int, [c_void_p]),
+    "vame_debug_timeline": (c_int, [c_int]),
+    "vame_debug_timeline_read": (c_int, [c_void_p, c_void_p, c_int]),
     "vame_debug_gru_sweep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vame_p16_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vame_pack_p16": (c_int, [c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -186,6 +186,25 @@ static Side& side() {
   }
   return S;
 }
+// ---- optional section timeline (measurement hook): cudaEvents on the caller's stream at section boundaries -------------
+struct Timeline {
+  bool on = false;
+  int n = 0;
+  cudaEvent_t ev[64];
+  const char* name[64];
+};
+static Timeline& timeline() {
+  static Timeline T;
+  return T;
+}
+static inline void mark(cudaStream_t st, const char* name) {
+  Timeline& T = timeline();
+  if (!T.on || T.n >= 64) return;
+  if (!T.ev[T.n]) cudaEventCreate(&T.ev[T.n]);
+  cudaEventRecord(T.ev[T.n], st);
+  T.name[T.n++] = name;
+}
+
 // make `to` wait for everything enqueued on `from` so far
 static inline void edge(cudaStream_t from, cudaStream_t to) {
   if (from == to) return;
@@ -512,11 +531,14 @@ static void encoder_forward(const vame_dims& d, const float* P, const ParamLayou
   // layer 0: gi = x W_ih^T + (b_ih + [b_hr, b_hz, 0]) for both directions at once
   GemmB().A(w.x_p, nkc_of(F), nkc_of(F)).Bm(W.e0.wih_p[0], nkc_of(F), nkc_of(F))
       .run_fm(rows, 6 * H, w.e0.gi, rows, W.e0.bias_gi, st);
+  mark(st, "enc:x pack + gi0 gemm");
   gru_sweep_fwd(W.e0, P + L.e0.bhh[0] + 2 * H, P + L.e0.bhh[1] + 2 * H, w.e0, w.tiles, save, true, st);
+  mark(st, "enc:L0 sweep");
   // layer 1: input = [out_f(t), out_b(t)] (rnn_model.py:41, inter-layer dropout is 0 by default)
   GemmB().A(w.e0.out_p[0], nkcH, nkcH).A(w.e0.out_p[1], nkcH, nkcH)
       .Bm(W.e1.wih_p[0], nkcH, nkcH).Bm(W.e1.wih_p[1], nkcH, nkcH)
       .run_fm(rows, 6 * H, w.e1.gi, rows, W.e1.bias_gi, st);
+  mark(st, "enc:gi1 gemm");
   gru_sweep_fwd(W.e1, P + L.e1.bhh[0] + 2 * H, P + L.e1.bhh[1] + 2 * H, w.e1, w.tiles, save, true, st);
 }
 
@@ -633,12 +655,15 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int T = d->time_window, F = d->num_features, Z = d->zdims;
   cudaMemsetAsync(w.acc, 0, 8 * sizeof(double), st);
+  mark(st, "fwd:start");
   encoder_forward(*d, params, L, W, w, x, x_bs, x_ts, save, st);
+  mark(st, "fwd:encoder done");
   const void* hp[4] = {final_h_p(w.e0, 0, w.tiles), final_h_p(w.e0, 1, w.tiles), final_h_p(w.e1, 0, w.tiles), final_h_p(w.e1, 1, w.tiles)};
   lambda_linear(*d, params, L, W, w, hp, st);
   if (eps) cudaMemcpyAsync(w.eps, eps, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
   launch_lambda_fwd(w.lin, 2 * Z, eps ? w.eps : nullptr, batch, Z, d->softplus, w.z, w.mu, w.logvar, w.acc, st);
   pack_rows(w.z, Z, w.B_pad, Z, batch, w.z_p, st);
+  mark(st, "fwd:lambda done");
   cudaStream_t sA = (d->future_decoder && g_opt_streams) ? side().s[0] : st;
   if (d->future_decoder) {
     edge(st, sA);
@@ -646,6 +671,7 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
   }
   decoder_forward(*d, 0, params, L, W, w, save, st);
   if (d->future_decoder) edge(sA, st);
+  mark(st, "fwd:decoders done");
   if (pred) launch_tb_to_bt(w.dec[0].pred_tb, batch, T, F, w.B_pad, pred, st);
   if (future && d->future_decoder) launch_tb_to_bt(w.dec[1].pred_tb, batch, d->future_steps, F, w.B_pad, future, st);
   if (z) cudaMemcpyAsync(z, w.z, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
@@ -723,6 +749,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     w.e0.h0[dd] = w.zeros_f32; w.e0.h0_p[dd] = w.zeros_p;
     w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
   }
+  mark(st, "bwd:start");
   pack_T(w.z, Z, Z, Bp, B, w.zT_p, st);                                   // [Z rows, K = B_pad]
   edge(st, sB);
   // operands that only depend on the forward pass: transposed activations for the weight-gradient GEMMs
@@ -753,7 +780,9 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     // ---- data-gradient chain: hidden_to_output backward, BPTT, dz
     pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);
     GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_fm((int)rows, 2 * Hd, D.ddec, rows, nullptr, sd);
+    if (i == 0) mark(st, "bwd:dec dpred pack + ddec gemm");
     gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + (size_t)Hd * rows, rows, nullptr, nullptr, 0, true, sd);
+    if (i == 0) mark(st, "bwd:dec sweep");
     for (int dd = 0; dd < 2; ++dd) {         // the input is z at every step -> reduce dgi over time first
       launch_timesum_fm(D.g.dgi[dd], rows, steps, Bp, 3 * Hd, D.dgi_sum[dd], sd);                // [3H][B_pad]
       pack_T(D.dgi_sum[dd], Bp, Bp, 3 * Hd, 3 * Hd, D.dgi_sum_p[dd], sd);                        // -> [B_pad rows, K = 3H]
@@ -786,6 +815,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     launch_colsum(D.dhid, 2 * Hd, B, 2 * Hd, G + L.l2h_b[i], sw);
   }
 
+  mark(st, "bwd:dec dz chain");
   // ---- Lambda backward (main chain: dlin -> dhidden)
   if (use_loss_grads && g_opt_streams) edge(side().s[2], st);   // k-means prior gradient (vame_loss may have left it running)
   {
@@ -819,10 +849,12 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     }
   }
 
+  mark(st, "bwd:lambda bwd + dhidden gemm");
   // ---- encoder layer 1 (only h_n is used downstream, rnn_model.py:41-43: no per-step output gradient)
   const long rows = (long)T * Bp;
   const int nk = (int)(rows / KCHUNK), nkc3 = nkc_of(3 * H);
   gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * Bp, w.dhidden + (size_t)3 * H * Bp, Bp, true, st);
+  mark(st, "bwd:L1 sweep");
   edge(st, sB);
   GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
       .run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
@@ -834,6 +866,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
           .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sB);
   }
   // ---- encoder layer 0
+  mark(st, "bwd:dx1 gemm");
   gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st);
   edge(st, sB);
   gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB);
@@ -841,7 +874,9 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     pack_rows(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], sB);
     GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sB);
   }
+  mark(st, "bwd:L0 sweep");
   edge(sB, st);
+  mark(st, "bwd:side-stream tail (weight gradients)");
   if (used_sA) edge(sA, st);                 // only streams that were forked into this call may be joined (graph capture isolation)
   return check_launch("vame_backward");
 }
@@ -872,6 +907,29 @@ int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* 
   if (which == 0) gru_sweep_fwd(W.e1, params + L.e1.bhh[0] + 2 * H, params + L.e1.bhh[1] + 2 * H, w.e1, w.tiles, true, true, st);
   else gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * w.B_pad, w.dhidden + (size_t)3 * H * w.B_pad, w.B_pad, true, st);
   return check_launch("vame_debug_gru_sweep");
+}
+
+/* measurement hook: enable = 1 starts recording section boundaries (cudaEvents on the caller's stream) in the next
+ * vame_forward / vame_backward calls; vame_debug_timeline_read synchronises and returns the number of sections, their
+ * names (static strings) and durations in ms. */
+int vame_debug_timeline(int enable) {
+  Timeline& T = timeline();
+  T.on = enable != 0;
+  T.n = 0;
+  return 0;
+}
+int vame_debug_timeline_read(const char** names, float* ms, int max) {
+  Timeline& T = timeline();
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (int i = 1; i < T.n && n < max; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, T.ev[i - 1], T.ev[i]);
+    names[n] = T.name[i];
+    ms[n++] = t;
+  }
+  T.n = 0;
+  return n;
 }
 
 int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef, double* loss_out,
