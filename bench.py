@@ -269,7 +269,10 @@ def main():
         ts._phase1()                                       # leaves forward + backward state in the workspace
         ws = eng.workspace(B, True)
         res = {}
-        for which, name in ((0, "gru_step_fwd_kernel"), (1, "gru_step_bwd_kernel")):
+        pers = lib.vame_get_option(b"persistent")
+        names = ("gru_seq_fwd_kernel (per time step)" if pers & 1 else "gru_step_fwd_kernel",
+                 "gru_seq_bwd_kernel (per time step)" if pers & 2 else "gru_step_bwd_kernel")
+        for which, name in ((0, names[0]), (1, names[1])):
             for _ in range(3):
                 L.check(lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, which, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream()), "sweep")
             torch.cuda.synchronize()
@@ -284,13 +287,18 @@ def main():
         flops_launch = 2 * B * (3 * H) * H * 2                      # both directions: [B,H] x [H,3H] MACs, MAC = 2 FLOP
         dom = max(res, key=res.get)
         ach = flops_launch / res[dom] / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom.split(" ")[0])
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
-                "traffic": None, "peak_source": how + ", burst figure (kernel timed alone)",
-                "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 3 * flops_launch,
+                "traffic": traffic, "peak_source": how + ", burst figure (kernel timed alone)",
+                "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 4 * flops_launch,
                 "us_per_launch": {k: v * 1e6 for k, v in res.items()},
-                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction; the kernel issues 3x that in bf16 MMAs "
-                        "(hi*hi + hi*lo + lo*hi), so the algorithmic ceiling is 1/3 of the bf16 peak; B=%d leaves most SMs idle "
-                        "(latency-bound recurrence)" % B,
+                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 3-4x that in "
+                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/3 of the bf16 peak; B=%d keeps 32 of 148 "
+                        "SMs busy in a serial chain of %d dependent steps (latency-bound: ~1.5 us of MMA in a ~7-10 us step, "
+                        "DESIGN.md section 4)" % (B, 6 * T),
                 "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
                 "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
 

@@ -24,6 +24,7 @@ long vame_launch_count(void);
  * "streams" (default 1) runs independent branches on internal side streams; "persistent" (default 2) bit0/bit1 select the
  * persistent cluster kernel for the forward/backward sweeps */
 int vame_set_option(const char* name, int value);
+int vame_get_option(const char* name);   /* -1 for unknown names */
 /* measurement hook: device buffer of 16 uint64 that gru_step_fwd_kernel's CTA 0 fills with %globaltimer stamps (NULL = off) */
 int vame_set_debug_buffer(void* device_u64x16);
 

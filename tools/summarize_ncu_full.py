@@ -17,8 +17,13 @@ def main(rep, out=None, title=""):
     hdr, units = rd[0], rd[1]
     idx = {h: i for i, h in enumerate(hdr)}
     lines = ["# %s" % (title or rep), "", "`ncu --set full --clock-control none --import-source on` (one GPU, cold caches per replay).", ""]
+    seen = {}
     for row in rd[2:]:
-        lines.append("## %s" % row[idx["Kernel Name"]].strip())
+        kn = row[idx["Kernel Name"]].strip()
+        seen[kn] = seen.get(kn, 0) + 1
+        if seen[kn] > 2:
+            continue
+        lines.append("## %s" % kn)
         lines.append("")
         lines.append("| metric | value | unit |")
         lines.append("|---|---:|---|")

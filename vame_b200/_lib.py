@@ -16,6 +16,7 @@ SIGNATURES = {
     "vame_abi_version": (c_int, []),
     "vame_launch_count": (c_long, []),
     "vame_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "vame_get_option": (c_int, [ctypes.c_char_p]),
     "vame_set_debug_buffer": (c_int, [c_void_p]),
     "vame_debug_timeline": (c_int, [c_int]),
     "vame_debug_timeline_read": (c_int, [c_void_p, c_void_p, c_int]),

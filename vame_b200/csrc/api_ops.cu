@@ -27,6 +27,15 @@ int vame_set_debug_buffer(void* device_u64x16) {
   return 0;
 }
 
+int vame_get_option(const char* name) {
+  if (!name) return -1;
+  if (strcmp(name, "pdl") == 0) return vb::g_opt_pdl;
+  if (strcmp(name, "persistent") == 0) return vb::g_opt_persistent;
+  if (strcmp(name, "flags") == 0) return vb::g_opt_flags;
+  if (strcmp(name, "streams") == 0) return vb::g_opt_streams;
+  return -1;
+}
+
 int vame_set_option(const char* name, int value) {
   VB_REQUIRE(name, "vame_set_option: null name");
   if (strcmp(name, "pdl") == 0) {
