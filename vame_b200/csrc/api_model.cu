@@ -361,7 +361,7 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
     GruFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
     a.flags = use_flags ? 1 : 0;
-    a.flag_expected = (unsigned int)(H / 32) * 8u;            // every warp of every slice CTA signals once
+    a.flag_expected = (unsigned int)(H / 32) * (g_opt_warps16 ? 16u : 8u);   // every warp of every slice CTA signals once
     for (int d = 0; d < 2; ++d) {
       const int t = d == 0 ? s : L.steps - 1 - s;
       const int tprev = d == 0 ? t - 1 : t + 1;

@@ -64,6 +64,52 @@ __device__ __forceinline__ void st16_p16(__nv_bfloat16* tile, int rows_in_tile, 
   *reinterpret_cast<uint4*>(lo + off + 64) = lo1;
 }
 
+// ---- width-generic versions (N = values per thread: 16 with 8 warps per CTA, 8 with 16 warps per CTA) ----
+template <int N>
+__device__ __forceinline__ void ldN(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+template <int N>
+__device__ __forceinline__ void ldfN(const float* p, long ld, float* v) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = p[i * ld];
+}
+template <int N>
+__device__ __forceinline__ void stfN(float* p, long ld, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i * ld] = v[i];
+}
+template <int N>
+__device__ __forceinline__ void stN_p16(__nv_bfloat16* tile, int rows_in_tile, int r, int k, const float* v) {
+  __nv_bfloat16* lo = tile + (size_t)rows_in_tile * KCHUNK;
+  const int off = p16_in_tile(r, k);
+#pragma unroll
+  for (int a = 0; a < N / 8; ++a) {
+    uint4 h, l;
+    split8(v + 8 * a, h, l);
+    *reinterpret_cast<uint4*>(tile + off + 64 * a) = h;
+    *reinterpret_cast<uint4*>(lo + off + 64 * a) = l;
+  }
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, float* v) {
+  if constexpr (N == 16) tmem_ld16(taddr, v);
+  else tmem_ld8(taddr, v);
+}
+
 // optional in-kernel timeline (vame_set_debug_buffer): CTA (0,0,0) thread 0 records %globaltimer at fixed points
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -85,7 +131,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 constexpr int F_WTILE = 96 * KCHUNK * 2 * 2;     // 24576 B : one K chunk of the W slice (hi + lo)
 constexpr int F_ATILE = 128 * KCHUNK * 2 * 2;    // 32768 B : one K chunk of the h tile (hi + lo)
 
-__global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a) {
+template <int UPT>
+__global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(const GruFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nkc = (H + KCHUNK - 1) / KCHUNK;
   uint8_t* sW = smem;
@@ -98,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   const int c = blockIdx.x, tile = blockIdx.y;
   const GruDirFwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
@@ -131,15 +178,15 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   }
   const int r_in = q * 32 + lane;
   const long b = (long)tile * 128 + r_in;
-  const int j0 = half * 16;            // first unit inside the slice
+  const int j0 = half * UPT;           // first unit inside the slice
   const int u0 = c * 32 + j0;          // first hidden unit handled by this thread
-  float gir[16], giz[16], gin[16], bhn[16];
+  float gir[UPT], giz[UPT], gin[UPT], bhn[UPT];
   {
     const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts);
-    ldf16(gi_row + (long)u0 * d.gi_ld, d.gi_ld, gir);
-    ldf16(gi_row + (long)(H + u0) * d.gi_ld, d.gi_ld, giz);
-    ldf16(gi_row + (long)(2 * H + u0) * d.gi_ld, d.gi_ld, gin);
-    ld16(d.b_hn + u0, bhn);
+    ldfN<UPT>(gi_row + (long)u0 * d.gi_ld, d.gi_ld, gir);
+    ldfN<UPT>(gi_row + (long)(H + u0) * d.gi_ld, d.gi_ld, giz);
+    ldfN<UPT>(gi_row + (long)(2 * H + u0) * d.gi_ld, d.gi_ld, gin);
+    ldN<UPT>(d.b_hn + u0, bhn);
   }
 
   DBG_STAMP(1);
@@ -192,35 +239,35 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     __syncwarp();
   }
 
-  float hprev[16];
-  if (!a.flags) ldf16(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);     // complete + visible after griddepcontrol.wait
+  float hprev[UPT];
+  if (!a.flags) ldfN<UPT>(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);     // complete + visible after griddepcontrol.wait
   mbar_wait(done, 0);                   // (with flags this also orders the h_in read below after the producer's release)
   __syncwarp();
   if (a.flags) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) hprev[i] = ld_cg(d.h_in + (long)(u0 + i) * d.h_in_ld + b);
+    for (int i = 0; i < UPT; ++i) hprev[i] = ld_cg(d.h_in + (long)(u0 + i) * d.h_in_ld + b);
   }
   DBG_STAMP(5);
   tc_fence_after();
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-  float ar[16], az[16], an[16];
+  float ar[UPT], az[UPT], an[UPT];
   {
-    float br[16], bz[16], bn[16];                 // columns 96.. hold the (* w_lo) products
-    tmem_ld16(taddr + j0, ar);
-    tmem_ld16(taddr + 32 + j0, az);
-    tmem_ld16(taddr + 64 + j0, an);
-    tmem_ld16(taddr + 96 + j0, br);
-    tmem_ld16(taddr + 128 + j0, bz);
-    tmem_ld16(taddr + 160 + j0, bn);
+    float br[UPT], bz[UPT], bn[UPT];                 // columns 96.. hold the (* w_lo) products
+    tmem_ldN<UPT>(taddr + j0, ar);
+    tmem_ldN<UPT>(taddr + 32 + j0, az);
+    tmem_ldN<UPT>(taddr + 64 + j0, an);
+    tmem_ldN<UPT>(taddr + 96 + j0, br);
+    tmem_ldN<UPT>(taddr + 128 + j0, bz);
+    tmem_ldN<UPT>(taddr + 160 + j0, bn);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
+    for (int i = 0; i < UPT; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
   }
   DBG_STAMP(8);
 
-  float hn[16];
+  float hn[UPT];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < UPT; ++i) {
     const float r = gate_sigmoid(gir[i] + ar[i]);
     const float z = gate_sigmoid(giz[i] + az[i]);
     const float ghn = an[i] + bhn[i];
@@ -229,11 +276,11 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
     ar[i] = r; az[i] = z; an[i] = n; bhn[i] = ghn;
   }
   DBG_STAMP(9);
-  stf16(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
+  stfN<UPT>(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
   {
     const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
-    st16_p16(t, 128, r_in, kk, hn);
+    stN_p16<UPT>(t, 128, r_in, kk, hn);
   }
   if (a.flags) {                        // publish: everything the next step reads is written above
     fence_proxy_async_all();
@@ -244,10 +291,10 @@ __global__ void __launch_bounds__(256, 1) gru_step_fwd_kernel(const GruFwdArgs a
   DBG_STAMP(10);
   if (d.sv_r) {
     const long so = (long)u0 * d.sv_ld + b;
-    stf16(d.sv_r + so, d.sv_ld, ar);
-    stf16(d.sv_z + so, d.sv_ld, az);
-    stf16(d.sv_n + so, d.sv_ld, an);
-    stf16(d.sv_ghn + so, d.sv_ld, bhn);
+    stfN<UPT>(d.sv_r + so, d.sv_ld, ar);
+    stfN<UPT>(d.sv_z + so, d.sv_ld, az);
+    stfN<UPT>(d.sv_n + so, d.sv_ld, an);
+    stfN<UPT>(d.sv_ghn + so, d.sv_ld, bhn);
   }
   DBG_STAMP(6);
   // flag mode: kernels complete in launch order (each waits here for its predecessor), so the completion of the last step
@@ -282,14 +329,20 @@ void launch_gru_step_fwd(const GruFwdArgs& a_in, cudaStream_t st) {
   const size_t smem = (size_t)nkc * (F_WTILE + F_ATILE) + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
   count_launch();
-  cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel, a);
+  if (g_opt_warps16) {                     // 16 warps, 8 units per thread: the serial gate epilogue is twice as parallel
+    launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 512, smem, st, a.pdl);
+    cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<8>, a);
+  } else {
+    launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
+    cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16>, a);
+  }
 }
 
 // =================================================================================================
@@ -660,7 +713,8 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
 // exchanges the H/32 partial products dgh_c W_hh[c-rows, :] with the other CTAs of the cluster through global memory
 // (L2-coherent loads) between steps.
 // =================================================================================================
-__global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs a) {
+template <int UPT>
+__global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(const GruSeqBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nrb = (H + 127) / 128, nsl = H / 32;
   const size_t wchunk = (size_t)nrb * 2 * B_APLANE;
@@ -673,7 +727,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
   const int c = blockIdx.x, tile = blockIdx.y;
   const GruSeqDirBwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
   const uint32_t tmem_cols = (H <= 32) ? 32 : (H <= 64) ? 64 : (H <= 128) ? 128 : 256;
   const long bpad = (long)a.tiles * 128;
   const size_t slotf = (size_t)bpad * H, pslot = (size_t)(nsl + 1) * slotf;
@@ -704,47 +758,47 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
   }
   const int r_in = q * 32 + lane;
   const long b = (long)tile * 128 + r_in;
-  const int j0 = half * 16, u0 = c * 32 + j0;
+  const int j0 = half * UPT, u0 = c * 32 + j0;
   const uint32_t idesc = make_idesc_bf16(128, H);
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-  const int hh = H / 2;
-  float carry[16];
+  const int hh = H / (32 / UPT);            // TMEM columns drained by each warp group
+  float carry[UPT];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) carry[i] = 0.f;
-  if (d.dh_last) ldf16(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
+  for (int i = 0; i < UPT; ++i) carry[i] = 0.f;
+  if (d.dh_last) ldfN<UPT>(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
 
   for (int s = 0; s < a.steps; ++s) {
     const int t = d.reverse ? s : a.steps - 1 - s;                       // BPTT order = reverse of the forward order
     const bool first_fwd = d.reverse ? (t == a.steps - 1) : (t == 0);
     const int tprev = d.reverse ? t + 1 : t - 1;
-    float r[16], z[16], n[16], ghn[16], hp[16], dh[16];
+    float r[UPT], z[UPT], n[UPT], ghn[UPT], hp[UPT], dh[UPT];
     {
       const long so = (long)u0 * d.sv_ld + (long)t * bpad + b;
-      ldf16(d.sv[0] + so, d.sv_ld, r);
-      ldf16(d.sv[1] + so, d.sv_ld, z);
-      ldf16(d.sv[2] + so, d.sv_ld, n);
-      ldf16(d.sv[3] + so, d.sv_ld, ghn);
+      ldfN<UPT>(d.sv[0] + so, d.sv_ld, r);
+      ldfN<UPT>(d.sv[1] + so, d.sv_ld, z);
+      ldfN<UPT>(d.sv[2] + so, d.sv_ld, n);
+      ldfN<UPT>(d.sv[3] + so, d.sv_ld, ghn);
     }
-    if (first_fwd) ldf16(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hp);
-    else ldf16(d.out + (long)u0 * d.out_ld + (long)tprev * bpad + b, d.out_ld, hp);
-    if (d.dout) ldf16(d.dout + (long)u0 * d.dout_ld + (long)t * bpad + b, d.dout_ld, dh);
+    if (first_fwd) ldfN<UPT>(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hp);
+    else ldfN<UPT>(d.out + (long)u0 * d.out_ld + (long)tprev * bpad + b, d.out_ld, hp);
+    if (d.dout) ldfN<UPT>(d.dout + (long)u0 * d.dout_ld + (long)t * bpad + b, d.dout_ld, dh);
     else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+      for (int i = 0; i < UPT; ++i) dh[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dh[i] += carry[i];
+    for (int i = 0; i < UPT; ++i) dh[i] += carry[i];
     if (s > 0) {
       cluster_wait_acquire();                                            // all partial products of the previous step are published
       const float* pin = d.parts + ((s - 1) & 1) * pslot + (long)u0 * bpad + b;
       for (int p = 0; p < nsl; ++p) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dh[i] += ld_cg(pin + (long)p * slotf + (long)i * bpad);
+        for (int i = 0; i < UPT; ++i) dh[i] += ld_cg(pin + (long)p * slotf + (long)i * bpad);
       }
     }
-    float dar[16], daz[16], dan[16], dgn[16];
+    float dar[UPT], daz[UPT], dan[UPT], dgn[UPT];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < UPT; ++i) {
       const float dn = dh[i] * (1.0f - z[i]);
       const float dz = dh[i] * (hp[i] - n[i]);
       dan[i] = dn * (1.0f - n[i] * n[i]);
@@ -756,9 +810,9 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
     {
       __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(sA);
       __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sA + 2 * B_APLANE);
-      st16_p16(a0, 128, r_in, j0, dar);
-      st16_p16(a0, 128, r_in, 32 + j0, daz);
-      st16_p16(a1, 128, r_in, j0, dgn);
+      stN_p16<UPT>(a0, 128, r_in, j0, dar);
+      stN_p16<UPT>(a0, 128, r_in, 32 + j0, daz);
+      stN_p16<UPT>(a1, 128, r_in, j0, dgn);
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -787,12 +841,12 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
     // outputs that do not need the MMA
     {
       const long o = (long)t * bpad + b;
-      stf16(d.dgi + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
-      stf16(d.dgi + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
-      stf16(d.dgi + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dan);
-      stf16(d.dgh + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
-      stf16(d.dgh + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
-      stf16(d.dgh + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dgn);
+      stfN<UPT>(d.dgi + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stfN<UPT>(d.dgi + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stfN<UPT>(d.dgi + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dan);
+      stfN<UPT>(d.dgh + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stfN<UPT>(d.dgh + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stfN<UPT>(d.dgh + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dgn);
     }
     if (d.dgi_p) {
       const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
@@ -801,21 +855,21 @@ __global__ void __launch_bounds__(256, 1) gru_seq_bwd_kernel(const GruSeqBwdArgs
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         const int k = g * H + u0;
-        st16_p16(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+        stN_p16<UPT>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
       }
     }
     float* pout = d.parts + (s & 1) * pslot;
-    if (s == a.steps - 1) stf16(pout + ((long)nsl * H + u0) * bpad + b, bpad, carry);   // final carry -> dh0 reduction
+    if (s == a.steps - 1) stfN<UPT>(pout + ((long)nsl * H + u0) * bpad + b, bpad, carry);   // final carry -> dh0 reduction
 
     mbar_wait(done, ph);
     __syncwarp();
     tc_fence_after();
     float* pbase = pout + (long)c * H * bpad + b;
     for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
-      float v[16];
-      tmem_ld16(taddr + c0, v);
+      float v[UPT];
+      tmem_ldN<UPT>(taddr + c0, v);
       tmem_ld_wait();
-      stf16(pbase + (long)c0 * bpad, bpad, v);
+      stfN<UPT>(pbase + (long)c0 * bpad, bpad, v);
     }
     tc_fence_before();
     if (s + 1 < a.steps) cluster_arrive_release();   // release at cluster scope publishes the partial sums to the peers
@@ -829,12 +883,14 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * B_APLANE + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
+  const bool w16 = g_opt_warps16 && (a.H % 64 == 0);       // each of the 4 warp groups drains H/4 (multiple of 16) columns
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(a.H / 32, a.tiles, a.ndir);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(w16 ? 512 : 256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -845,7 +901,8 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   count_launch();
-  cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel, a);
+  if (w16) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8>, a);
+  else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16>, a);
 }
 
 void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st) {

@@ -11,6 +11,7 @@ extern int g_opt_pdl;       // 1: chain the recurrent steps with programmatic de
 extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline stamps or nullptr
 extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through release/acquire flags (tail of step t overlaps t+1);
                             //    default 0: measured equal to griddepcontrol.wait (tools/gpu_probe_graph.py, profiles/)
+extern int g_opt_warps16;   // 1: 16 warps per CTA (8 hidden units per thread) in the default recurrent kernels
 extern int g_opt_streams;
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
