@@ -75,7 +75,7 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
         msv = (_ct.c_float * 64)()
         nsec = lib.vame_debug_timeline_read(names, msv, 64)
         lib.vame_debug_timeline(0)
-        print("[%s pdl=%d] SECTIONS " % (mode, pdl) + " | ".join("%s %.0fus" % (names[i].decode(), msv[i] * 1e3) for i in range(nsec)), flush=True)
+        print("[%s pdl=%d] SECTIONS (us since fwd:start) " % (mode, pdl) + " | ".join("%s @%.0f" % (names[i].decode(), msv[i] * 1e3) for i in range(nsec)), flush=True)
         # host-side launch cost
         t0 = time.perf_counter()
         for _ in range(5):

@@ -490,12 +490,15 @@ static void pack_outT(GruBuf& L, int Bp, cudaStream_t st) {      // forward acti
   const long rows = (long)L.steps * Bp;
   for (int d = 0; d < 2; ++d) pack_rows(L.out[d], rows, L.H, (int)rows, L.H, L.outT_p[d], st);   // out is already [H][rows]
 }
-static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st) {
+// dgi_rowsum_fused: the caller packs dgi (encoder layers) and lets that pass produce db_ih
+static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st,
+                                bool dgi_rowsum_fused = false) {
   const int H = L.H;
   const long rows = (long)L.steps * Bp;
   const int cB = Bp / KCHUNK, nk = (int)(rows / KCHUNK);
   for (int d = 0; d < 2; ++d) {
-    pack_rows(L.dgh[d], rows, 3 * H, (int)rows, 3 * H, L.dghT_p[d], st);                           // dgh is already [3H][rows]
+    // dgh is already [3H][rows]; its row sums (= db_hh) are accumulated by the same pass
+    launch_pack_p16_rowsum(L.dgh[d], rows, 3 * H, (int)rows, 3 * H, L.dghT_p[d], G + o.bhh[d], st);
     const void* h0T = d == 0 ? h0T0 : h0T1;
     GemmB gb;
     gb.A(L.dghT_p[d], nk, nk);
@@ -508,8 +511,7 @@ static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* 
       gb.Bm(h0T, cB, cB);
     }
     gb.run(3 * H, H, G + o.whh[d], H, nullptr, 1, splits_for(3 * H, H, nk), st);
-    launch_rowsum_fm(L.dgh[d], rows, rows, 3 * H, G + o.bhh[d], st);
-    launch_rowsum_fm(L.dgi[d], rows, rows, 3 * H, G + o.bih[d], st);
+    if (!dgi_rowsum_fused) launch_rowsum_fm(L.dgi[d], rows, rows, 3 * H, G + o.bih[d], st);
   }
 }
 
@@ -756,6 +758,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   pack_outT(w.e0, Bp, sB);
   pack_outT(w.e1, Bp, sB);
   pack_T(w.x_tb, F, F, T * Bp, T * Bp, w.xT_p, sB);
+  mark(sB, "side:early packs done");
 
   const int ndec = d->future_decoder ? 2 : 1;
   const float* dz_dec[2] = {nullptr, nullptr};
@@ -813,6 +816,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     pack_T(D.dhid, 2 * Hd, 2 * Hd, Bp, B, D.dhidT_p, sw);
     GemmB().A(D.dhidT_p, nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB).run(2 * Hd, Z, G + L.l2h_w[i], Z, nullptr, 1, splits_for(2 * Hd, Z, nkcB), sw);
     launch_colsum(D.dhid, 2 * Hd, B, 2 * Hd, G + L.l2h_b[i], sw);
+    if (i == 0) mark(sw, "side:decoder weight grads done");
   }
 
   mark(st, "bwd:dec dz chain");
@@ -847,6 +851,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
       GemmB().A(w.dlinT_p, nkcB, nkcB).Bm(w.hidT_p[i], nkcB, nkcB)
           .run(2 * Z, H, G + L.lam_w + (long)i * H, 4 * H, nullptr, 1, splits_for(2 * Z, H, nkcB), sB);
     }
+    mark(sB, "side:lambda weight grads done");
   }
 
   mark(st, "bwd:lambda bwd + dhidden gemm");
@@ -858,20 +863,21 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   edge(st, sB);
   GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
       .run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
-  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB);
+  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB, true);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
-    pack_rows(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], sB);
+    launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sB);
     for (int e = 0; e < 2; ++e)
       GemmB().A(w.e1.dgiT_p[dd], nk, nk).Bm(w.e0.outT_p[e], nk, nk)
           .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sB);
   }
+  mark(sB, "side:L1 weight grads done");
   // ---- encoder layer 0
   mark(st, "bwd:dx1 gemm");
   gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st);
   edge(st, sB);
-  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB);
+  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
-    pack_rows(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], sB);
+    launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sB);
     GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sB);
   }
   mark(st, "bwd:L0 sweep");
@@ -922,9 +928,9 @@ int vame_debug_timeline_read(const char** names, float* ms, int max) {
   Timeline& T = timeline();
   cudaDeviceSynchronize();
   int n = 0;
-  for (int i = 1; i < T.n && n < max; ++i) {
+  for (int i = 1; i < T.n && n < max; ++i) {     // absolute time of every mark since the first one (marks may be on side streams)
     float t = 0.f;
-    cudaEventElapsedTime(&t, T.ev[i - 1], T.ev[i]);
+    cudaEventElapsedTime(&t, T.ev[0], T.ev[i]);
     names[n] = T.name[i];
     ms[n++] = t;
   }

@@ -866,10 +866,10 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
     tc_fence_after();
     float* pbase = pout + (long)c * H * bpad + b;
     for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
-      float v[UPT];
-      tmem_ldN<UPT>(taddr + c0, v);
+      float v[16];
+      tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
-      stfN<UPT>(pbase + (long)c0 * bpad, bpad, v);
+      stfN<16>(pbase + (long)c0 * bpad, bpad, v);
     }
     tc_fence_before();
     if (s + 1 < a.steps) cluster_arrive_release();   // release at cluster scope publishes the partial sums to the peers

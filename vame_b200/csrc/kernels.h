@@ -21,6 +21,9 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
 // value(r, k) = src[i * ld + j] with (i, j) = transposed ? (k, r) : (r, k); zero outside i < nrows_src, j < ncols_src
 void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
                      const int* col_map, int RB, void* out, cudaStream_t st);
+// plain pack of a row-major [R_src, K] matrix that also accumulates rowsum[r] += sum_k src[r, k]
+void launch_pack_p16_rowsum(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st);
+
 // batched pack jobs (one launch): kind 0 = generic pack_p16, 1 / 2 = W_hh forward / backward slices (R = H), 3 = fused bias (R = H)
 struct PackJob {
   const float* src; const float* src2; void* out;

@@ -7,9 +7,11 @@ namespace vb {
 // One thread produces one 16-byte atom row (8 consecutive k) of both planes.
 // value(r, k) = src[rm * ld + km]  (or src[km * ld + rm] when transposed), rm = row_map ? row_map[r] : r, idem km;
 // out-of-range / negative map entries give 0.
+// rowsum != nullptr (non-transposed sources only): additionally accumulates rowsum[r] += sum_k value(r, k) — the bias
+// gradient of a feature-major gate-gradient matrix comes for free with the pack that reads it anyway.
 __device__ __forceinline__ void pack_p16_body(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src,
                                               int K_src, const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
-                                              __nv_bfloat16* __restrict__ out, long bid, long nb) {
+                                              __nv_bfloat16* __restrict__ out, long bid, long nb, float* __restrict__ rowsum = nullptr) {
   const int nkc = (K + KCHUNK - 1) / KCHUNK;
   const int nrb = (R + RB - 1) / RB;
   const long total = (long)nrb * RB * nkc * 8;           // atom rows
@@ -42,7 +44,25 @@ __device__ __forceinline__ void pack_p16_body(const float* __restrict__ src, lon
     const int off = p16_in_tile(rr, kk);
     *reinterpret_cast<uint4*>(tile + off) = hi;
     *reinterpret_cast<uint4*>(tile + (size_t)RB * KCHUNK + off) = lo;
+    if (rowsum) {
+      // non-transposed order: the lanes of a warp hold consecutive 8-wide k groups; a row has nkc*8 groups.  Reduce over the
+      // lanes that share this thread's row, one atomic per (warp, row).
+      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      const unsigned mask = __activemask();
+      const long r0 = __shfl_sync(mask, r, 0);
+      const bool uniform = __all_sync(mask, r == r0);
+      if (uniform && mask == 0xffffffffu) {
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0 && r < R) atomicAdd(rowsum + r, s);
+      } else if (r < R) {
+        atomicAdd(rowsum + r, s);
+      }
+    }
   }
+}
+__global__ void pack_p16_rowsum_kernel(const float* __restrict__ src, long ld, int R, int K, int R_src, int RB,
+                                       __nv_bfloat16* __restrict__ out, float* __restrict__ rowsum) {
+  pack_p16_body(src, ld, 0, R, K, R_src, K, nullptr, nullptr, RB, out, blockIdx.x, gridDim.x, rowsum);
 }
 __global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int transposed, int R, int K, int R_src, int K_src,
                                 const int* __restrict__ row_map, const int* __restrict__ col_map, int RB,
@@ -61,6 +81,16 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
   count_launch();
   pack_p16_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, ld, transposed, R, K, R_src, K_src, row_map, col_map, RB,
                                                         (__nv_bfloat16*)out);
+}
+
+void launch_pack_p16_rowsum(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st) {
+  const int nkc = (K + KCHUNK - 1) / KCHUNK, nrb = (R + 127) / 128;
+  long total = (long)nrb * 128 * nkc * 8;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  count_launch();
+  pack_p16_rowsum_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld, R, K, R_src, 128, (__nv_bfloat16*)out, rowsum);
 }
 
 // ------------------------------------------------------------------------------------------------
