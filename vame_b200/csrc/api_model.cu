@@ -219,6 +219,8 @@ static inline void edge(cudaStream_t from, cudaStream_t to) {
 // ================================================================================================
 static inline GemmSeg seg(const void* p, long rb_stride, int nkc) { return GemmSeg{p, rb_stride, nkc}; }
 
+// SMs that the side-stream GEMMs can count on while a recurrent sweep runs on the main stream (set by vame_backward)
+static int g_side_sms = 148;
 struct GemmB {
   GemmArgs g{};
   int na = 0, nb = 0;
@@ -226,6 +228,7 @@ struct GemmB {
   GemmB& Bm(const void* p, long rbs, int nkc) { g.b[nb++] = seg(p, rbs, nkc); return *this; }
   void run(int M, int N, float* C, long ldc, const float* bias, int atomic, int splits, cudaStream_t st) {
     g.M = M; g.N = N; g.C = C; g.ldc = ldc; g.bias = bias; g.atomic = atomic; g.splits = splits;
+    g.max_ctas = atomic ? g_side_sms : 0;      // accumulating (weight-gradient) GEMMs run beside a sweep
     launch_gemm_p16(g, st);
   }
   // feature-major output: C[n*ldc + m]
@@ -244,7 +247,7 @@ static inline void pack_T(const float* src, long ld, int R, int K, int K_src, vo
 }
 static inline int splits_for(int M, int N, int nkc) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  int s = 148 / (tiles > 0 ? tiles : 1);
+  int s = g_side_sms / (tiles > 0 ? tiles : 1);
   if (s < 1) s = 1;
   if (s > nkc) s = nkc;
   if (s > 32) s = 32;
@@ -331,6 +334,7 @@ static void zero_p16_padding(GruBuf& L, int tiles, bool fwd, cudaStream_t st) {
   }
 }
 
+static int g_fwd_concurrent = 1;     // forward sweeps that run side by side (2 while the decoder and the future decoder overlap)
 static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b_hn1, GruBuf& L, int tiles, bool save, bool pdl,
                           cudaStream_t st) {
   const int H = L.H;
@@ -361,7 +365,10 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
     GruFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.pdl = (pdl && g_opt_pdl && s > 0) ? 1 : 0;
     a.flags = use_flags ? 1 : 0;
-    a.flag_expected = (unsigned int)(H / 32) * (g_opt_warps16 ? 16u : 8u);   // every warp of every slice CTA signals once
+    // 16-unit slices double the CTAs (shorter MMA chain and epilogue per step) as long as two concurrent sweeps
+    // (decoder + future decoder) still fit the 148 SMs in one wave
+    a.upc = (g_opt_slice16 && g_fwd_concurrent * tiles * (H / 16) * 2 <= 148) ? 16 : 32;
+    a.flag_expected = (unsigned int)(H / a.upc) * (g_opt_warps16 ? 16u : 8u);   // every warp of every slice CTA signals once
     for (int d = 0; d < 2; ++d) {
       const int t = d == 0 ? s : L.steps - 1 - s;
       const int tprev = d == 0 ? t - 1 : t + 1;
@@ -409,8 +416,10 @@ static inline const void* final_h_p(const GruBuf& L, int d, int tiles) {
 
 // dout0/1: feature-major [H][dout_ld] upstream gradients of the per-step outputs (slot t at + t*B_pad) or nullptr;
 // dhl0/1: feature-major [H][dhl_ld] gradient of the final hidden state or nullptr
-static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float* dout0, const float* dout1, long dout_ld,
-                          const float* dhl0, const float* dhl1, long dhl_ld, bool pdl, cudaStream_t st) {
+// dgi_sum / dgi_sum_p (optional, per direction): time sums of dgi written by the persistent kernel; returns true if they were produced
+static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float* dout0, const float* dout1, long dout_ld,
+                          const float* dhl0, const float* dhl1, long dhl_ld, bool pdl, cudaStream_t st,
+                          float* const* dgi_sum = nullptr, void* const* dgi_sum_p = nullptr) {
   const int H = L.H, nsl = H / 32, nkc3 = nkc_of(3 * H);
   const long Bp = (long)tiles * 128;
   const size_t slotf = (size_t)Bp * H;
@@ -432,10 +441,13 @@ static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
       D.parts = L.parts[d];
       D.dgi = L.dgi[d]; D.dgh = L.dgh[d]; D.dg_ld = seq_ld;
       D.dgi_p = L.dgi_p[d]; D.dgi_p_slot_elems = (long)tiles * nkc3 * (long)p16_tile_elems(128);
+      D.dgi_sum = dgi_sum ? dgi_sum[d] : nullptr;
+      D.dgi_sum_p = dgi_sum ? dgi_sum_p[d] : nullptr;
+      if (dgi_sum && ((3 * H) % KCHUNK) != 0) cudaMemsetAsync(dgi_sum_p[d], 0, (size_t)tiles * nkc3 * p16_tile_bytes(128), st);
       D.reverse = d;
     }
     launch_gru_seq_bwd(a, st);
-    return;
+    return dgi_sum != nullptr;
   }
   const bool use_flags = pdl && g_opt_pdl && g_opt_flags;
   if (use_flags) cudaMemsetAsync(L.flags, 0, (size_t)2 * L.steps * tiles * sizeof(unsigned int), st);
@@ -478,6 +490,7 @@ static void gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
     }
     launch_gru_step_bwd(a, st);
   }
+  return false;
 }
 static inline const float* final_parts(const GruBuf& L, int d, int tiles) {
   const size_t pslot = (size_t)(L.H / 32 + 1) * tiles * 128 * L.H;
@@ -568,7 +581,9 @@ static void decoder_forward(const vame_dims& d, int which, const float* P, const
     launch_h0_prepare(D.hid + (size_t)dd * w.B * Hd, 1, w.B, Bp, Hd, D.g.h0[dd], D.g.h0_p[dd], st);
   // the decoder input is z at every time step (rnn_model.py:169-170): one projection per sample
   GemmB().A(w.z_p, nkcZ, nkcZ).Bm(Wg.wih_p[0], nkcZ, nkcZ).run_fm(Bp, 6 * Hd, D.g.gi, Bp, Wg.bias_gi, st);
+  g_fwd_concurrent = (d.future_decoder && g_opt_streams) ? 2 : 1;
   gru_sweep_fwd(Wg, P + o.bhh[0] + 2 * Hd, P + o.bhh[1] + 2 * Hd, D.g, w.tiles, save, true, st);
+  g_fwd_concurrent = 1;
   // prediction = hidden_to_output([out_f, out_b])
   GemmB().A(D.g.out_p[0], nkcH, nkcH).A(D.g.out_p[1], nkcH, nkcH).Bm(W.h2o_p[which][0], nkcH, nkcH).Bm(W.h2o_p[which][1], nkcH, nkcH)
       .run(steps * Bp, F, D.pred_tb, F, P + L.h2o_b[which], 0, 1, st);
@@ -744,6 +759,10 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc, Bp = w.B_pad, B = batch;
+  {   // SMs left for the weight-gradient GEMMs while a sweep (tiles x H/32 slices x 2 directions CTAs, 1 per SM) is running
+    const int sweep = w.tiles * (H / 32) * 2 * (d->future_decoder ? 2 : 1);
+    g_side_sms = g_opt_streams ? (sweep < 100 ? 148 - sweep : 48) : 148;
+  }
   const int nkcB = Bp / KCHUNK;
   float* G = grads;
   cudaMemsetAsync(G, 0, (size_t)L.total * 4, st);
@@ -781,34 +800,43 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     const GruPacked& Wg = i == 0 ? W.dec : W.fut;
     if (!use_loss_grads) launch_bt_to_tb(ext, B, steps, F, (long)steps * F, F, Bp, D.dpred_tb, sd);
     // ---- data-gradient chain: hidden_to_output backward, BPTT, dz
+    cudaMemsetAsync(D.dz, 0, (size_t)B * Z * 4, sd);                      // accumulated by the split-K dz GEMM after the sweep
     pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);
     GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_fm((int)rows, 2 * Hd, D.ddec, rows, nullptr, sd);
     if (i == 0) mark(st, "bwd:dec dpred pack + ddec gemm");
-    gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + (size_t)Hd * rows, rows, nullptr, nullptr, 0, true, sd);
-    if (i == 0) mark(st, "bwd:dec sweep");
-    for (int dd = 0; dd < 2; ++dd) {         // the input is z at every step -> reduce dgi over time first
-      launch_timesum_fm(D.g.dgi[dd], rows, steps, Bp, 3 * Hd, D.dgi_sum[dd], sd);                // [3H][B_pad]
-      pack_T(D.dgi_sum[dd], Bp, Bp, 3 * Hd, 3 * Hd, D.dgi_sum_p[dd], sd);                        // -> [B_pad rows, K = 3H]
+    {   // weight-gradient operands that only need the forward pass and dpred: packed on sw while the sweep runs
+      edge(sd, sw);
+      pack_T(D.dpred_tb, F, F, (int)rows, (int)rows, D.dpredT_p, sw);
+      launch_colsum(D.dpred_tb, F, rows, F, G + L.h2o_b[i], sw);
+      for (int dd = 0; dd < 2; ++dd) pack_rows(D.g.h0[dd], Bp, Hd, Bp, Hd, D.g.h0T_p[dd], sw);       // h0 is [H][B_pad]
+      pack_outT(D.g, Bp, sw);
+      for (int dd = 0; dd < 2; ++dd)                                        // dW_out[:, dd*H:(dd+1)*H] = dpred^T out_dd
+        GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
+            .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), sw);
     }
-    GemmB().A(D.dgi_sum_p[0], nkc3, nkc3).A(D.dgi_sum_p[1], nkc3, nkc3).Bm(Wg.wihT_p[0], nkc3, nkc3).Bm(Wg.wihT_p[1], nkc3, nkc3)
-        .run(B, Z, D.dz, Z, nullptr, 0, 1, sd);
+    const bool have_sums = gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + (size_t)Hd * rows, rows, nullptr, nullptr, 0, true, sd,
+                                         D.dgi_sum, D.dgi_sum_p);
+    if (i == 0) mark(st, "bwd:dec sweep");
+    edge(sd, sw);                            // recurrent weight gradients start as soon as the sweep is done (beside the dz chain)
+    gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, sw);
+    if (!have_sums) {
+      for (int dd = 0; dd < 2; ++dd) {       // the input is z at every step -> reduce dgi over time first
+        launch_timesum_fm(D.g.dgi[dd], rows, steps, Bp, 3 * Hd, D.dgi_sum[dd], sd);              // [3H][B_pad]
+        pack_T(D.dgi_sum[dd], Bp, Bp, 3 * Hd, 3 * Hd, D.dgi_sum_p[dd], sd);                      // -> [B_pad rows, K = 3H]
+      }
+    }
     // latent_to_hidden backward through the inverse of the .view(2,B,H) quirk
-    launch_parts_reduce(final_parts(D.g, 0, w.tiles), Hd / 32 + 1, (long)(final_parts(D.g, 1, w.tiles) - final_parts(D.g, 0, w.tiles)), 2, B,
-                        Bp, Hd, D.dhid, sd);
-    pack_rows(D.dhid, 2 * Hd, Bp, 2 * Hd, B, D.dhid_p, sd);
-    GemmB().A(D.dhid_p, nkc2H, nkc2H).Bm(W.l2hT_p[i], nkc2H, nkc2H).run(B, Z, D.dz, Z, nullptr, 1, 1, sd);
+    launch_parts_reduce_pack(final_parts(D.g, 0, w.tiles), Hd / 32 + 1,
+                             (long)(final_parts(D.g, 1, w.tiles) - final_parts(D.g, 0, w.tiles)), 2, B, Bp, Hd, D.dhid, D.dhid_p, sd);
+    // dz = [dgi_sum_f, dgi_sum_b, dhid] [W_ih_f ; W_ih_b ; W_l2h]: one split-K GEMM over the concatenated K
+    GemmB().A(D.dgi_sum_p[0], nkc3, nkc3).A(D.dgi_sum_p[1], nkc3, nkc3).A(D.dhid_p, nkc2H, nkc2H)
+        .Bm(Wg.wihT_p[0], nkc3, nkc3).Bm(Wg.wihT_p[1], nkc3, nkc3).Bm(W.l2hT_p[i], nkc2H, nkc2H)
+        .run(B, Z, D.dz, Z, nullptr, 1, 8, sd);
     dz_dec[i] = D.dz;
-    // ---- weight gradients of this decoder (off the critical path)
+    // ---- remaining weight gradients of this decoder (they need dgi_sum / dhid of the dz chain)
     edge(sd, sw);
     if (i == 1) edge(sA, st);                // main needs dz of the future decoder, not its weight gradients
-    pack_T(D.dpred_tb, F, F, (int)rows, (int)rows, D.dpredT_p, sw);
-    launch_colsum(D.dpred_tb, F, rows, F, G + L.h2o_b[i], sw);
-    for (int dd = 0; dd < 2; ++dd) pack_rows(D.g.h0[dd], Bp, Hd, Bp, Hd, D.g.h0T_p[dd], sw);       // h0 is [H][B_pad]
-    pack_outT(D.g, Bp, sw);
-    gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, sw);
-    for (int dd = 0; dd < 2; ++dd) {                                      // dW_out[:, dd*H:(dd+1)*H] = dpred^T out_dd
-      GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
-          .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), sw);
+    for (int dd = 0; dd < 2; ++dd) {
       pack_rows(D.dgi_sum[dd], Bp, 3 * Hd, Bp, 3 * Hd, D.dgi_sumT_p[dd], sw);
       GemmB().A(D.dgi_sumT_p[dd], nkcB, nkcB).Bm(w.zT_p, nkcB, nkcB)
           .run(3 * Hd, Z, G + o.wih[dd], Z, nullptr, 1, splits_for(3 * Hd, Z, nkcB), sw);
@@ -875,6 +903,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   mark(st, "bwd:dx1 gemm");
   gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st);
   edge(st, sB);
+  g_side_sms = 148;                          // nothing else runs beside the last block
   gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
     launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sB);

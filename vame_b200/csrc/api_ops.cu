@@ -10,6 +10,7 @@ long g_launch_count = 0;
 int g_opt_pdl = 1;
 int g_opt_streams = 1;
 int g_opt_warps16 = 1;
+int g_opt_slice16 = 1;
 int g_opt_flags = 0;           // measured: no gain (the gpu-scope publish costs what the kernel-completion flush costs)
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
 unsigned long long* g_dbg_buffer = nullptr;
@@ -35,6 +36,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "flags") == 0) return vb::g_opt_flags;
   if (strcmp(name, "streams") == 0) return vb::g_opt_streams;
   if (strcmp(name, "warps16") == 0) return vb::g_opt_warps16;
+  if (strcmp(name, "slice16") == 0) return vb::g_opt_slice16;
   return -1;
 }
 
@@ -58,6 +60,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "streams") == 0) {
     vb::g_opt_streams = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "slice16") == 0) {
+    vb::g_opt_slice16 = value ? 1 : 0;
     return 0;
   }
   return vb::fail("vame_set_option: unknown option");

@@ -95,6 +95,10 @@ __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // orders this thread's generic-proxy accesses (st.global / ld.global) against async-proxy accesses (TMA bulk copies)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// vectorised split-K accumulation: one 16-byte reduction per lane (PTX ISA 8.1, sm_90+); p must be 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }   // L2-coherent load (bypasses the non-coherent L1)
 // inter-kernel hand-over flags (PDL chains without griddepcontrol.wait): release-increment / acquire-poll at gpu scope
 __device__ __forceinline__ void flag_release_add(unsigned int* p, unsigned int v) {

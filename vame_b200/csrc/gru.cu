@@ -87,12 +87,20 @@ template <int N>
 __device__ __forceinline__ void stN_p16(__nv_bfloat16* tile, int rows_in_tile, int r, int k, const float* v) {
   __nv_bfloat16* lo = tile + (size_t)rows_in_tile * KCHUNK;
   const int off = p16_in_tile(r, k);
+  if constexpr (N == 4) {                 // half an atom: k % 4 == 0
+    __nv_bfloat16 h[4], l[4];
 #pragma unroll
-  for (int a = 0; a < N / 8; ++a) {
-    uint4 h, l;
-    split8(v + 8 * a, h, l);
-    *reinterpret_cast<uint4*>(tile + off + 64 * a) = h;
-    *reinterpret_cast<uint4*>(lo + off + 64 * a) = l;
+    for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
+    *reinterpret_cast<uint2*>(tile + off) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+  } else {
+#pragma unroll
+    for (int a = 0; a < N / 8; ++a) {
+      uint4 h, l;
+      split8(v + 8 * a, h, l);
+      *reinterpret_cast<uint4*>(tile + off + 64 * a) = h;
+      *reinterpret_cast<uint4*>(lo + off + 64 * a) = l;
+    }
   }
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -104,10 +112,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 template <int N>
 __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float* v) {
   if constexpr (N == 16) tmem_ld16(taddr, v);
-  else tmem_ld8(taddr, v);
+  else if constexpr (N == 8) tmem_ld8(taddr, v);
+  else tmem_ld4(taddr, v);
 }
 
 // optional in-kernel timeline (vame_set_debug_buffer): CTA (0,0,0) thread 0 records %globaltimer at fixed points
@@ -128,15 +146,19 @@ __device__ __forceinline__ unsigned long long gtime() {
 // =================================================================================================
 // forward step
 // =================================================================================================
-constexpr int F_WTILE = 96 * KCHUNK * 2 * 2;     // 24576 B : one K chunk of the W slice (hi + lo)
+constexpr int F_WSUB = 48 * KCHUNK * 2 * 2;      // 12288 B : one K chunk of a 16-unit W slice (hi + lo planes of 48 rows)
+constexpr int F_WTILE = 2 * F_WSUB;              // 24576 B : one K chunk of a 32-unit W slice
 constexpr int F_ATILE = 128 * KCHUNK * 2 * 2;    // 32768 B : one K chunk of the h tile (hi + lo)
 
-template <int UPT>
-__global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(const GruFwdArgs a) {
+// UPC = hidden units per CTA (16 or 32), UPT = units per thread; 128 * UPC / UPT threads.
+// TMEM columns of sub-slice s (16 units): [96 s, 96 s + 48) = a * w_hi for (r, z, n) x 16, [96 s + 48, 96 s + 96) = a * w_lo.
+template <int UPC, int UPT>
+__global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(const GruFwdArgs a) {
+  constexpr int WT = (UPC / 16) * F_WSUB;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nkc = (H + KCHUNK - 1) / KCHUNK;
   uint8_t* sW = smem;
-  uint8_t* sA = smem + (size_t)nkc * F_WTILE;
+  uint8_t* sA = smem + (size_t)nkc * WT;
   uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + (size_t)nkc * F_ATILE);
   uint64_t* abar = wbar + 4;
   uint64_t* done = abar + 4;
@@ -168,10 +190,13 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(co
   DBG_STAMP(0);
   if (warp == 0) {
     if (lane == 0) {
-      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p);
       for (int kc = 0; kc < nkc; ++kc) {
-        mbar_expect_tx(&wbar[kc], F_WTILE);
-        bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+        mbar_expect_tx(&wbar[kc], WT);
+#pragma unroll
+        for (int sub = 0; sub < UPC / 16; ++sub)
+          bulk_g2s(sW + (size_t)kc * WT + sub * F_WSUB, wp + ((size_t)(c * (UPC / 16) + sub) * nkc + kc) * p16_tile_elems(48), F_WSUB,
+                   &wbar[kc]);
       }
     }
     __syncwarp();
@@ -179,7 +204,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(co
   const int r_in = q * 32 + lane;
   const long b = (long)tile * 128 + r_in;
   const int j0 = half * UPT;           // first unit inside the slice
-  const int u0 = c * 32 + j0;          // first hidden unit handled by this thread
+  const int u0 = c * UPC + j0;         // first hidden unit handled by this thread
   float gir[UPT], giz[UPT], gin[UPT], bhn[UPT];
   {
     const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts);
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(co
         mbar_expect_tx(&abar[kc], F_ATILE);
         bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
       }
-      const uint32_t idesc = make_idesc_bf16(128, 192);
+      const uint32_t idesc = make_idesc_bf16(128, 6 * UPC);
       // the issue loop is the critical resource (one thread): descriptors are precomputed, the k-steps fully unrolled
       const uint64_t dA = make_desc(smem_u32(sA)), dAl = make_desc(smem_u32(sA) + 128 * KCHUNK * 2), dW = make_desc(smem_u32(sW));
 #pragma unroll
@@ -224,8 +249,8 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(co
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < ksteps) {
-              // one descriptor covers [W_hi ; W_lo] (192 rows): D[:, 0:96] += a*w_hi, D[:, 96:192] += a*w_lo
-              const uint32_t ao = kc * F_ATILE + ks * 2 * ATOM_BYTES, wo = kc * F_WTILE + ks * 2 * ATOM_BYTES;
+              // one descriptor covers the [W_hi ; W_lo] planes of all sub-slices (6 UPC rows)
+              const uint32_t ao = kc * F_ATILE + ks * 2 * ATOM_BYTES, wo = kc * WT + ks * 2 * ATOM_BYTES;
               if (kc == 0 && ks == 0) umma_bf16_c<0>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
               else umma_bf16_c<1>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
               umma_bf16_c<1>(tmem, desc_advance(dA, ao), desc_advance(dW, wo), idesc);
@@ -253,12 +278,13 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_step_fwd_kernel(co
   float ar[UPT], az[UPT], an[UPT];
   {
     float br[UPT], bz[UPT], bn[UPT];                 // columns 96.. hold the (* w_lo) products
-    tmem_ldN<UPT>(taddr + j0, ar);
-    tmem_ldN<UPT>(taddr + 32 + j0, az);
-    tmem_ldN<UPT>(taddr + 64 + j0, an);
-    tmem_ldN<UPT>(taddr + 96 + j0, br);
-    tmem_ldN<UPT>(taddr + 128 + j0, bz);
-    tmem_ldN<UPT>(taddr + 160 + j0, bn);
+    const uint32_t cb = taddr + (j0 / 16) * 96 + (j0 % 16);
+    tmem_ldN<UPT>(cb, ar);
+    tmem_ldN<UPT>(cb + 16, az);
+    tmem_ldN<UPT>(cb + 32, an);
+    tmem_ldN<UPT>(cb + 48, br);
+    tmem_ldN<UPT>(cb + 64, bz);
+    tmem_ldN<UPT>(cb + 80, bn);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < UPT; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
@@ -326,22 +352,28 @@ void launch_gru_step_fwd(const GruFwdArgs& a_in, cudaStream_t st) {
   GruFwdArgs a = a_in;
   a.dbg = g_dbg_buffer;
   const int nkc = (a.H + KCHUNK - 1) / KCHUNK;
-  const size_t smem = (size_t)nkc * (F_WTILE + F_ATILE) + 256;
+  const int upc = a.upc == 16 ? 16 : 32;
+  const size_t smem = (size_t)nkc * ((upc / 16) * F_WSUB + F_ATILE) + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_step_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_step_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_step_fwd_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   count_launch();
-  if (g_opt_warps16) {                     // 16 warps, 8 units per thread: the serial gate epilogue is twice as parallel
-    launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 512, smem, st, a.pdl);
-    cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<8>, a);
+  const dim3 grid(a.H / upc, a.tiles, a.ndir);
+  // 16 warps: the serial gate epilogue is twice as parallel (8 or 4 units per thread instead of 16 or 8)
+  launch_cfg(cfg, attr, grid, g_opt_warps16 ? 512 : 256, smem, st, a.pdl);
+  if (upc == 32) {
+    if (g_opt_warps16) cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<32, 8>, a);
+    else cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<32, 16>, a);
   } else {
-    launch_cfg(cfg, attr, dim3(a.H / 32, a.tiles, a.ndir), 256, smem, st, a.pdl);
-    cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16>, a);
+    if (g_opt_warps16) cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16, 4>, a);
+    else cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16, 8>, a);
   }
 }
 
@@ -385,10 +417,11 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
 
   if (warp == 0) {
     if (lane == 0) {
-      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p) + (size_t)c * nkc * p16_tile_elems(96);
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p);
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_expect_tx(&wbar[kc], F_WTILE);
-        bulk_g2s(sW + (size_t)kc * F_WTILE, wp + (size_t)kc * p16_tile_elems(96), F_WTILE, &wbar[kc]);
+        for (int sub = 0; sub < 2; ++sub)
+          bulk_g2s(sW + (size_t)kc * F_WTILE + sub * F_WSUB, wp + ((size_t)(2 * c + sub) * nkc + kc) * p16_tile_elems(48), F_WSUB, &wbar[kc]);
       }
     }
     __syncwarp();
@@ -457,12 +490,13 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
     float ar[16], az[16], an[16];
     {
       float br[16], bz[16], bn[16];
-      tmem_ld16(taddr + j0, ar);
-      tmem_ld16(taddr + 32 + j0, az);
-      tmem_ld16(taddr + 64 + j0, an);
-      tmem_ld16(taddr + 96 + j0, br);
-      tmem_ld16(taddr + 128 + j0, bz);
-      tmem_ld16(taddr + 160 + j0, bn);
+      const uint32_t cb = taddr + half * 96;       // sub-slice `half`: (r, z, n) x 16 hi-products, then the lo-products
+      tmem_ld16(cb, ar);
+      tmem_ld16(cb + 16, az);
+      tmem_ld16(cb + 32, an);
+      tmem_ld16(cb + 48, br);
+      tmem_ld16(cb + 64, bz);
+      tmem_ld16(cb + 80, bn);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) { ar[i] += br[i]; az[i] += bz[i]; an[i] += bn[i]; }
@@ -713,7 +747,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
 // exchanges the H/32 partial products dgh_c W_hh[c-rows, :] with the other CTAs of the cluster through global memory
 // (L2-coherent loads) between steps.
 // =================================================================================================
-template <int UPT>
+template <int UPT, bool SUM>
 __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(const GruSeqBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nrb = (H + 127) / 128, nsl = H / 32;
@@ -763,8 +797,13 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
   const int hh = H / (32 / UPT);            // TMEM columns drained by each warp group
   float carry[UPT];
+  float sum_r[SUM ? UPT : 1], sum_z[SUM ? UPT : 1], sum_n[SUM ? UPT : 1];   // time sums of the input-gate gradients (decoders)
 #pragma unroll
   for (int i = 0; i < UPT; ++i) carry[i] = 0.f;
+  if constexpr (SUM) {
+#pragma unroll
+    for (int i = 0; i < UPT; ++i) sum_r[i] = sum_z[i] = sum_n[i] = 0.f;
+  }
   if (d.dh_last) ldfN<UPT>(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
 
   for (int s = 0; s < a.steps; ++s) {
@@ -806,6 +845,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
       dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
       dgn[i] = dan[i] * r[i];
       carry[i] = dh[i] * z[i];
+      if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
     }
     {
       __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(sA);
@@ -874,6 +914,18 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
     tc_fence_before();
     if (s + 1 < a.steps) cluster_arrive_release();   // release at cluster scope publishes the partial sums to the peers
   }
+  if constexpr (SUM) {
+    stfN<UPT>(d.dgi_sum + (long)u0 * bpad + b, bpad, sum_r);
+    stfN<UPT>(d.dgi_sum + (long)(H + u0) * bpad + b, bpad, sum_z);
+    stfN<UPT>(d.dgi_sum + (long)(2 * H + u0) * bpad + b, bpad, sum_n);
+    const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int k = g * H + u0;
+      stN_p16<UPT>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? sum_r : (g == 1 ? sum_z : sum_n));
+    }
+  }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);
 }
@@ -883,8 +935,10 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * B_APLANE + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
   const bool w16 = g_opt_warps16 && (a.H % 64 == 0);       // each of the 4 warp groups drains H/4 (multiple of 16) columns
@@ -901,8 +955,14 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   count_launch();
-  if (w16) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8>, a);
-  else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16>, a);
+  const bool sum = a.d[0].dgi_sum != nullptr;          // (set for both directions or for none)
+  if (w16) {
+    if (sum) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8, true>, a);
+    else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8, false>, a);
+  } else {
+    if (sum) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16, true>, a);
+    else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16, false>, a);
+  }
 }
 
 void launch_gru_step_bwd(const GruBwdArgs& a, cudaStream_t st) {

@@ -12,7 +12,8 @@ extern unsigned long long* g_dbg_buffer;   // device buffer for kernel timeline 
 extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through release/acquire flags (tail of step t overlaps t+1);
                             //    default 0: measured equal to griddepcontrol.wait (tools/gpu_probe_graph.py, profiles/)
 extern int g_opt_warps16;   // 1: 16 warps per CTA (8 hidden units per thread) in the default recurrent kernels
-extern int g_opt_streams;
+extern int g_opt_streams;   // 1: run independent branches of a step on internal side streams
+extern int g_opt_slice16;   // 1: forward step kernels own 16 hidden units per CTA (twice the CTAs, N = 96 MMAs) when the sweep fits the GPU
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 inline void count_launch(int n = 1) { g_launch_count += n; }
@@ -60,7 +61,9 @@ struct GemmArgs {
   int c_fm;
   const float* bias;    // [N] or nullptr (added only by split 0)
   int atomic;           // 1: red.add into C (split-K / accumulation), 0: plain store
-  int splits;           // gridDim.z
+  int splits;           // k splits (work items = tiles x splits)
+  int max_ctas;         // upper bound of the persistent grid (0 = all SMs): SMs held by a concurrently running sweep are not
+                        // available, and a persistent grid larger than the free SMs would serialise into a second wave
 };
 void launch_gemm_p16(const GemmArgs& g, cudaStream_t st);
 
@@ -88,6 +91,7 @@ struct GruDirFwd {
 struct GruFwdArgs {
   GruDirFwd d[2];
   int ndir, H, tiles;
+  int upc;                // hidden units per CTA: 16 or 32 (0 = 32)
   int pdl;                // launch with programmatic stream serialization
   int flags;              // 1: the recurrence dependency is carried by flag_in/flag_out instead of griddepcontrol.wait, so the
                           //    tail of step t (saved-gate stores, teardown) overlaps step t+1
@@ -123,6 +127,8 @@ struct GruSeqDirBwd {
   float* parts;                                // [2 slots][H/32 + 1][H][B_pad] partial sums exchanged between the CTAs
   float* dgi; float* dgh; long dg_ld;          // outputs, feature-major [3H][dg_ld] (slot t at + t*B_pad)
   void* dgi_p; long dgi_p_slot_elems;          // optional P16 copy of dgi per t
+  float* dgi_sum; void* dgi_sum_p;             // optional: sum over t of dgi, feature-major [3H][B_pad] and P16 [B_pad rows, K = 3H]
+                                               // (decoders: the GRU input is z at every step, so dz needs only the time sum)
   int reverse;                                 // direction of the FORWARD recurrence (0: t ascending) -> BPTT runs the other way
 };
 struct GruSeqBwdArgs {

@@ -100,22 +100,25 @@ __device__ __forceinline__ void pack_whh_body(const float* __restrict__ w, int H
                                               long nb) {
   const int nsl = H / 32;
   if (mode == 0) {
+    // forward operand: slices of 16 hidden units = 48 rows [r(16) z(16) n(16)], one P16 tile (hi plane, lo plane) per
+    // (slice, K chunk).  A step CTA that owns 16 (32) units loads 1 (2) consecutive slices per chunk; one UMMA descriptor
+    // then spans [hi48 ; lo48] (N = 96) or [hi48 ; lo48 ; hi48 ; lo48] (N = 192).
     const int nkc = (H + KCHUNK - 1) / KCHUNK;
-    const long total = (long)nsl * 96 * nkc * 8;
+    const long total = (long)(H / 16) * 48 * nkc * 8;
     for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
       const int k8g = (int)(idx % (nkc * 8));
       const int p = (int)(idx / (nkc * 8));            // packed row
-      const int c = p / 96, g = (p % 96) / 32, j = p % 32;
-      const int srow = g * H + 32 * c + j, kbase = k8g * 8;
+      const int c = p / 48, g = (p % 48) / 16, j = p % 16;
+      const int srow = g * H + 16 * c + j, kbase = k8g * 8;
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (kbase + i < H) ? w[(long)srow * H + kbase + i] : 0.f;
       uint4 hi, lo;
       split8(v, hi, lo);
-      __nv_bfloat16* tile = out + ((size_t)c * nkc + kbase / KCHUNK) * p16_tile_elems(96);
-      const int off = p16_in_tile(p % 96, kbase % KCHUNK);
+      __nv_bfloat16* tile = out + ((size_t)c * nkc + kbase / KCHUNK) * p16_tile_elems(48);
+      const int off = p16_in_tile(p % 48, kbase % KCHUNK);
       *reinterpret_cast<uint4*>(tile + off) = hi;
-      *reinterpret_cast<uint4*>(tile + 96 * KCHUNK + off) = lo;
+      *reinterpret_cast<uint4*>(tile + 48 * KCHUNK + off) = lo;
     }
   } else {
     const int nrb = (H + 127) / 128;

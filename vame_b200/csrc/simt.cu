@@ -266,9 +266,16 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, long rows, i
   if (n >= N) return;
   const long per = (rows + gridDim.y - 1) / gridDim.y;
   const long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  float s = 0.f;
-  for (long r = r0; r < r1; ++r) s += X[r * ld + n];
-  atomicAdd(out + n, s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long r = r0;
+  for (; r + 3 < r1; r += 4) {                      // four independent loads in flight per thread
+    s0 += X[r * ld + n];
+    s1 += X[(r + 1) * ld + n];
+    s2 += X[(r + 2) * ld + n];
+    s3 += X[(r + 3) * ld + n];
+  }
+  for (; r < r1; ++r) s0 += X[r * ld + n];
+  atomicAdd(out + n, (s0 + s1) + (s2 + s3));
 }
 
 // feature-major time reduction: out[c*Bp + b] = sum_t X[c*ld + t*Bp + b]
@@ -334,6 +341,39 @@ __global__ void parts_reduce_kernel(const float* __restrict__ parts, int n_parts
     float s = 0.f;
     for (int p = 0; p < n_parts; ++p) s += parts[d * dir_stride + ((long)p * H + u) * B_pad + b];
     out[((long)d * B + b) * H + u] = s;
+  }
+}
+
+// same reduction, 8 consecutive units per thread, that also emits the P16 operand of the latent_to_hidden backward GEMM: the
+// flat [D][B][H] result viewed as [B rows][D*H] (the inverse of the reference's view quirk), rows >= B zero
+__global__ void parts_reduce_pack_kernel(const float* __restrict__ parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H,
+                                         float* __restrict__ out, __nv_bfloat16* __restrict__ out_p) {
+  const int K = D * H, k8n = K / 8, nkc = (K + KCHUNK - 1) / KCHUNK;
+  const long total = (long)B_pad * k8n;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % B_pad), col = (int)(idx / B_pad) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (r < B) {
+      const long f = (long)r * K + col;
+      const int d = (int)(f / ((long)B * H));
+      const long rem = f % ((long)B * H);
+      const int b = (int)(rem / H), u = (int)(rem % H);
+      const float* p0 = parts + d * dir_stride + (long)u * B_pad + b;
+      for (int p = 0; p < n_parts; ++p) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += p0[((long)p * H + i) * B_pad];
+      }
+      *reinterpret_cast<float4*>(out + f) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out + f + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    __nv_bfloat16* tile = out_p + ((size_t)(r / 128) * nkc + col / KCHUNK) * p16_tile_elems(128);
+    const int off = p16_in_tile(r % 128, col % KCHUNK);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
   }
 }
 
@@ -435,7 +475,7 @@ void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda,
   cluster_prior_kernel<<<1, 1024, CP_SMEM, st>>>(z, B, Z, kloss, lmbda, bsize, gcoef, hyper, dz, acc);
 }
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st) {
-  int ysplit = (int)min((long)64, (rows + 127) / 128);
+  int ysplit = (int)min((long)256, (rows + 31) / 32);
   if (ysplit < 1) ysplit = 1;
   count_launch();
   colsum_kernel<<<dim3((N + 127) / 128, ysplit), 128, 0, st>>>(X, ld, rows, N, out);
@@ -458,6 +498,12 @@ void launch_fm_to_rows(const float* src, long ld, int H, int B, float* dst, long
 void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, cudaStream_t st) {
   count_launch();
   parts_reduce_kernel<<<grid_for((long)D * B_pad * H, 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out);
+}
+void launch_parts_reduce_pack(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, void* out_p,
+                              cudaStream_t st) {
+  count_launch();
+  parts_reduce_pack_kernel<<<grid_for((long)B_pad * (D * H / 8), 256), 256, 0, st>>>(parts, n_parts, dir_stride, D, B, B_pad, H, out,
+                                                                                  (__nv_bfloat16*)out_p);
 }
 void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
                  float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st) {

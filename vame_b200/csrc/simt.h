@@ -35,6 +35,9 @@ void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out
 void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st);
 void launch_fm_to_rows(const float* src, long ld, int H, int B, float* dst, long dst_ld, cudaStream_t st);
 void launch_parts_reduce(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, cudaStream_t st);
+// + P16 [B_pad rows, K = D*H] of the result viewed as [B][D*H]
+void launch_parts_reduce_pack(const float* parts, int n_parts, long dir_stride, int D, int B, int B_pad, int H, float* out, void* out_p,
+                              cudaStream_t st);
 // step_dev: device int32 step counter (incremented by the kernel chain); lr from hyper[HY_LR] when hyper != nullptr
 void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long n, float lr, const float* hyper, int* step_dev,
                  float* scratch2, float b1, float b2, float eps, float grad_scale, cudaStream_t st);
