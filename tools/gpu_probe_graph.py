@@ -97,6 +97,16 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
                  "tmem loaded", "math done", "h stores issued"]
         print("[%s pdl=%d] fwd step kernel timeline (ns since start of last launch): " % (mode, pdl) +
               ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
+        dbg.zero_()
+        lib.vame_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+        lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 1, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
+        torch.cuda.synchronize()
+        lib.vame_set_debug_buffer(None)
+        st = dbg.cpu().tolist()
+        names = ["loop top", "after cluster wait", "parts summed + math + smem A written", "after syncthreads", "mma issued",
+                 "before mma wait", "mma done", "parts stored", "after cluster arrive", "gate-grad stores issued"]
+        print("[%s pdl=%d] bwd persistent kernel, step 10 timeline (ns): " % (mode, pdl) +
+              ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
         e0.record()
         for _ in range(20):
             lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 0, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())

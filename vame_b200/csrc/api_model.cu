@@ -367,7 +367,12 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
     a.flags = use_flags ? 1 : 0;
     // 16-unit slices double the CTAs (shorter MMA chain and epilogue per step) as long as two concurrent sweeps
     // (decoder + future decoder) still fit the 148 SMs in one wave
-    a.upc = (g_opt_slice16 && g_fwd_concurrent * tiles * (H / 16) * 2 <= 148) ? 16 : 32;
+    // CTA shape: use as many SMs as one wave allows: first halve the rows per CTA (M = 64), then the units per CTA (16) -
+    // as long as the concurrent sweeps still fit the 148 SMs
+    int ctas = g_fwd_concurrent * tiles * (H / 32) * 2;
+    a.mt = 128; a.upc = 32;
+    if (g_opt_m64 && g_opt_warps16 && 2 * ctas <= 148) { a.mt = 64; ctas *= 2; }
+    if (g_opt_slice16 && 2 * ctas <= 148) { a.upc = 16; ctas *= 2; }
     a.flag_expected = (unsigned int)(H / a.upc) * (g_opt_warps16 ? 16u : 8u);   // every warp of every slice CTA signals once
     for (int d = 0; d < 2; ++d) {
       const int t = d == 0 ? s : L.steps - 1 - s;
@@ -416,6 +421,7 @@ static inline const void* final_h_p(const GruBuf& L, int d, int tiles) {
 
 // dout0/1: feature-major [H][dout_ld] upstream gradients of the per-step outputs (slot t at + t*B_pad) or nullptr;
 // dhl0/1: feature-major [H][dhl_ld] gradient of the final hidden state or nullptr
+static int g_bwd_concurrent = 1;     // backward sweeps that run side by side (2 with a future decoder)
 // dgi_sum / dgi_sum_p (optional, per direction): time sums of dgi written by the persistent kernel; returns true if they were produced
 static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float* dout0, const float* dout1, long dout_ld,
                           const float* dhl0, const float* dhl1, long dhl_ld, bool pdl, cudaStream_t st,
@@ -428,6 +434,7 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
   if (g_opt_persistent & 2) {                   // one cluster kernel for the whole BPTT sweep
     GruSeqBwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
+    a.mt = (g_opt_m64 && g_bwd_concurrent * tiles * (H / 32) * 2 * 2 <= 148) ? 64 : 128;
     const long seq_ld = (long)L.steps * Bp;
     for (int d = 0; d < 2; ++d) {
       GruSeqDirBwd& D = a.d[d];
@@ -814,8 +821,10 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
         GemmB().A(D.dpredT_p, nk, nk).Bm(D.g.outT_p[dd], nk, nk)
             .run(F, Hd, G + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, nullptr, 1, splits_for(F, Hd, nk), sw);
     }
+    g_bwd_concurrent = (ndec == 2 && g_opt_streams) ? 2 : 1;
     const bool have_sums = gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + (size_t)Hd * rows, rows, nullptr, nullptr, 0, true, sd,
                                          D.dgi_sum, D.dgi_sum_p);
+    g_bwd_concurrent = 1;
     if (i == 0) mark(st, "bwd:dec sweep");
     edge(sd, sw);                            // recurrent weight gradients start as soon as the sweep is done (beside the dz chain)
     gru_recurrent_grads(o, D.g, Bp, D.g.h0T_p[0], D.g.h0T_p[1], G, sw);

@@ -11,6 +11,7 @@ int g_opt_pdl = 1;
 int g_opt_streams = 1;
 int g_opt_warps16 = 1;
 int g_opt_slice16 = 1;
+int g_opt_m64 = 1;
 int g_opt_flags = 0;           // measured: no gain (the gpu-scope publish costs what the kernel-completion flush costs)
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
 unsigned long long* g_dbg_buffer = nullptr;
@@ -37,6 +38,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "streams") == 0) return vb::g_opt_streams;
   if (strcmp(name, "warps16") == 0) return vb::g_opt_warps16;
   if (strcmp(name, "slice16") == 0) return vb::g_opt_slice16;
+  if (strcmp(name, "m64") == 0) return vb::g_opt_m64;
   return -1;
 }
 
@@ -64,6 +66,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "slice16") == 0) {
     vb::g_opt_slice16 = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "m64") == 0) {
+    vb::g_opt_m64 = value ? 1 : 0;
     return 0;
   }
   return vb::fail("vame_set_option: unknown option");

@@ -151,20 +151,25 @@ constexpr int F_WTILE = 2 * F_WSUB;              // 24576 B : one K chunk of a 3
 constexpr int F_ATILE = 128 * KCHUNK * 2 * 2;    // 32768 B : one K chunk of the h tile (hi + lo)
 
 // UPC = hidden units per CTA (16 or 32), UPT = units per thread; 128 * UPC / UPT threads.
+// MT = batch rows per CTA: 128, or 64 (grid.y = 2 x tiles; tcgen05.mma M = 64 keeps D in lanes 0-15 of each TMEM lane quarter,
+// so lanes 16-31 of every warp idle through the element-wise part).  Halving the rows per CTA while doubling the CTAs
+// shortens the step as long as the grid fits the GPU in one wave.
 // TMEM columns of sub-slice s (16 units): [96 s, 96 s + 48) = a * w_hi for (r, z, n) x 16, [96 s + 48, 96 s + 96) = a * w_lo.
-template <int UPC, int UPT>
+template <int UPC, int UPT, int MT>
 __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(const GruFwdArgs a) {
   constexpr int WT = (UPC / 16) * F_WSUB;
+  constexpr int APL = MT * KCHUNK * 2;          // one plane (hi or lo) of a K chunk of the h tile
+  constexpr int AT = 2 * APL;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nkc = (H + KCHUNK - 1) / KCHUNK;
   uint8_t* sW = smem;
   uint8_t* sA = smem + (size_t)nkc * WT;
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + (size_t)nkc * F_ATILE);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + (size_t)nkc * AT);
   uint64_t* abar = wbar + 4;
   uint64_t* done = abar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-  const int c = blockIdx.x, tile = blockIdx.y;
+  const int c = blockIdx.x, tile = blockIdx.y / (128 / MT), hf = blockIdx.y % (128 / MT);
   const GruDirFwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
@@ -201,12 +206,15 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
     }
     __syncwarp();
   }
-  const int r_in = q * 32 + lane;
+  const bool act = (MT == 128) || lane < 16;                                      // this lane owns a row
+  const int r_in = (MT == 128) ? q * 32 + lane : hf * 64 + q * 16 + (lane & 15);  // row inside the 128-row tile
   const long b = (long)tile * 128 + r_in;
   const int j0 = half * UPT;           // first unit inside the slice
   const int u0 = c * UPC + j0;         // first hidden unit handled by this thread
   float gir[UPT], giz[UPT], gin[UPT], bhn[UPT];
-  {
+#pragma unroll
+  for (int i = 0; i < UPT; ++i) gir[i] = giz[i] = gin[i] = bhn[i] = 0.f;
+  if (act) {
     const float* gi_row = d.gi + (b * d.gi_bs + (long)d.t * d.gi_ts);
     ldfN<UPT>(gi_row + (long)u0 * d.gi_ld, d.gi_ld, gir);
     ldfN<UPT>(gi_row + (long)(H + u0) * d.gi_ld, d.gi_ld, giz);
@@ -232,12 +240,18 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
       }
       const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(d.h_in_p) + (size_t)tile * nkc * p16_tile_elems(128);
       for (int kc = 0; kc < nkc; ++kc) {
-        mbar_expect_tx(&abar[kc], F_ATILE);
-        bulk_g2s(sA + (size_t)kc * F_ATILE, hp + (size_t)kc * p16_tile_elems(128), F_ATILE, &abar[kc]);
+        mbar_expect_tx(&abar[kc], AT);
+        if constexpr (MT == 128) {
+          bulk_g2s(sA + (size_t)kc * AT, hp + (size_t)kc * p16_tile_elems(128), AT, &abar[kc]);
+        } else {       // rows [64 hf, 64 hf + 64) of the hi plane and of the lo plane: two contiguous 8 KB pieces
+          const __nv_bfloat16* t = hp + (size_t)kc * p16_tile_elems(128) + (size_t)hf * 64 * KCHUNK;
+          bulk_g2s(sA + (size_t)kc * AT, t, APL, &abar[kc]);
+          bulk_g2s(sA + (size_t)kc * AT + APL, t + 128 * KCHUNK, APL, &abar[kc]);
+        }
       }
-      const uint32_t idesc = make_idesc_bf16(128, 6 * UPC);
+      const uint32_t idesc = make_idesc_bf16(MT, 6 * UPC);
       // the issue loop is the critical resource (one thread): descriptors are precomputed, the k-steps fully unrolled
-      const uint64_t dA = make_desc(smem_u32(sA)), dAl = make_desc(smem_u32(sA) + 128 * KCHUNK * 2), dW = make_desc(smem_u32(sW));
+      const uint64_t dA = make_desc(smem_u32(sA)), dAl = make_desc(smem_u32(sA) + APL), dW = make_desc(smem_u32(sW));
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         if (kc < nkc) {
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < ksteps) {
               // one descriptor covers the [W_hi ; W_lo] planes of all sub-slices (6 UPC rows)
-              const uint32_t ao = kc * F_ATILE + ks * 2 * ATOM_BYTES, wo = kc * WT + ks * 2 * ATOM_BYTES;
+              const uint32_t ao = kc * AT + ks * 2 * ATOM_BYTES, wo = kc * WT + ks * 2 * ATOM_BYTES;
               if (kc == 0 && ks == 0) umma_bf16_c<0>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
               else umma_bf16_c<1>(tmem, desc_advance(dAl, ao), desc_advance(dW, wo), idesc);
               umma_bf16_c<1>(tmem, desc_advance(dA, ao), desc_advance(dW, wo), idesc);
@@ -265,10 +279,12 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
   }
 
   float hprev[UPT];
-  if (!a.flags) ldfN<UPT>(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);     // complete + visible after griddepcontrol.wait
+#pragma unroll
+  for (int i = 0; i < UPT; ++i) hprev[i] = 0.f;
+  if (!a.flags && act) ldfN<UPT>(d.h_in + (long)u0 * d.h_in_ld + b, d.h_in_ld, hprev);     // complete + visible after griddepcontrol.wait
   mbar_wait(done, 0);                   // (with flags this also orders the h_in read below after the producer's release)
   __syncwarp();
-  if (a.flags) {
+  if (a.flags && act) {
 #pragma unroll
     for (int i = 0; i < UPT; ++i) hprev[i] = ld_cg(d.h_in + (long)(u0 + i) * d.h_in_ld + b);
   }
@@ -302,8 +318,8 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
     ar[i] = r; az[i] = z; an[i] = n; bhn[i] = ghn;
   }
   DBG_STAMP(9);
-  stfN<UPT>(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
-  {
+  if (act) stfN<UPT>(d.h_out + (long)u0 * d.h_out_ld + b, d.h_out_ld, hn);
+  if (act) {
     const int kc = u0 / KCHUNK, kk = u0 % KCHUNK;
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.h_out_p) + ((size_t)tile * nkc + kc) * p16_tile_elems(128);
     stN_p16<UPT>(t, 128, r_in, kk, hn);
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
     if (lane == 0) flag_release_add(d.flag_out + tile, 1u);
   }
   DBG_STAMP(10);
-  if (d.sv_r) {
+  if (d.sv_r && act) {
     const long so = (long)u0 * d.sv_ld + b;
     stfN<UPT>(d.sv_r + so, d.sv_ld, ar);
     stfN<UPT>(d.sv_z + so, d.sv_ld, az);
@@ -348,32 +364,37 @@ static void launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 
   }
 }
 
+template <int UPC, int UPT, int MT>
+static void launch_fwd_variant(const GruFwdArgs& a, size_t smem, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(gru_step_fwd_kernel<UPC, UPT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, dim3(a.H / UPC, a.tiles * (128 / MT), a.ndir), 128 * (UPC / UPT), smem, st, a.pdl);
+  cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<UPC, UPT, MT>, a);
+}
+
 void launch_gru_step_fwd(const GruFwdArgs& a_in, cudaStream_t st) {
   GruFwdArgs a = a_in;
   a.dbg = g_dbg_buffer;
   const int nkc = (a.H + KCHUNK - 1) / KCHUNK;
   const int upc = a.upc == 16 ? 16 : 32;
-  const size_t smem = (size_t)nkc * ((upc / 16) * F_WSUB + F_ATILE) + 256;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_step_fwd_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_step_fwd_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_step_fwd_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_step_fwd_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_smem = smem;
-  }
-  cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  const int mt = (a.mt == 64 && g_opt_warps16 && !a.flags) ? 64 : 128;      // (the flag arrays are per 128-row tile)
+  const size_t smem = (size_t)nkc * ((upc / 16) * F_WSUB + mt * KCHUNK * 4) + 256;
   count_launch();
-  const dim3 grid(a.H / upc, a.tiles, a.ndir);
   // 16 warps: the serial gate epilogue is twice as parallel (8 or 4 units per thread instead of 16 or 8)
-  launch_cfg(cfg, attr, grid, g_opt_warps16 ? 512 : 256, smem, st, a.pdl);
-  if (upc == 32) {
-    if (g_opt_warps16) cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<32, 8>, a);
-    else cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<32, 16>, a);
+  if (mt == 64) {
+    if (upc == 32) launch_fwd_variant<32, 8, 64>(a, smem, st);
+    else launch_fwd_variant<16, 4, 64>(a, smem, st);
+  } else if (upc == 32) {
+    if (g_opt_warps16) launch_fwd_variant<32, 8, 128>(a, smem, st);
+    else launch_fwd_variant<32, 16, 128>(a, smem, st);
   } else {
-    if (g_opt_warps16) cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16, 4>, a);
-    else cudaLaunchKernelEx(&cfg, gru_step_fwd_kernel<16, 8>, a);
+    if (g_opt_warps16) launch_fwd_variant<16, 4, 128>(a, smem, st);
+    else launch_fwd_variant<16, 8, 128>(a, smem, st);
   }
 }
 
@@ -747,18 +768,24 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
 // exchanges the H/32 partial products dgh_c W_hh[c-rows, :] with the other CTAs of the cluster through global memory
 // (L2-coherent loads) between steps.
 // =================================================================================================
-template <int UPT, bool SUM>
+// MT = batch rows per CTA (128, or 64 with grid.y = 2 x tiles; see the forward step kernel).
+// With M = 64 the accumulator rows live in lanes 0-15 of each TMEM lane quarter: lane l and lane l + 16 of a warp then share
+// row l and split the warp group's UPT units between them (U = UPT / 2 units per thread); only the TMEM drain is done by the
+// lower half-warp, which hands half of each 16-column batch to its partner lanes with shuffles.
+template <int UPT, bool SUM, int MT>
 __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(const GruSeqBwdArgs a) {
+  constexpr int APL = MT * KCHUNK * 2;      // one plane of one K chunk of the A operand (dgh slice of this CTA)
+  constexpr int U = (MT == 64) ? UPT / 2 : UPT;   // units per thread
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, nrb = (H + 127) / 128, nsl = H / 32;
   const size_t wchunk = (size_t)nrb * 2 * B_APLANE;
   uint8_t* sW = smem;
   uint8_t* sA = smem + 2 * wchunk;
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + 4 * B_APLANE);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sA + 4 * APL);
   uint64_t* done = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-  const int c = blockIdx.x, tile = blockIdx.y;
+  const int c = blockIdx.x, tile = blockIdx.y / (128 / MT), hf = blockIdx.y % (128 / MT);
   const GruSeqDirBwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
@@ -790,54 +817,63 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
     }
     __syncwarp();
   }
-  const int r_in = q * 32 + lane;
+  const int hl = (MT == 64) ? (lane >> 4) : 0;                                    // which half of the warp group's units
+  const bool tm = (MT == 128) || lane < 16;                                       // this lane reads accumulator rows
+  const int r_loc = (MT == 128) ? q * 32 + lane : q * 16 + (lane & 15);           // row inside this CTA's M tile
+  const int r_in = (MT == 128) ? r_loc : hf * 64 + r_loc;                         // row inside the 128-row tile
   const long b = (long)tile * 128 + r_in;
-  const int j0 = half * UPT, u0 = c * 32 + j0;
-  const uint32_t idesc = make_idesc_bf16(128, H);
+  const int j0 = half * UPT + hl * U, u0 = c * 32 + j0;
+  const uint32_t idesc = make_idesc_bf16(MT, H);
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
   const int hh = H / (32 / UPT);            // TMEM columns drained by each warp group
-  float carry[UPT];
-  float sum_r[SUM ? UPT : 1], sum_z[SUM ? UPT : 1], sum_n[SUM ? UPT : 1];   // time sums of the input-gate gradients (decoders)
+  float carry[U];
+  float sum_r[SUM ? U : 1], sum_z[SUM ? U : 1], sum_n[SUM ? U : 1];   // time sums of the input-gate gradients (decoders)
 #pragma unroll
-  for (int i = 0; i < UPT; ++i) carry[i] = 0.f;
+  for (int i = 0; i < U; ++i) carry[i] = 0.f;
   if constexpr (SUM) {
 #pragma unroll
-    for (int i = 0; i < UPT; ++i) sum_r[i] = sum_z[i] = sum_n[i] = 0.f;
+    for (int i = 0; i < U; ++i) sum_r[i] = sum_z[i] = sum_n[i] = 0.f;
   }
-  if (d.dh_last) ldfN<UPT>(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
+  if (d.dh_last) ldfN<U>(d.dh_last + (long)u0 * d.dh_last_ld + b, d.dh_last_ld, carry);
 
   for (int s = 0; s < a.steps; ++s) {
     const int t = d.reverse ? s : a.steps - 1 - s;                       // BPTT order = reverse of the forward order
     const bool first_fwd = d.reverse ? (t == a.steps - 1) : (t == 0);
     const int tprev = d.reverse ? t + 1 : t - 1;
-    float r[UPT], z[UPT], n[UPT], ghn[UPT], hp[UPT], dh[UPT];
+#define SEQ_STAMP(i)                   \
+  do {                                 \
+    if (s == 10) DBG_STAMP(i);         \
+  } while (0)
+    SEQ_STAMP(0);
+    float r[U], z[U], n[U], ghn[U], hp[U], dh[U];
     {
       const long so = (long)u0 * d.sv_ld + (long)t * bpad + b;
-      ldfN<UPT>(d.sv[0] + so, d.sv_ld, r);
-      ldfN<UPT>(d.sv[1] + so, d.sv_ld, z);
-      ldfN<UPT>(d.sv[2] + so, d.sv_ld, n);
-      ldfN<UPT>(d.sv[3] + so, d.sv_ld, ghn);
+      ldfN<U>(d.sv[0] + so, d.sv_ld, r);
+      ldfN<U>(d.sv[1] + so, d.sv_ld, z);
+      ldfN<U>(d.sv[2] + so, d.sv_ld, n);
+      ldfN<U>(d.sv[3] + so, d.sv_ld, ghn);
     }
-    if (first_fwd) ldfN<UPT>(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hp);
-    else ldfN<UPT>(d.out + (long)u0 * d.out_ld + (long)tprev * bpad + b, d.out_ld, hp);
-    if (d.dout) ldfN<UPT>(d.dout + (long)u0 * d.dout_ld + (long)t * bpad + b, d.dout_ld, dh);
+    if (first_fwd) ldfN<U>(d.h0 + (long)u0 * d.h0_ld + b, d.h0_ld, hp);
+    else ldfN<U>(d.out + (long)u0 * d.out_ld + (long)tprev * bpad + b, d.out_ld, hp);
+    if (d.dout) ldfN<U>(d.dout + (long)u0 * d.dout_ld + (long)t * bpad + b, d.dout_ld, dh);
     else {
 #pragma unroll
-      for (int i = 0; i < UPT; ++i) dh[i] = 0.f;
+      for (int i = 0; i < U; ++i) dh[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < UPT; ++i) dh[i] += carry[i];
+    for (int i = 0; i < U; ++i) dh[i] += carry[i];
     if (s > 0) {
       cluster_wait_acquire();                                            // all partial products of the previous step are published
+      SEQ_STAMP(1);
       const float* pin = d.parts + ((s - 1) & 1) * pslot + (long)u0 * bpad + b;
       for (int p = 0; p < nsl; ++p) {
 #pragma unroll
-        for (int i = 0; i < UPT; ++i) dh[i] += ld_cg(pin + (long)p * slotf + (long)i * bpad);
+        for (int i = 0; i < U; ++i) dh[i] += ld_cg(pin + (long)p * slotf + (long)i * bpad);
       }
     }
-    float dar[UPT], daz[UPT], dan[UPT], dgn[UPT];
+    float dar[U], daz[U], dan[U], dgn[U];
 #pragma unroll
-    for (int i = 0; i < UPT; ++i) {
+    for (int i = 0; i < U; ++i) {
       const float dn = dh[i] * (1.0f - z[i]);
       const float dz = dh[i] * (hp[i] - n[i]);
       dan[i] = dn * (1.0f - n[i] * n[i]);
@@ -849,13 +885,15 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
     }
     {
       __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(sA);
-      __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sA + 2 * B_APLANE);
-      stN_p16<UPT>(a0, 128, r_in, j0, dar);
-      stN_p16<UPT>(a0, 128, r_in, 32 + j0, daz);
-      stN_p16<UPT>(a1, 128, r_in, j0, dgn);
+      __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sA + 2 * APL);
+      stN_p16<U>(a0, MT, r_loc, j0, dar);
+      stN_p16<U>(a0, MT, r_loc, 32 + j0, daz);
+      stN_p16<U>(a1, MT, r_loc, j0, dgn);
     }
+    SEQ_STAMP(2);
     fence_proxy_async_smem();
     __syncthreads();
+    SEQ_STAMP(3);
     const uint32_t ph = s & 1;
     if (warp == 0) {
       if (lane == 0) {
@@ -867,26 +905,27 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
 #pragma unroll
           for (int kk = 0; kk < 6; ++kk) {                 // k-steps 0..3 in chunk 0, 4..5 in chunk 1
             const uint32_t kc = kk >> 2, ko = (kk & 3) * 2 * ATOM_BYTES;
-            const uint32_t ao = kc * 2 * B_APLANE + ko, wo = kc * wch + ko;
-            if (kk == 0) umma_bf16_c<0>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
-            else umma_bf16_c<1>(tmem, desc_advance(dA0, ao + B_APLANE), desc_advance(dW0, wo), idesc);
+            const uint32_t ao = kc * 2 * APL + ko, wo = kc * wch + ko;
+            if (kk == 0) umma_bf16_c<0>(tmem, desc_advance(dA0, ao + APL), desc_advance(dW0, wo), idesc);
+            else umma_bf16_c<1>(tmem, desc_advance(dA0, ao + APL), desc_advance(dW0, wo), idesc);
             umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo + wplane), idesc);
             umma_bf16_c<1>(tmem, desc_advance(dA0, ao), desc_advance(dW0, wo), idesc);
           }
         }
         umma_commit(done);
+        SEQ_STAMP(4);
       }
       __syncwarp();
     }
-    // outputs that do not need the MMA
+    // outputs that do not need the MMA (read by later kernels: weight-gradient GEMMs, dx of the layer below)
     {
       const long o = (long)t * bpad + b;
-      stfN<UPT>(d.dgi + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
-      stfN<UPT>(d.dgi + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
-      stfN<UPT>(d.dgi + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dan);
-      stfN<UPT>(d.dgh + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
-      stfN<UPT>(d.dgh + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
-      stfN<UPT>(d.dgh + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dgn);
+      stfN<U>(d.dgi + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stfN<U>(d.dgi + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stfN<U>(d.dgi + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dan);
+      stfN<U>(d.dgh + (long)u0 * d.dg_ld + o, d.dg_ld, dar);
+      stfN<U>(d.dgh + (long)(H + u0) * d.dg_ld + o, d.dg_ld, daz);
+      stfN<U>(d.dgh + (long)(2 * H + u0) * d.dg_ld + o, d.dg_ld, dgn);
     }
     if (d.dgi_p) {
       const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
@@ -895,56 +934,68 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         const int k = g * H + u0;
-        stN_p16<UPT>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
+        stN_p16<U>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? dar : (g == 1 ? daz : dan));
       }
     }
     float* pout = d.parts + (s & 1) * pslot;
-    if (s == a.steps - 1) stfN<UPT>(pout + ((long)nsl * H + u0) * bpad + b, bpad, carry);   // final carry -> dh0 reduction
+    if (s == a.steps - 1) stfN<U>(pout + ((long)nsl * H + u0) * bpad + b, bpad, carry);   // final carry -> dh0 reduction
 
+    SEQ_STAMP(5);
     mbar_wait(done, ph);
     __syncwarp();
+    SEQ_STAMP(6);
     tc_fence_after();
     float* pbase = pout + (long)c * H * bpad + b;
     for (int c0 = half * hh; c0 < (half + 1) * hh; c0 += 16) {
       float v[16];
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
-      stfN<16>(pbase + (long)c0 * bpad, bpad, v);
+      if constexpr (MT == 128) {
+        stfN<16>(pbase + (long)c0 * bpad, bpad, v);
+      } else {
+        // rows live in lanes 0-15; lane l + 16 takes over columns c0 + 8 .. c0 + 15 of row l
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float hi8 = __shfl_sync(0xffffffffu, v[8 + i], lane & 15);
+          w[i] = tm ? v[i] : hi8;
+        }
+        stfN<8>(pbase + (long)(c0 + hl * 8) * bpad, bpad, w);
+      }
     }
     tc_fence_before();
+    SEQ_STAMP(7);
     if (s + 1 < a.steps) cluster_arrive_release();   // release at cluster scope publishes the partial sums to the peers
+    SEQ_STAMP(8);
   }
   if constexpr (SUM) {
-    stfN<UPT>(d.dgi_sum + (long)u0 * bpad + b, bpad, sum_r);
-    stfN<UPT>(d.dgi_sum + (long)(H + u0) * bpad + b, bpad, sum_z);
-    stfN<UPT>(d.dgi_sum + (long)(2 * H + u0) * bpad + b, bpad, sum_n);
+    stfN<U>(d.dgi_sum + (long)u0 * bpad + b, bpad, sum_r);
+    stfN<U>(d.dgi_sum + (long)(H + u0) * bpad + b, bpad, sum_z);
+    stfN<U>(d.dgi_sum + (long)(2 * H + u0) * bpad + b, bpad, sum_n);
     const int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)tile * nkc3 * p16_tile_elems(128);
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
       const int k = g * H + u0;
-      stN_p16<UPT>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? sum_r : (g == 1 ? sum_z : sum_n));
+      stN_p16<U>(base + (size_t)(k / KCHUNK) * p16_tile_elems(128), 128, r_in, k % KCHUNK, g == 0 ? sum_r : (g == 1 ? sum_z : sum_n));
     }
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, tmem_cols);
 }
 
-void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
+template <int UPT, bool SUM, int MT>
+static void launch_seq_bwd_variant(const GruSeqBwdArgs& a, cudaStream_t st) {
   const int nrb = (a.H + 127) / 128;
-  const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * B_APLANE + 256;
+  const size_t smem = (size_t)2 * nrb * 2 * B_APLANE + 4 * (MT * KCHUNK * 2) + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gru_seq_bwd_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gru_seq_bwd_kernel<UPT, SUM, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_smem = smem;
   }
-  const bool w16 = g_opt_warps16 && (a.H % 64 == 0);       // each of the 4 warp groups drains H/4 (multiple of 16) columns
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3(a.H / 32, a.tiles, a.ndir);
-  cfg.blockDim = dim3(w16 ? 512 : 256);
+  cfg.gridDim = dim3(a.H / 32, a.tiles * (128 / MT), a.ndir);
+  cfg.blockDim = dim3(128 * (32 / UPT));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -954,14 +1005,25 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<UPT, SUM, MT>, a);
+}
+
+void launch_gru_seq_bwd(const GruSeqBwdArgs& a_in, cudaStream_t st) {
+  GruSeqBwdArgs a = a_in;
+  a.dbg = g_dbg_buffer;
+  const bool w16 = g_opt_warps16 && (a.H % 64 == 0);       // each of the 4 warp groups drains H/4 (multiple of 16) columns
+  const bool m64 = a.mt == 64 && w16;
+  const bool sum = a.d[0].dgi_sum != nullptr;              // (set for both directions or for none)
   count_launch();
-  const bool sum = a.d[0].dgi_sum != nullptr;          // (set for both directions or for none)
-  if (w16) {
-    if (sum) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8, true>, a);
-    else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<8, false>, a);
+  if (m64) {
+    if (sum) launch_seq_bwd_variant<8, true, 64>(a, st);
+    else launch_seq_bwd_variant<8, false, 64>(a, st);
+  } else if (w16) {
+    if (sum) launch_seq_bwd_variant<8, true, 128>(a, st);
+    else launch_seq_bwd_variant<8, false, 128>(a, st);
   } else {
-    if (sum) cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16, true>, a);
-    else cudaLaunchKernelEx(&cfg, gru_seq_bwd_kernel<16, false>, a);
+    if (sum) launch_seq_bwd_variant<16, true, 128>(a, st);
+    else launch_seq_bwd_variant<16, false, 128>(a, st);
   }
 }
 

@@ -13,6 +13,7 @@ extern int g_opt_flags;     // 1: PDL-chained step kernels hand h over through r
                             //    default 0: measured equal to griddepcontrol.wait (tools/gpu_probe_graph.py, profiles/)
 extern int g_opt_warps16;   // 1: 16 warps per CTA (8 hidden units per thread) in the default recurrent kernels
 extern int g_opt_streams;   // 1: run independent branches of a step on internal side streams
+extern int g_opt_m64;       // 1: recurrent kernels take 64 batch rows per CTA (twice the CTAs) when the sweep fits the GPU
 extern int g_opt_slice16;   // 1: forward step kernels own 16 hidden units per CTA (twice the CTAs, N = 96 MMAs) when the sweep fits the GPU
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
@@ -92,6 +93,7 @@ struct GruFwdArgs {
   GruDirFwd d[2];
   int ndir, H, tiles;
   int upc;                // hidden units per CTA: 16 or 32 (0 = 32)
+  int mt;                 // batch rows per CTA: 64 or 128 (0 = 128)
   int pdl;                // launch with programmatic stream serialization
   int flags;              // 1: the recurrence dependency is carried by flag_in/flag_out instead of griddepcontrol.wait, so the
                           //    tail of step t (saved-gate stores, teardown) overlaps step t+1
@@ -134,6 +136,8 @@ struct GruSeqDirBwd {
 struct GruSeqBwdArgs {
   GruSeqDirBwd d[2];
   int ndir, H, tiles, steps;
+  int mt;                    // batch rows per CTA: 64 or 128 (0 = 128)
+  unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
 };
 void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 
