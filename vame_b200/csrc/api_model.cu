@@ -172,16 +172,16 @@ static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
 // with the latency-bound recurrent sweeps; fork/join are event edges, so the whole thing stays CUDA-graph capturable.
 // ================================================================================================
 struct Side {
-  cudaStream_t s[3];       // [0] future decoder, [1] weight-gradient work, [2] k-means prior
-  cudaEvent_t ev[32];
+  cudaStream_t s[4];       // [0] future decoder, [1] weight-gradient work, [2] k-means prior, [3] second weight-gradient stream
+  cudaEvent_t ev[64];
   int nev;
 };
 static Side& side() {
   static Side S{};
   static bool init = false;
   if (!init) {
-    for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4; ++i) cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 64; ++i) cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
     init = true;
   }
   return S;
@@ -209,7 +209,7 @@ static inline void mark(cudaStream_t st, const char* name) {
 static inline void edge(cudaStream_t from, cudaStream_t to) {
   if (from == to) return;
   Side& S = side();
-  cudaEvent_t e = S.ev[S.nev++ & 31];
+  cudaEvent_t e = S.ev[S.nev++ & 63];
   cudaEventRecord(e, from);
   cudaStreamWaitEvent(to, e, 0);
 }
@@ -511,12 +511,13 @@ static void pack_outT(GruBuf& L, int Bp, cudaStream_t st) {      // forward acti
   for (int d = 0; d < 2; ++d) pack_rows(L.out[d], rows, L.H, (int)rows, L.H, L.outT_p[d], st);   // out is already [H][rows]
 }
 // dgi_rowsum_fused: the caller packs dgi (encoder layers) and lets that pass produce db_ih
-static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st,
-                                bool dgi_rowsum_fused = false) {
+static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* h0T0, const void* h0T1, float* G, cudaStream_t st0,
+                                bool dgi_rowsum_fused = false, cudaStream_t st1 = nullptr) {
   const int H = L.H;
   const long rows = (long)L.steps * Bp;
   const int cB = Bp / KCHUNK, nk = (int)(rows / KCHUNK);
   for (int d = 0; d < 2; ++d) {
+    cudaStream_t st = (d == 1 && st1) ? st1 : st0;           // the two directions are independent
     // dgh is already [3H][rows]; its row sums (= db_hh) are accumulated by the same pass
     launch_pack_p16_rowsum(L.dgh[d], rows, 3 * H, (int)rows, 3 * H, L.dghT_p[d], G + o.bhh[d], st);
     const void* h0T = d == 0 ? h0T0 : h0T1;
@@ -767,7 +768,8 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc, Bp = w.B_pad, B = batch;
   {   // SMs left for the weight-gradient GEMMs while a sweep (tiles x H/32 slices x 2 directions CTAs, 1 per SM) is running
-    const int sweep = w.tiles * (H / 32) * 2 * (d->future_decoder ? 2 : 1);
+    int sweep = w.tiles * (H / 32) * 2 * (d->future_decoder ? 2 : 1);
+    if (g_opt_m64 && 2 * sweep <= 148) sweep *= 2;          // (same rule as gru_sweep_bwd: 64-row CTAs when they fit)
     g_side_sms = g_opt_streams ? (sweep < 100 ? 148 - sweep : 48) : 148;
   }
   const int nkcB = Bp / KCHUNK;
@@ -785,6 +787,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   pack_outT(w.e1, Bp, sB);
   pack_T(w.x_tb, F, F, T * Bp, T * Bp, w.xT_p, sB);
   mark(sB, "side:early packs done");
+  if (g_opt_streams) edge(sB, side().s[3]);   // the second weight-gradient stream also reads these operands
 
   const int ndec = d->future_decoder ? 2 : 1;
   const float* dz_dec[2] = {nullptr, nullptr};
@@ -897,29 +900,38 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   const int nk = (int)(rows / KCHUNK), nkc3 = nkc_of(3 * H);
   gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * Bp, w.dhidden + (size_t)3 * H * Bp, Bp, true, st);
   mark(st, "bwd:L1 sweep");
+  // the weight gradients of the two directions are independent: one side stream each (their fixed per-kernel costs overlap)
+  cudaStream_t sC = g_opt_streams ? side().s[3] : st;
+  cudaStream_t sdir[2] = {sB, sC};
+  const int side_total = g_side_sms;
+  if (g_opt_streams) g_side_sms = side_total / 2;
   edge(st, sB);
+  edge(st, sC);
   GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
       .run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
-  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB, true);
+  gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
-    launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sB);
+    launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sdir[dd]);
     for (int e = 0; e < 2; ++e)
       GemmB().A(w.e1.dgiT_p[dd], nk, nk).Bm(w.e0.outT_p[e], nk, nk)
-          .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sB);
+          .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sdir[dd]);
   }
   mark(sB, "side:L1 weight grads done");
   // ---- encoder layer 0
   mark(st, "bwd:dx1 gemm");
   gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st);
   edge(st, sB);
-  g_side_sms = 148;                          // nothing else runs beside the last block
-  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true);
+  edge(st, sC);
+  g_side_sms = g_opt_streams ? 74 : 148;     // nothing else runs beside the last block: half of the GPU per direction
+  gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
-    launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sB);
-    GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk).run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sB);
+    launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sdir[dd]);
+    GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk)
+        .run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sdir[dd]);
   }
   mark(st, "bwd:L0 sweep");
   edge(sB, st);
+  edge(sC, st);
   mark(st, "bwd:side-stream tail (weight gradients)");
   if (used_sA) edge(sA, st);                 // only streams that were forked into this call may be joined (graph capture isolation)
   return check_launch("vame_backward");
