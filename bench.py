@@ -296,9 +296,9 @@ def main():
                 "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 4 * flops_launch,
                 "us_per_launch": {k: v * 1e6 for k, v in res.items()},
                 "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 3-4x that in "
-                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/3 of the bf16 peak; B=%d keeps 32 of 148 "
-                        "SMs busy in a serial chain of %d dependent steps (latency-bound: ~1.5 us of MMA in a ~7-10 us step, "
-                        "DESIGN.md section 4)" % (B, 6 * T),
+                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/3 of the bf16 peak; the step is a serial "
+                        "chain of %d dependent time-step launches/phases on 64-128 of 148 SMs, latency-bound (about 1-2 us of MMA in a "
+                        "5-7 us step: cross-SM hand-over of h / partial sums, L2 round trips; DESIGN.md section 4)" % (6 * T),
                 "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
                 "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
 

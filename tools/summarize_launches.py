@@ -5,7 +5,8 @@ import sys
 from collections import defaultdict
 
 
-def main(path, out=None, title=""):
+def main(path, out=None, title="", step=None):
+    """step = k: keep only the launches of the k-th train step (1-based; a step ends with its adam_amsgrad_kernel)."""
     rows = []
     with open(path, newline="") as fh:
         lines = [ln for ln in fh if not ln.startswith("==")]
@@ -22,6 +23,10 @@ def main(path, out=None, title=""):
         elif unit in ("ms", "msecond"):
             v *= 1e6
         rows.append((name, v))
+    if step is not None:
+        ends = [i for i, (n, _) in enumerate(rows) if n.startswith("adam_amsgrad_kernel")]
+        lo = ends[step - 2] + 1 if step >= 2 else 0
+        rows = rows[lo:ends[step - 1] + 1]
     agg = defaultdict(lambda: [0, 0.0])
     for n, v in rows:
         agg[n][0] += 1
@@ -40,4 +45,5 @@ def main(path, out=None, title=""):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else "")
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else "",
+         int(sys.argv[4]) if len(sys.argv) > 4 else None)
