@@ -70,8 +70,69 @@ __global__ void pack_p16_kernel(const float* __restrict__ src, long ld, int tran
   pack_p16_body(src, ld, transposed, R, K, R_src, K_src, row_map, col_map, RB, out, blockIdx.x, gridDim.x);
 }
 
+// Fast path of the plain (row-major source, no maps) pack for K % 64 == 0, 16-byte aligned rows: a warp owns 8 rows x `kspan`
+// columns; lane = (row % 8) * 4 + (8-wide k group % 4), so every load instruction reads 8 x 128 contiguous bytes and every store
+// instruction writes 512 contiguous bytes of a tile plane ([r8][k8][8 rows][8 elts]); the optional row sums are kept in
+// registers over the whole span (one atomic per row and span).
+__global__ void __launch_bounds__(256) pack_rows_fast_kernel(const float* __restrict__ src, long ld, int R, int K, int R_src,
+                                                             __nv_bfloat16* __restrict__ out, float* __restrict__ rowsum, int kspan) {
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r7 = lane >> 2, k8l = lane & 3;
+  const int nkc = K / KCHUNK, nrg = ((R + 127) / 128) * 16, nks = (K + kspan - 1) / kspan;
+  for (long job = (long)blockIdx.x * wpb + warp; job < (long)nrg * nks; job += (long)gridDim.x * wpb) {
+    const int rg = (int)(job / nks), ks = (int)(job % nks);
+    const int r = rg * 8 + r7;
+    const bool valid = r < R_src;
+    const float* row = src + (long)r * ld;
+    __nv_bfloat16* tile_row = out + (size_t)(r >> 7) * nkc * p16_tile_elems(128);
+    const int rr = r & 127;
+    const int kend = min(K, (ks + 1) * kspan);
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = ks * kspan + k8l * 8; k < kend; k += 32) {
+      float v[8];
+      if (valid) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row + k + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      __nv_bfloat16* tile = tile_row + (size_t)(k >> 6) * p16_tile_elems(128);
+      const int off = p16_in_tile(rr, k & 63);
+      *reinterpret_cast<uint4*>(tile + off) = hi;
+      *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    if (rowsum) {
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (k8l == 0 && r < R && valid) atomicAdd(rowsum + r, s);
+    }
+  }
+}
+static bool pack_fast_ok(const float* src, long ld, int K) {
+  return (K % KCHUNK) == 0 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+static void launch_pack_rows_fast(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st) {
+  const int kspan = K >= 4096 ? 512 : (K >= 512 ? 256 : 64);
+  const long jobs = (long)((R + 127) / 128) * 16 * ((K + kspan - 1) / kspan);
+  long blocks = (jobs + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  count_launch();
+  pack_rows_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld, R, K, R_src, (__nv_bfloat16*)out, rowsum, kspan);
+}
+
 void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, int R_src, int K_src, const int* row_map,
                      const int* col_map, int RB, void* out, cudaStream_t st) {
+  if (!transposed && !row_map && !col_map && RB == 128 && K_src == K && pack_fast_ok(src, ld, K)) {
+    launch_pack_rows_fast(src, ld, R, K, R_src, out, nullptr, st);
+    return;
+  }
   const int nkc = (K + KCHUNK - 1) / KCHUNK, nrb = (R + RB - 1) / RB;
   long total = (long)nrb * RB * nkc * 8;
   int threads = 256;
@@ -84,6 +145,10 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
 }
 
 void launch_pack_p16_rowsum(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st) {
+  if (pack_fast_ok(src, ld, K)) {
+    launch_pack_rows_fast(src, ld, R, K, R_src, out, rowsum, st);
+    return;
+  }
   const int nkc = (K + KCHUNK - 1) / KCHUNK, nrb = (R + 127) / 128;
   long total = (long)nrb * 128 * nkc * 8;
   long blocks = (total + 255) / 256;
