@@ -144,6 +144,27 @@ int vame_debug_timeline_read(const char** names, float* ms, int max);
 int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef,
                       double* loss_out, float* dlatent, void* stream);
 
+/* ---- k-means on the latent vectors ---------------------------------------------------------------------
+ * Replaces sklearn.cluster.KMeans(init='k-means++', n_clusters, random_state, n_init).fit / .predict as called at
+ * vame/analysis/pose_segmentation.py:141-143 and :183-185.  x is [n, dim] fp32 row-major on the device (dim <= 64,
+ * k <= 128); the host side (vame_b200/kmeans.py) draws the random numbers with the same numpy RandomState stream as
+ * sklearn and drives these entry points. */
+size_t vame_kmeans_workspace_bytes(long n, int dim, int k);
+/* Lloyd iterations from centers_init [k, dim]: mean-centred data, tol relative to the mean feature variance, stops on
+ * unchanged labels or centre shift <= tol, final E-step with the final centres.  Blocking (one status read per iteration).
+ * labels int32 [n], centers_out [k, dim], inertia_out device double[1] (may be NULL), n_iter_out host int (may be NULL). */
+int vame_kmeans_lloyd(const float* x, long n, int dim, int k, const float* centers_init, int max_iter, float tol, int* labels,
+                      float* centers_out, double* inertia_out, int* n_iter_out, void* ws, size_t ws_bytes, void* stream);
+/* KMeans.predict */
+int vame_kmeans_assign(const float* x, long n, int dim, int k, const float* centers, int* labels, double* inertia_out, void* ws,
+                       size_t ws_bytes, void* stream);
+/* k-means++ round: newmin[j][i] = min(closest[i], |x_i - x_cand[j]|^2) (closest NULL: no min), pot[j] = sum_i newmin[j][i];
+ * cand device int64[m], m <= 8, newmin [m, n], pot device double[m] */
+int vame_kmeans_candidates(const float* x, long n, int dim, const long* cand, int m, const float* closest, float* newmin, double* pot,
+                           void* stream);
+/* k-means++ sampling: idx[j] = searchsorted(cumsum_fp64(closest), vals[j]) clipped to n - 1; vals device double[m], idx device int64[m] */
+int vame_kmeans_sample(const float* closest, long n, const double* vals, int m, long* idx, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,16 +194,48 @@ def gen_video1(rm, ps):
     print("wrote video1", clean.shape, lat.shape)
 
 
+def gen_kmeans(ps):
+    """k-means step: outputs of the reference's own same_parameterization / individual_parameterization
+    (vame/analysis/pose_segmentation.py:127-196, i.e. sklearn KMeans) on synthetic latent vectors of two 'files', plus
+    single-run pieces (sklearn kmeans_plusplus seeding, KMeans(init=array, n_init=1)) that pin the Lloyd restatement."""
+    from sklearn.cluster import KMeans, kmeans_plusplus
+    rng = np.random.RandomState(7)
+    k, Z = 8, 30
+    cent = rng.randn(k, Z).astype(np.float32) * 0.35
+    X = np.concatenate([cent[i] + (0.4 + 0.15 * i) * rng.randn(375, Z).astype(np.float32) for i in range(k)]).astype(np.float32)
+    X = X[rng.permutation(X.shape[0])]
+    files = ["a", "b"]
+    lat = [X[:1800], X[1800:]]
+    cfg = {"random_state_kmeans": 42, "random_state_kmeans: ": 42, "n_init_kmeans": 3}
+    lab_s, cen_s, use_s = ps.same_parameterization(cfg, files, lat, k, "kmeans")
+    lab_i, cen_i, use_i = ps.individual_parameterization(cfg, files, lat, k)
+    seed = 12345
+    init, idx = kmeans_plusplus(X, k, random_state=seed)
+    km = KMeans(n_clusters=k, init=init, n_init=1).fit(X)
+    out = {"X": X, "split": np.array([1800]), "k": np.array([k]),
+           "same_labels0": lab_s[0], "same_labels1": lab_s[1], "same_centers": cen_s[0], "same_usage0": use_s[0], "same_usage1": use_s[1],
+           "ind_labels0": lab_i[0], "ind_labels1": lab_i[1], "ind_centers0": cen_i[0], "ind_centers1": cen_i[1],
+           "pp_seed": np.array([seed]), "pp_init": init, "pp_idx": idx,
+           "single_labels": km.labels_, "single_centers": km.cluster_centers_, "single_inertia": np.array([km.inertia_]),
+           "single_n_iter": np.array([km.n_iter_])}
+    np.savez_compressed(os.path.join(OUT, "kmeans_blobs.npz"), **out)
+    print("kmeans_blobs: single inertia %.4f n_iter %d" % (km.inertia_, km.n_iter_))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
     rm, rv, ps = reference_modules()
     torch.set_num_threads(os.cpu_count())
+    if "--only-kmeans" in sys.argv:
+        gen_kmeans(ps)
+        return
     for name in CASES:
         gen_step_case(name, rm, rv)
     gen_train_fn(rm, rv)
     gen_embed_synth(rm, ps)
     gen_video1(rm, ps)
+    gen_kmeans(ps)
 
 
 if __name__ == "__main__":

@@ -159,3 +159,31 @@ def test_port_vs_live_reference_forward():
         b = port.forward(x, None)
     for u, v in zip(a, b):
         assert torch.allclose(u, v, rtol=1e-6, atol=1e-6)
+
+
+# ---- k-means: numpy restatement vs the reference's own same/individual_parameterization outputs --------
+def _kmeans_gold():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmeans_blobs.npz"))
+
+
+def test_kmeans_seeding_and_lloyd_match_sklearn():
+    from oracle import kmeans_numpy as K
+    g = _kmeans_gold()
+    X, k = g["X"], int(g["k"][0])
+    _, idx = K.kmeans_plusplus(X, k, np.random.RandomState(int(g["pp_seed"][0])))
+    assert np.array_equal(idx, g["pp_idx"])
+    lab, cen, inertia, n_iter = K.lloyd(X, g["pp_init"])
+    assert np.array_equal(lab, g["single_labels"])
+    assert np.abs(cen - g["single_centers"]).max() < 1e-5
+    assert abs(inertia - float(g["single_inertia"][0])) / inertia < 1e-6
+    assert n_iter == int(g["single_n_iter"][0])
+
+
+def test_kmeans_full_fit_matches_reference_parameterizations():
+    from oracle import kmeans_numpy as K
+    g = _kmeans_gold()
+    X, k, sp = g["X"], int(g["k"][0]), int(g["split"][0])
+    for i, (a, b) in enumerate(((0, sp), (sp, X.shape[0]))):          # individual_parameterization: seed 42, n_init 3
+        lab, cen, _, _ = K.kmeans(X[a:b], k, 42, 3)
+        assert np.array_equal(lab, g["ind_labels%d" % i])
+        assert np.abs(cen - g["ind_centers%d" % i]).max() < 1e-5

@@ -45,6 +45,12 @@ SIGNATURES = {
                                     c_size_t, c_void_p]),
     "vame_decoder_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vame_cluster_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "vame_kmeans_workspace_bytes": (c_size_t, [c_long, c_int, c_int]),
+    "vame_kmeans_lloyd": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "vame_kmeans_assign": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_kmeans_candidates": (c_int, [c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vame_kmeans_sample": (c_int, [c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 

@@ -45,9 +45,20 @@ def install(verbose=False):
         rv.use_gpu = True
     ps = sys.modules.get("vame.analysis.pose_segmentation")
     if ps is not None:
-        for n in ("load_model", "embedd_latent_vectors"):
+        for n in ("load_model", "embedd_latent_vectors", "individual_parameterization"):
             setattr(ps, n, getattr(_ps, n))
             done.append((ps.__name__, n))
+        # k-means parameterization on the device; the HMM branch of same_parameterization stays the reference's
+        if not hasattr(ps, "_ref_same_parameterization"):
+            ps._ref_same_parameterization = ps.same_parameterization
+
+        def same_parameterization(cfg, files, latent_vector_files, states, parameterization):
+            if parameterization == "kmeans":
+                return _ps.same_parameterization(cfg, files, latent_vector_files, states, parameterization)
+            return ps._ref_same_parameterization(cfg, files, latent_vector_files, states, parameterization)
+
+        ps.same_parameterization = same_parameterization
+        done.append((ps.__name__, "same_parameterization"))
     if verbose:
         for m, n in done:
             print("vame_b200: %s.%s -> B200 path" % (m, n))

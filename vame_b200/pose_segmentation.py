@@ -67,3 +67,63 @@ def embedd_latent_vectors(cfg, files, model, fixed):
             latent_vector_files.append(embed_series(model, data, temp_win))
     model.train(was_training)
     return latent_vector_files
+
+
+# ---- k-means parameterization ------------------------------------------------------------------------
+def consecutive(data, stepsize=1):
+    """pose_segmentation.py:103-105"""
+    data = data[:]
+    return np.split(data, np.where(np.diff(data) != stepsize)[0] + 1)
+
+
+def get_motif_usage(label):
+    """Motif usage counts with zero-filled gaps between the observed labels  [pose_segmentation.py:108-125]."""
+    values, counts = np.unique(label, return_counts=True)
+    cons = consecutive(values)
+    if len(cons) == 1:
+        return counts
+    usage = list(counts)
+    for i in range(len(cons) - 1):
+        gap = (cons[i + 1][0] - cons[i][-1]) - 1
+        for j in range(1, gap + 1):
+            usage.insert(cons[i][-1] + j, 0)
+    return np.array(usage)
+
+
+def same_parameterization(cfg, files, latent_vector_files, states, parameterization):
+    """One k-means over the concatenated latent vectors of all files  [pose_segmentation.py:127-170]; the reference hard-codes
+    random_state=42, n_init=20 here (:141).  Only the "kmeans" parameterization is accelerated."""
+    if parameterization != "kmeans":
+        raise VameB200Error("vame_b200.same_parameterization: only parameterization='kmeans' is implemented (got %r)" % (parameterization,))
+    from .kmeans import DeviceKMeans
+    latent_vector_cat = np.concatenate(latent_vector_files, axis=0)
+    print("Using kmeans as parameterization!")
+    km = DeviceKMeans(states, random_state=42, n_init=20).fit(latent_vector_cat)
+    clust_center = km.cluster_centers_
+    label = km.predict(latent_vector_cat).cpu().numpy()
+    labels, cluster_centers, motif_usages = [], [], []
+    idx = 0
+    for i, _file in enumerate(files):
+        file_len = latent_vector_files[i].shape[0]
+        labels.append(label[idx:idx + file_len])
+        cluster_centers.append(clust_center)
+        motif_usages.append(get_motif_usage(label[idx:idx + file_len]))
+        idx += file_len
+    return labels, cluster_centers, motif_usages
+
+
+def individual_parameterization(cfg, files, latent_vector_files, cluster):
+    """One k-means per file  [pose_segmentation.py:173-196] (the reference reads the seed from the key
+    'random_state_kmeans: ', trailing colon and space included; both spellings are accepted here)."""
+    from .kmeans import DeviceKMeans
+    random_state = cfg["random_state_kmeans: "] if "random_state_kmeans: " in cfg else cfg["random_state_kmeans"]
+    n_init = cfg["n_init_kmeans"]
+    labels, cluster_centers, motif_usages = [], [], []
+    for i, file in enumerate(files):
+        print(file)
+        km = DeviceKMeans(cluster, random_state=random_state, n_init=n_init).fit(latent_vector_files[i])
+        label = km.predict(latent_vector_files[i]).cpu().numpy()
+        motif_usages.append(get_motif_usage(label))
+        labels.append(label)
+        cluster_centers.append(km.cluster_centers_)
+    return labels, cluster_centers, motif_usages
