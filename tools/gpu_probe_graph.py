@@ -97,6 +97,10 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
                  "tmem loaded", "math done", "h stores issued"]
         print("[%s pdl=%d] fwd step kernel timeline (ns since start of last launch): " % (mode, pdl) +
               ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
+        if lib.vame_get_option(b"rw") & 1:
+            # rw forward kernel, step 10 of CTA 0: 0 loop top, 1 after cluster wait, 2 MMAs issued (MMA lane), 3 last gate's MMAs done,
+            # 4 gate math done, 5 h pushed to the peers, 6 after cluster arrive, 7 global stores + next gi loads issued
+            print("[%s pdl=%d] rw fwd stamps (ns since loop top): %s" % (mode, pdl, [st[i] - st[0] for i in range(8)]), flush=True)
         dbg.zero_()
         lib.vame_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
         lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 1, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
@@ -107,6 +111,11 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
                  "before mma wait", "mma done", "parts stored", "after cluster arrive", "gate-grad stores issued"]
         print("[%s pdl=%d] bwd persistent kernel, step 10 timeline (ns): " % (mode, pdl) +
               ", ".join("%s=%d" % (n, st[i] - st[0]) for i, n in enumerate(names)), flush=True)
+        if lib.vame_get_option(b"rw") & 2:
+            # rw backward kernel, step 10 of CTA 0: 0 loop top, 1 after cluster wait, 2 gate gradients + operand written,
+            # 3 MMAs issued (MMA lane), 4 partial sums pushed, 5 after cluster arrive, 6 next step's loads issued
+            print("[%s pdl=%d] rw bwd stamps (ns since loop top): %s" % (mode, pdl, [st[i] - st[0] for i in range(7)]), flush=True)
+        print("[%s pdl=%d] rw=%d rw_timeouts=%d" % (mode, pdl, lib.vame_get_option(b"rw"), lib.vame_get_option(b"rw_timeouts")), flush=True)
         e0.record()
         for _ in range(20):
             lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 0, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())

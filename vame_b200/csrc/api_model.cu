@@ -23,6 +23,7 @@ struct GruBuf {
   float* h0[2]; void* h0_p[2];          // initial state (zeros for the encoder)
   float* dgi[2]; float* dgh[2]; void* dgi_p[2];
   float* parts[2];
+  int parts_n;                          // partial-sum slots that hold the final dh0 after the last backward sweep (1 after an rw sweep)
   void* dghT_p[2]; void* dgiT_p[2]; void* outT_p[2]; void* h0T_p[2];
   unsigned int* flags;                  // [2 dirs][steps][tiles] hand-over counters of the per-step kernels
 };
@@ -278,6 +279,10 @@ struct JobQ {
     PackJob j{}; j.src = w; j.out = out; j.kind = 1 + mode; j.R = H;
     push(j);
   }
+  void whh_rw(const float* w, int H, int mode, void* out) {
+    PackJob j{}; j.src = w; j.out = out; j.kind = 4 + mode; j.R = H;
+    push(j);
+  }
   void bias(const float* b_ih, const float* b_hh, int H, float* out) {
     PackJob j{}; j.src = b_ih; j.src2 = b_hh; j.out = out; j.kind = 3; j.R = H;
     push(j);
@@ -290,6 +295,10 @@ static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W
   for (int d = 0; d < 2; ++d) {
     q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
     q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
+    if (W.whh_rw[d]) {
+      q.whh_rw(P + o.whh[d], H, 0, W.whh_rw[d]);
+      q.whh_rw(P + o.whh[d], H, 1, W.whhT_rw[d]);
+    }
     q.T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d]);                 // [In rows, K = 3H]
     q.bias(P + o.bih[d], P + o.bhh[d], H, W.bias_gi + (size_t)d * 3 * H);
   }
@@ -339,13 +348,16 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
                           cudaStream_t st) {
   const int H = L.H;
   zero_p16_padding(L, tiles, true, st);
-  if (g_opt_persistent & 1) {                   // one cluster kernel for the whole sweep
+  // resident-weight cluster kernel (gru_rw.cu): needs 8 consecutive batch rows of gi per vector load
+  const bool rw = (g_opt_rw & 1) && W.whh_rw[0] && rw_applicable(H, tiles) && L.gi_bs == 1 && (L.gi_ts % 4) == 0;
+  if (rw || (g_opt_persistent & 1)) {           // one cluster kernel for the whole sweep
     GruSeqFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
     const long Bp = (long)tiles * 128;
     for (int d = 0; d < 2; ++d) {
       GruSeqDirFwd& D = a.d[d];
       D.w_p = W.whh_p[d]; D.b_hn = d == 0 ? b_hn0 : b_hn1;
+      D.w_rw = W.whh_rw[d];
       D.gi = L.gi + (size_t)d * 3 * H * L.gi_ld; D.gi_ld = L.gi_ld; D.gi_bs = L.gi_bs; D.gi_ts = L.gi_ts;
       D.h0 = L.h0[d]; D.h0_ld = Bp; D.h0_p = L.h0_p[d];
       D.out = L.out[d]; D.out_ld = (long)L.out_slots * Bp; D.out_slots = L.out_slots;
@@ -355,7 +367,8 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
       D.sv_ld = (long)L.steps * Bp;
       D.reverse = d;
     }
-    launch_gru_seq_fwd(a, st);
+    if (rw) launch_gru_rw_fwd(a, st);
+    else launch_gru_seq_fwd(a, st);
     return;
   }
   const size_t slotp = (size_t)tiles * nkc_of(H) * p16_tile_elems(128);
@@ -431,7 +444,9 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
   const size_t slotf = (size_t)Bp * H;
   const size_t pslot = (size_t)(nsl + 1) * slotf;
   zero_p16_padding(L, tiles, false, st);
-  if (g_opt_persistent & 2) {                   // one cluster kernel for the whole BPTT sweep
+  const bool rw = (g_opt_rw & 2) && W.whhT_rw[0] && rw_applicable(H, tiles);
+  L.parts_n = rw ? 1 : nsl + 1;
+  if (rw || (g_opt_persistent & 2)) {           // one cluster kernel for the whole BPTT sweep
     GruSeqBwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
     a.mt = (g_opt_m64 && g_bwd_concurrent * tiles * (H / 32) * 2 * 2 <= 148) ? 64 : 128;
@@ -439,6 +454,8 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
     for (int d = 0; d < 2; ++d) {
       GruSeqDirBwd& D = a.d[d];
       D.wT_p = W.whhT_p[d];
+      D.wT_rw = W.whhT_rw[d];
+      D.dh0_out = L.parts[d] + ((L.steps - 1) & 1) * pslot;          // = final_parts(L, d, tiles), slot 0
       D.dh_last = d == 0 ? dhl0 : dhl1; D.dh_last_ld = dhl_ld;
       D.dout = d == 0 ? dout0 : dout1; D.dout_ld = dout_ld;
       for (int i = 0; i < 4; ++i) D.sv[i] = L.sv[d][i];
@@ -453,7 +470,8 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
       if (dgi_sum && ((3 * H) % KCHUNK) != 0) cudaMemsetAsync(dgi_sum_p[d], 0, (size_t)tiles * nkc3 * p16_tile_bytes(128), st);
       D.reverse = d;
     }
-    launch_gru_seq_bwd(a, st);
+    if (rw) launch_gru_rw_bwd(a, st);
+    else launch_gru_seq_bwd(a, st);
     return dgi_sum != nullptr;
   }
   const bool use_flags = pdl && g_opt_pdl && g_opt_flags;
@@ -838,7 +856,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
       }
     }
     // latent_to_hidden backward through the inverse of the .view(2,B,H) quirk
-    launch_parts_reduce_pack(final_parts(D.g, 0, w.tiles), Hd / 32 + 1,
+    launch_parts_reduce_pack(final_parts(D.g, 0, w.tiles), D.g.parts_n,
                              (long)(final_parts(D.g, 1, w.tiles) - final_parts(D.g, 0, w.tiles)), 2, B, Bp, Hd, D.dhid, D.dhid_p, sd);
     // dz = [dgi_sum_f, dgi_sum_b, dhid] [W_ih_f ; W_ih_b ; W_l2h]: one split-K GEMM over the concatenated K
     GemmB().A(D.dgi_sum_p[0], nkc3, nkc3).A(D.dgi_sum_p[1], nkc3, nkc3).A(D.dhid_p, nkc2H, nkc2H)

@@ -14,6 +14,8 @@ int g_opt_slice16 = 1;
 int g_opt_m64 = 1;
 int g_opt_flags = 0;           // measured: no gain (the gpu-scope publish costs what the kernel-completion flush costs)
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
+int g_opt_rw = 3;              // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels when applicable
+int g_opt_rw_waves = 1;
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -39,6 +41,9 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "warps16") == 0) return vb::g_opt_warps16;
   if (strcmp(name, "slice16") == 0) return vb::g_opt_slice16;
   if (strcmp(name, "m64") == 0) return vb::g_opt_m64;
+  if (strcmp(name, "rw") == 0) return vb::g_opt_rw;
+  if (strcmp(name, "rw_waves") == 0) return vb::g_opt_rw_waves;
+  if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
   return -1;
 }
 
@@ -70,6 +75,14 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "m64") == 0) {
     vb::g_opt_m64 = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "rw") == 0) {
+    vb::g_opt_rw = value & 3;
+    return 0;
+  }
+  if (strcmp(name, "rw_waves") == 0) {
+    vb::g_opt_rw_waves = value < 1 ? 1 : value;
     return 0;
   }
   return vb::fail("vame_set_option: unknown option");

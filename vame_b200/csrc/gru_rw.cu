@@ -1,0 +1,649 @@
+// Resident-weight recurrent sweeps ("rw" kernels): the whole forward / BPTT sweep of one bi-GRU layer in one
+// thread-block-cluster kernel whose recurrence never leaves the cluster.
+//
+// Why: in the slice kernels of gru.cu a time step hands h_t (or the BPTT partial sums) from the producing SMs to the
+// consuming SMs through L2 (64 KB per CTA and step) - a 1.7 us round trip that dominates the 5 / 7 us step at B = 256.
+// Here the GEMM is transposed (swap-AB): the WEIGHTS are the M side of tcgen05.mma and stay in shared memory for the
+// whole sweep, the batch rows are the (small) N side.
+//   * a cluster of 4 CTAs owns 16 batch rows of one direction; CTA c owns the gate rows of H/4 hidden units:
+//     3 (gates) x H/64 (k chunks) A tiles of 128 rows x 64 k bf16 = 3 H^2 bytes (192 KB at H = 256).  A tile row (= TMEM lane)
+//     32 q + l holds the bf16 HI plane of unit 16 q + l for l < 16 and the LO plane of unit 16 q + l - 16 for l >= 16, so the
+//     hi / lo partial products of one unit sit in the two half-warps of the warp that owns TMEM lane quarter q.
+//   * the B operand is h_{t-1} of the 16 rows as [16 hi rows ; 16 lo rows] x H (K-major, 4 KB per k chunk): ONE
+//     MMA (M = 128, N = 32, K = 16) yields all four hi/lo partial products.  3 H/16 = 48 MMAs per step and CTA.
+//   * after the gate math every CTA pushes its 16 x H/4 slice of h_t (bf16 hi/lo, already in UMMA operand layout) into the
+//     B operand buffer of all 4 CTAs with 16-byte st.shared::cluster stores (12 KB out per CTA and step) and the cluster
+//     synchronises with ONE barrier.cluster per step (double-buffered operand).  No L2 round trip, no TMA re-fetch.
+//   * BPTT: dh_{t-1}^T = W_hh^T dgh^T as a K-split: CTA c holds W_hh^T[:, gate rows of its units] (H/64 A tiles of 128 x 3H/4),
+//     builds the dgh^T operand of its own units locally and pushes the fp32 partial sums of the units owned by CTA o into
+//     o's receive buffer (4 source slots); the operand buffer aliases the receive slot that was consumed at the top of the step.
+// Numerics are those of the slice kernels (bf16 hi/lo split of both operands, fp32 accumulation, all four partial
+// products); cell equations: torch.nn.GRU as used at vame/model/rnn_model.py:41,106,141, BPTT: SURVEY.md section 3.5.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+
+__device__ unsigned int g_rw_timeouts = 0;     // bounded mbarrier waits that gave up (must stay 0; read by vame_debug_rw_timeouts)
+
+#ifdef VAME_ACCURATE_MATH
+__device__ __forceinline__ float rw_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float rw_tanh(float x) { return tanhf(x); }
+#else
+__device__ __forceinline__ float rw_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float rw_tanh(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+#endif
+
+constexpr int RW_ATILE = 128 * KCHUNK * 2;     // 16384 B: 128 weight rows x 64 k (bf16)
+constexpr int RW_BTILE = 32 * KCHUNK * 2;      //  4096 B: [16 hi rows ; 16 lo rows] x 64 k (bf16)
+constexpr int RW_THREADS = 160;                // warps 0-3: element-wise work (one TMEM lane quarter each), warp 4: TMA + MMA issue
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// a wait that cannot hang the GPU: a protocol bug shows up as a counted time-out (and wrong numbers), not as a dead box
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < (1 << 24); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  atomicAdd(&g_rw_timeouts, 1u);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 element-wise warps
+
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// One accumulator block of 32 columns: this lane's row holds (plane of lane) x [h_hi rows 0-15 | h_lo rows 0-15].
+// Lane l < 16 ends up with rows 0-7, lane l + 16 with rows 8-15 of the same unit, hi and lo planes summed.
+__device__ __forceinline__ void rw_reduce32(uint32_t taddr, int half, float* out8) {
+  float v[32];
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16, v + 16);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float lo = v[i] + v[16 + i], hi = v[8 + i] + v[24 + i];
+    const float send = half ? lo : hi, keep = half ? hi : lo;
+    out8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+}
+
+// v[i] = value(unit of this lane, row 8 half + i).  8 x 8 transpose inside each group of 8 lanes (3 butterfly stages on
+// packed bf16 hi|lo words): afterwards this lane holds row 8 half + (lane & 7) for the 8 consecutive units of its octet,
+// as one 16-byte vector per plane - an atom row of the UMMA K-major operand layout.
+__device__ __forceinline__ void rw_transpose_pack(const float* v, int lane, uint4& hi, uint4& lo) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 h, l;
+    split_bf16(v[i], h, l);
+    w[i] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+  }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    const bool bit = (lane & d) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j & d) continue;
+      const uint32_t x = bit ? w[j] : w[j | d];
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+      if (bit) w[j] = y;
+      else w[j | d] = y;
+    }
+  }
+  hi.x = (w[0] & 0xffffu) | (w[1] << 16); hi.y = (w[2] & 0xffffu) | (w[3] << 16);
+  hi.z = (w[4] & 0xffffu) | (w[5] << 16); hi.w = (w[6] & 0xffffu) | (w[7] << 16);
+  lo.x = (w[0] >> 16) | (w[1] & 0xffff0000u); lo.y = (w[2] >> 16) | (w[3] & 0xffff0000u);
+  lo.z = (w[4] >> 16) | (w[5] & 0xffff0000u); lo.w = (w[6] >> 16) | (w[7] & 0xffff0000u);
+}
+// byte offset of (row n of the 32-row operand, k) inside an operand buffer of RW_BTILE-sized k chunks; k % 8 == 0
+__device__ __forceinline__ uint32_t rw_b_off(int n, int k) { return (uint32_t)(k >> 6) * RW_BTILE + 2u * (uint32_t)p16_in_tile(n, k & 63); }
+
+#define RW_STAMP(i)                                                                                          \
+  do {                                                                                                        \
+    if (a.dbg && s == 10 && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {      \
+      unsigned long long t_;                                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
+      a.dbg[(i)] = t_;                                                                                        \
+    }                                                                                                         \
+  } while (0)
+#define RW_STAMP_MMA(i)                                                                                      \
+  do {                                                                                                        \
+    if (a.dbg && s == 10 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {                          \
+      unsigned long long t_;                                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
+      a.dbg[(i)] = t_;                                                                                        \
+    }                                                                                                         \
+  } while (0)
+
+// =================================================================================================
+// forward sweep
+// =================================================================================================
+// grid = (4, B_pad / 16, directions), cluster = (4, 1, 1), 160 threads.  NKC = H / 64.
+template <int NKC>
+__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqFwdArgs a) {
+  constexpr int H = 64 * NKC, UC = 16 * NKC;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
+  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [2][NKC][RW_BTILE]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + 2 * NKC * RW_BTILE);
+  uint64_t* done = wbar + 1;                                      // [3]: accumulator of gate g complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 3);
+
+  const uint32_t c = cluster_ctarank();
+  const GruSeqDirFwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
+  const bool epi = warp < 4 && q < NKC;                           // this warp owns 16 units of the slice
+  const long Bp = (long)a.tiles * 128;
+  const int steps = a.steps;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int g = 0; g < 3; ++g) mbar_init(&done[g], 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_rw) + (size_t)c * 3 * NKC * (RW_ATILE / 2);
+      mbar_expect_tx(wbar, 3 * NKC * RW_ATILE);
+      for (int i = 0; i < 3 * NKC; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+    }
+    __syncwarp();
+  }
+
+  const int j = 16 * q + (lane & 15);                             // unit inside the slice
+  const int u = (int)c * UC + j;                                  // hidden unit
+  const long b0 = (long)blockIdx.y * 16 + 8 * half;               // first of this lane's 8 batch rows
+  const int nrow = 8 * half + (lane & 7);                         // operand row this lane writes after the transpose
+  float hprev[8], bhn = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
+  if (epi) {
+    bhn = d.b_hn[u];
+    // initial state -> operand buffer 0 (every CTA builds the complete 16 x H operand from global memory)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[8];
+      ld8(d.h0 + (long)(cc * UC + j) * d.h0_ld + b0, v);
+      if (cc == (int)c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hprev[i] = v[i];
+      }
+      uint4 hi, lo;
+      rw_transpose_pack(v, lane, hi, lo);
+      const int k0 = cc * UC + 16 * q + 8 * oct;
+      *reinterpret_cast<uint4*>(sH + rw_b_off(nrow, k0)) = hi;
+      *reinterpret_cast<uint4*>(sH + rw_b_off(16 + nrow, k0)) = lo;
+    }
+    fence_proxy_async_smem();
+  }
+  // every CTA of the cluster is running and initialised before anyone writes into a peer's shared memory
+  cluster_arrive_release();
+  cluster_wait_acquire();
+
+  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+  float gir[8], giz[8], gin[8];
+  if (epi) {
+    const int t0 = d.reverse ? steps - 1 : 0;
+    const float* gi_row = d.gi + (b0 * d.gi_bs + (long)t0 * d.gi_ts);
+    ld8(gi_row + (long)u * d.gi_ld, gir);
+    ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+    ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+  }
+
+  for (int s = 0; s < steps; ++s) {
+    const int t = d.reverse ? steps - 1 - s : s;
+    const int so = (d.out_slots == steps) ? t : (s & 1);
+    const int sp = (d.out_p_slots == steps) ? t : (s & 1);
+    const uint32_t ph = s & 1;
+    RW_STAMP(0);
+    if (s > 0) cluster_wait_acquire();                            // every CTA's slice of h_{t-1} has landed in buffer s & 1
+    RW_STAMP(1);
+    if (warp == 4) {
+      if (lane == 0) {
+        if (s == 0) mbar_wait_b(wbar, 0);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(sH) + ph * NKC * RW_BTILE);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * RW_BTILE + ks * 2 * ATOM_BYTES;
+              if (kc == 0 && ks == 0) umma_bf16_c<0>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              else umma_bf16_c<1>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            }
+          }
+          umma_commit(&done[g]);
+        }
+        RW_STAMP_MMA(2);
+      }
+      __syncwarp();
+    }
+    float hn[8], sr[8], sz[8], sn[8], sg[8];
+    uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
+    if (epi) {
+      float ar[8], az[8], an[8];
+      mbar_wait_b(&done[0], ph);
+      tc_fence_after();
+      rw_reduce32(taddr, half, ar);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
+      mbar_wait_b(&done[1], ph);
+      tc_fence_after();
+      rw_reduce32(taddr + 32, half, az);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
+      mbar_wait_b(&done[2], ph);
+      tc_fence_after();
+      RW_STAMP(3);
+      rw_reduce32(taddr + 64, half, an);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] = an[i] + bhn;
+        sn[i] = rw_tanh(gin[i] + sr[i] * sg[i]);
+        hn[i] = (1.0f - sz[i]) * sn[i] + sz[i] * hprev[i];
+        hprev[i] = hn[i];
+      }
+      RW_STAMP(4);
+      rw_transpose_pack(hn, lane, phi, plo);
+      if (s + 1 < steps) {                                        // h_t -> operand buffer (s + 1) & 1 of all 4 CTAs
+        const int k0 = (int)c * UC + 16 * q + 8 * oct;
+        const uint32_t base = smem_u32(sH) + (ph ^ 1u) * NKC * RW_BTILE;
+        const uint32_t ohi = base + rw_b_off(nrow, k0), olo = base + rw_b_off(16 + nrow, k0);
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+          st_cluster_v4(mapa_u32(ohi, r), phi);
+          st_cluster_v4(mapa_u32(olo, r), plo);
+        }
+        fence_proxy_async_all();
+      }
+      tc_fence_before();
+    }
+    RW_STAMP(5);
+    if (s + 1 < steps) cluster_arrive_release();
+    RW_STAMP(6);
+    // ---- off the recurrence: sequence outputs, saved gates, next step's input projections ----
+    if (epi) {
+      st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
+      {
+        const long row = (long)blockIdx.y * 16 + nrow;            // batch row of the transposed vectors
+        const int k0 = (int)c * UC + 16 * q + 8 * oct;
+        __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                            ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
+        const int off = p16_in_tile((int)(row & 127), k0 & 63);
+        *reinterpret_cast<uint4*>(tl + off) = phi;
+        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
+      }
+      if (d.sv[0]) {
+        const long o = (long)u * d.sv_ld + (long)t * Bp + b0;
+        st8(d.sv[0] + o, sr);
+        st8(d.sv[1] + o, sz);
+        st8(d.sv[2] + o, sn);
+        st8(d.sv[3] + o, sg);
+      }
+      if (s + 1 < steps) {
+        const int tn = d.reverse ? t - 1 : t + 1;
+        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
+        ld8(gi_row + (long)u * d.gi_ld, gir);
+        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+      }
+    }
+    RW_STAMP(7);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// =================================================================================================
+// backward sweep (BPTT)
+// =================================================================================================
+// SUM: also accumulate the time sums of the input-gate gradients (decoders: the GRU input is z at every step).
+template <int NKC, bool SUM>
+__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqBwdArgs a) {
+  constexpr int H = 64 * NKC, UC = 16 * NKC;
+  constexpr int MT = NKC;                          // A tiles: 64 input units (hi + lo rows) each
+  constexpr int KS = 3 * NKC;                      // k-steps of 16 over the CTA's 3 UC gate rows
+  constexpr int NKB = (3 * UC + KCHUNK - 1) / KCHUNK;
+  constexpr int RSLOT = (4 * UC * 16 * 4 > NKB * RW_BTILE) ? 4 * UC * 16 * 4 : NKB * RW_BTILE;   // receive slot (also the operand)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                                             // [MT][NKB][RW_ATILE]
+  uint8_t* sR = smem + MT * NKB * RW_ATILE;                       // [2][RSLOT]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sR + 2 * RSLOT);
+  uint64_t* done = wbar + 1;                                      // [MT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 4);
+
+  const uint32_t c = cluster_ctarank();
+  const GruSeqDirBwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
+  const bool ew = warp < 4;                                       // element-wise warp (drains TMEM lane quarter q)
+  const bool epi = ew && q < NKC;                                 // ... that also owns 16 units of the slice
+  const long bpad = (long)a.tiles * 128;
+  const int steps = a.steps;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int m = 0; m < 4; ++m) mbar_init(&done[m], 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
+      mbar_expect_tx(wbar, MT * NKB * RW_ATILE);
+      for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+    }
+    __syncwarp();
+  }
+  cluster_arrive_release();
+  cluster_wait_acquire();
+
+  const int j = 16 * q + (lane & 15);
+  const int u = (int)c * UC + j;
+  const long b0 = (long)blockIdx.y * 16 + 8 * half;
+  const int nrow = 8 * half + (lane & 7);
+  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+
+  float carry[8];
+  float sum_r[SUM ? 8 : 1], sum_z[SUM ? 8 : 1], sum_n[SUM ? 8 : 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) carry[i] = 0.f;
+  if constexpr (SUM) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum_r[i] = sum_z[i] = sum_n[i] = 0.f;
+  }
+  float r[8], z[8], n[8], ghn[8], hp[8], dh[8];
+  auto load_step = [&](int s) {
+    const int t = d.reverse ? s : steps - 1 - s;
+    const bool first_fwd = d.reverse ? (t == steps - 1) : (t == 0);
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    const long so = (long)u * d.sv_ld + (long)t * bpad + b0;
+    ld8(d.sv[0] + so, r);
+    ld8(d.sv[1] + so, z);
+    ld8(d.sv[2] + so, n);
+    ld8(d.sv[3] + so, ghn);
+    if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
+    else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
+    if (d.dout) ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] = 0.f;
+    }
+  };
+  if (epi) {
+    if (d.dh_last) ld8(d.dh_last + (long)u * d.dh_last_ld + b0, carry);
+    load_step(0);
+  }
+
+  for (int s = 0; s < steps; ++s) {
+    const int t = d.reverse ? s : steps - 1 - s;
+    const uint32_t ph = s & 1;
+    uint8_t* rprev = sR + (ph ^ 1u) * RSLOT;                      // partial sums of step s - 1; then this step's operand
+    RW_STAMP(0);
+    if (s > 0) cluster_wait_acquire();                            // the partial sums of step s - 1 have landed
+    RW_STAMP(1);
+    float dar[8], daz[8], dan[8], dgn[8];
+    if (epi) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] += carry[i];
+      if (s > 0) {
+#pragma unroll
+        for (int src = 0; src < 4; ++src) {
+          float v[8];
+          ld8(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[i] += v[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dn = dh[i] * (1.0f - z[i]);
+        const float dz = dh[i] * (hp[i] - n[i]);
+        dan[i] = dn * (1.0f - n[i] * n[i]);
+        daz[i] = dz * z[i] * (1.0f - z[i]);
+        dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
+        dgn[i] = dan[i] * r[i];
+        carry[i] = dh[i] * z[i];
+        if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+      }
+    }
+    if (ew) epi_bar_sync();                                       // everyone has consumed rprev before it becomes the operand
+    uint4 rhi, rlo, zhi, zlo;
+    if (epi) {
+      uint4 ghi, glo;
+      rw_transpose_pack(dar, lane, rhi, rlo);
+      rw_transpose_pack(daz, lane, zhi, zlo);
+      rw_transpose_pack(dgn, lane, ghi, glo);
+      const int kq = 16 * q + 8 * oct;                            // operand k = gate * UC + unit inside the slice
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
+      fence_proxy_async_smem();
+    }
+    RW_STAMP(2);
+    __syncthreads();
+    if (warp == 4) {
+      if (lane == 0) {
+        if (s == 0) mbar_wait_b(wbar, 0);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
+            const uint32_t bo = (ks >> 2) * RW_BTILE + (ks & 3) * 2 * ATOM_BYTES;
+            if (ks == 0) umma_bf16_c<0>(tmem + m * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            else umma_bf16_c<1>(tmem + m * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+          }
+          umma_commit(&done[m]);
+        }
+        RW_STAMP_MMA(3);
+      }
+      __syncwarp();
+    }
+    // ---- outputs that do not need the MMA (weight-gradient GEMMs, dx of the layer below) ----
+    if (epi) {
+      const long o = (long)t * bpad + b0;
+      st8(d.dgi + (long)u * d.dg_ld + o, dar);
+      st8(d.dgi + (long)(H + u) * d.dg_ld + o, daz);
+      st8(d.dgi + (long)(2 * H + u) * d.dg_ld + o, dan);
+      st8(d.dgh + (long)u * d.dg_ld + o, dar);
+      st8(d.dgh + (long)(H + u) * d.dg_ld + o, daz);
+      st8(d.dgh + (long)(2 * H + u) * d.dg_ld + o, dgn);
+      if (d.dgi_p) {
+        uint4 nhi, nlo;
+        rw_transpose_pack(dan, lane, nhi, nlo);
+        constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+        const long row = (long)blockIdx.y * 16 + nrow;
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
+                              (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+        const int rr = (int)(row & 127);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int k = g * H + (int)c * UC + 16 * q + 8 * oct;
+          __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+          const int off = p16_in_tile(rr, k & 63);
+          *reinterpret_cast<uint4*>(tl + off) = g == 0 ? rhi : (g == 1 ? zhi : nhi);
+          *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = g == 0 ? rlo : (g == 1 ? zlo : nlo);
+        }
+      }
+    }
+    // ---- partial sums of dh_{t-1}: tile m / lane quarter q holds input units 64 m + 16 q .. + 15 -> push to their owner ----
+    if (ew) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mbar_wait_b(&done[m], ph);
+        tc_fence_after();
+        float part[8];
+        rw_reduce32(taddr + m * 32, half, part);
+        const int ui = 64 * m + 16 * q;                           // first input unit of this warp's lanes
+        const uint32_t owner = (uint32_t)(ui / UC);
+        const int ul = ui % UC + (lane & 15);
+        const uint32_t off = smem_u32(sR) + ph * RSLOT + (uint32_t)((((int)c * UC + ul) * 16 + 8 * half) * 4);
+        const uint32_t ra = mapa_u32(off, owner);
+        st_cluster_f4(ra, part[0], part[1], part[2], part[3]);
+        st_cluster_f4(ra + 16, part[4], part[5], part[6], part[7]);
+      }
+      tc_fence_before();
+    }
+    RW_STAMP(4);
+    cluster_arrive_release();
+    RW_STAMP(5);
+    if (epi && s + 1 < steps) load_step(s + 1);
+    RW_STAMP(6);
+  }
+  // gradient of the initial state: carry + the partial sums of the last step
+  cluster_wait_acquire();
+  if (epi) {
+    const uint8_t* rl = sR + ((steps - 1) & 1) * RSLOT;
+    float g0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g0[i] = carry[i];
+#pragma unroll
+    for (int src = 0; src < 4; ++src) {
+      float v[8];
+      ld8(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g0[i] += v[i];
+    }
+    st8(d.dh0_out + (long)u * bpad + b0, g0);
+    if constexpr (SUM) {
+      st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
+      st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
+      st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
+      constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+      const long row = (long)blockIdx.y * 16 + nrow;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+      const int rr = (int)(row & 127);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        uint4 hi, lo;
+        rw_transpose_pack(g == 0 ? sum_r : (g == 1 ? sum_z : sum_n), lane, hi, lo);
+        const int k = g * H + (int)c * UC + 16 * q + 8 * oct;
+        __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+        const int off = p16_in_tile(rr, k & 63);
+        *reinterpret_cast<uint4*>(tl + off) = hi;
+        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+bool rw_applicable(int H, int tiles) {
+  // one wave: 2 directions x (B_pad / 16) clusters x 4 CTAs must fit the SMs a cluster-of-4 launch can use (132 of 148)
+  return H >= 64 && H <= 256 && H % 64 == 0 && tiles >= 1 && tiles * 8 * 2 * 4 <= 132 * g_opt_rw_waves;
+}
+size_t rw_whh_bytes(int H) { return (size_t)4 * 3 * (H / 64) * RW_ATILE; }
+size_t rw_whhT_bytes(int H) {
+  const int UC = H / 4, nkb = (3 * UC + KCHUNK - 1) / KCHUNK;
+  return (size_t)4 * (H / 64) * nkb * RW_ATILE;
+}
+
+template <typename K, typename A>
+static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, cudaStream_t st) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(4, groups, ndir);
+  cfg.blockDim = dim3(RW_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
+  GruSeqFwdArgs a = a_in;
+  a.dbg = g_dbg_buffer;
+  const int nkc = a.H / 64, groups = a.tiles * 8;
+  const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
+  count_launch();
+  switch (nkc) {
+    case 1: rw_launch(gru_rw_fwd_kernel<1>, a, smem, groups, a.ndir, st); break;
+    case 2: rw_launch(gru_rw_fwd_kernel<2>, a, smem, groups, a.ndir, st); break;
+    case 3: rw_launch(gru_rw_fwd_kernel<3>, a, smem, groups, a.ndir, st); break;
+    default: rw_launch(gru_rw_fwd_kernel<4>, a, smem, groups, a.ndir, st); break;
+  }
+}
+
+template <bool SUM>
+static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
+  const int nkc = a.H / 64, groups = a.tiles * 8, UC = a.H / 4;
+  const int nkb = (3 * UC + KCHUNK - 1) / KCHUNK;
+  const size_t rslot = (size_t)(4 * UC * 16 * 4 > nkb * RW_BTILE ? 4 * UC * 16 * 4 : nkb * RW_BTILE);
+  const size_t smem = (size_t)nkc * nkb * RW_ATILE + 2 * rslot + 256;
+  switch (nkc) {
+    case 1: rw_launch(gru_rw_bwd_kernel<1, SUM>, a, smem, groups, a.ndir, st); break;
+    case 2: rw_launch(gru_rw_bwd_kernel<2, SUM>, a, smem, groups, a.ndir, st); break;
+    case 3: rw_launch(gru_rw_bwd_kernel<3, SUM>, a, smem, groups, a.ndir, st); break;
+    default: rw_launch(gru_rw_bwd_kernel<4, SUM>, a, smem, groups, a.ndir, st); break;
+  }
+}
+void launch_gru_rw_bwd(const GruSeqBwdArgs& a_in, cudaStream_t st) {
+  GruSeqBwdArgs a = a_in;
+  a.dbg = g_dbg_buffer;
+  count_launch();
+  if (a.d[0].dgi_sum) rw_launch_bwd<true>(a, st);
+  else rw_launch_bwd<false>(a, st);
+}
+
+unsigned int rw_timeouts() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_rw_timeouts, sizeof(v));
+  return v;
+}
+
+}  // namespace vb

@@ -17,6 +17,8 @@ extern int g_opt_m64;       // 1: recurrent kernels take 64 batch rows per CTA (
 extern int g_opt_slice16;   // 1: forward step kernels own 16 hidden units per CTA (twice the CTAs, N = 96 MMAs) when the sweep fits the GPU
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
+extern int g_opt_rw;         // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels (gru_rw.cu) when applicable
+extern int g_opt_rw_waves;   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 // ---- pack.cu -------------------------------------------------------------------------------------
@@ -26,7 +28,8 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
 // plain pack of a row-major [R_src, K] matrix that also accumulates rowsum[r] += sum_k src[r, k]
 void launch_pack_p16_rowsum(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st);
 
-// batched pack jobs (one launch): kind 0 = generic pack_p16, 1 / 2 = W_hh forward / backward slices (R = H), 3 = fused bias (R = H)
+// batched pack jobs (one launch): kind 0 = generic pack_p16, 1 / 2 = W_hh forward / backward slices (R = H), 3 = fused bias (R = H),
+// 4 / 5 = W_hh in the resident-weight forward / backward format of gru_rw.cu (R = H, H % 64 == 0)
 struct PackJob {
   const float* src; const float* src2; void* out;
   long ld;
@@ -105,6 +108,7 @@ void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
 // ---- persistent (whole-sweep) forward kernel: one thread-block cluster of H/32 CTAs per (batch tile, direction) ----
 struct GruSeqDirFwd {
   const void* w_p; const float* b_hn;
+  const void* w_rw;                                     // resident-weight format (pack kind 4), used by launch_gru_rw_fwd
   const float* gi; long gi_ld, gi_bs, gi_ts;
   const float* h0; long h0_ld; const void* h0_p;       // initial state: fp32 feature-major + P16
   float* out; long out_ld; int out_slots;               // fp32 h sequence, slot offset = slot*B_pad (slots = steps or 2)
@@ -115,12 +119,15 @@ struct GruSeqDirFwd {
 struct GruSeqFwdArgs {
   GruSeqDirFwd d[2];
   int ndir, H, tiles, steps;
+  unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
 };
 void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 
 // ---- persistent (whole-sweep) backward kernel, same cluster decomposition ----
 struct GruSeqDirBwd {
   const void* wT_p;
+  const void* wT_rw;                           // resident-weight format (pack kind 5), used by launch_gru_rw_bwd
+  float* dh0_out;                              // rw kernel only: gradient of the initial state, feature-major [H][B_pad]
   const float* dh_last; long dh_last_ld;       // gradient of the final hidden state, feature-major [H][ld], or nullptr
   const float* dout; long dout_ld;             // per-step output gradients, feature-major [H][dout_ld] (slot t at + t*B_pad) or nullptr
   const float* sv[4]; long sv_ld;              // saved gates r,z,n,ghn, [H][sv_ld]
@@ -140,6 +147,14 @@ struct GruSeqBwdArgs {
   unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
 };
 void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
+
+// ---- gru_rw.cu: resident-weight sweeps (4-CTA clusters, swap-AB, h / partial sums exchanged through DSMEM) ----
+bool rw_applicable(int H, int tiles);
+size_t rw_whh_bytes(int H);       // packed W_hh of one direction, forward format
+size_t rw_whhT_bytes(int H);      // ... backward format
+void launch_gru_rw_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
+void launch_gru_rw_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
+unsigned int rw_timeouts();       // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)
 
 struct GruDirBwd {
   const void* wT_p;       // P16 (RB=128) [H/32 slices][rb: H_pad/128][KC=2][2][128x64]: B[n=u, k=g*32+j] = W_hh[g*H+32c+j, u]

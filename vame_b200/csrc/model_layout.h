@@ -80,6 +80,8 @@ inline ParamLayout param_layout(const vame_dims& d) {
 struct GruPacked {
   void* whh_p[2];      // forward-step slices
   void* whhT_p[2];     // backward-step slices
+  void* whh_rw[2];     // resident-weight forward / backward formats of gru_rw.cu (nullptr when H % 64 != 0)
+  void* whhT_rw[2];
   void* wih_p[2];      // input projection B operand, K segments (encoder layer 1 has two: fwd / bwd halves of its input)
   int wih_nseg;
   void* wihT_p[2];     // per direction: [In rows, K = 3H] (for dx / dz)
@@ -101,6 +103,12 @@ inline void carve_gru_packed(Arena& A, GruPacked& g, int In, int H, int nseg) {
     g.whh_p[d] = A.raw(p16_bytes(3 * H, H, 96));
     g.whhT_p[d] = A.raw((size_t)(H / 32) * p16_bytes(H, 128, 128));
     g.wihT_p[d] = A.raw(p16_bytes(In, 3 * H, 128));
+    if (H % 64 == 0) {     // [4 CTAs][3 gates][H/64] and [4 CTAs][H/64][ceil(3H/4 / 64)] A tiles of 128 x 64 bf16
+      g.whh_rw[d] = A.raw((size_t)4 * 3 * (H / 64) * 16384);
+      g.whhT_rw[d] = A.raw((size_t)4 * (H / 64) * ((3 * (H / 4) + KCHUNK - 1) / KCHUNK) * 16384);
+    } else {
+      g.whh_rw[d] = g.whhT_rw[d] = nullptr;
+    }
   }
   g.wih_nseg = nseg;
   for (int s = 0; s < nseg; ++s) g.wih_p[s] = A.raw(p16_bytes(6 * H, In / nseg, 128));

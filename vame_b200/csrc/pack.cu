@@ -208,6 +208,43 @@ __device__ __forceinline__ void pack_whh_body(const float* __restrict__ w, int H
     }
   }
 }
+// W_hh [3H, H] -> resident-weight A tiles of gru_rw.cu (H % 64 == 0, UC = H/4 units per cluster CTA c).  A tile is 128 rows x
+// 64 k bf16 in the UMMA canonical K-major layout; tile row (= TMEM lane) L = 32 q + l carries the HI plane (l < 16) or the LO
+// plane (l >= 16) of one weight row.
+//   mode 0 (forward):  tiles [c][gate g][kc]; lane L <-> W_hh[g*H + c*UC + 16 q + (l & 15), :], zero if 16 q >= UC
+//   mode 1 (backward): tiles [c][m][kc], K = 3 UC (k = g*UC + j); lane L <-> input unit ui = 64 m + 16 q + (l & 15):
+//                      value(ui, k) = W_hh[g*H + c*UC + j, ui]
+__device__ __forceinline__ void pack_whh_rw_body(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out, long bid,
+                                                 long nb) {
+  const int NKC = H / 64, UC = H / 4;
+  const int NKB = (3 * UC + KCHUNK - 1) / KCHUNK;
+  const long ntiles = mode == 0 ? 4L * 3 * NKC : 4L * NKC * NKB;
+  const long total = ntiles * 128 * 8;
+  for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
+    const int k8 = (int)(idx & 7), L = (int)((idx >> 3) & 127);
+    const long tile = idx >> 10;
+    const int qq = L >> 5, l = L & 31, plane = l >> 4, jj = l & 15;
+    float v[8];
+    if (mode == 0) {
+      const int kc = (int)(tile % NKC), g = (int)((tile / NKC) % 3), c = (int)(tile / (3 * NKC));
+      const int j = 16 * qq + jj;
+      const long row = (long)g * H + c * UC + j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (j < UC) ? w[row * H + kc * KCHUNK + k8 * 8 + i] : 0.f;
+    } else {
+      const int kc = (int)(tile % NKB), m = (int)((tile / NKB) % NKC), c = (int)(tile / ((long)NKB * NKC));
+      const int ui = 64 * m + 16 * qq + jj;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc * KCHUNK + k8 * 8 + i;
+        v[i] = (k < 3 * UC) ? w[((long)(k / UC) * H + c * UC + (k % UC)) * H + ui] : 0.f;
+      }
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(out + (size_t)tile * (128 * KCHUNK) + p16_in_tile(L, k8 * 8)) = plane ? lo : hi;
+  }
+}
 __global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out) {
   pack_whh_body(w, H, mode, out, blockIdx.x, gridDim.x);
 }
@@ -243,6 +280,8 @@ __global__ void pack_jobs_kernel(const PackJobs jobs) {
     pack_p16_body(J.src, J.ld, J.transposed, J.R, J.K, J.R_src, J.K_src, nullptr, nullptr, J.RB, (__nv_bfloat16*)J.out, bid, nb);
   } else if (J.kind == 1 || J.kind == 2) {
     pack_whh_body(J.src, J.R, J.kind - 1, (__nv_bfloat16*)J.out, bid, nb);
+  } else if (J.kind == 4 || J.kind == 5) {
+    pack_whh_rw_body(J.src, J.R, J.kind - 4, (__nv_bfloat16*)J.out, bid, nb);
   } else {                                         // fused projection bias: out[i] = b_ih[i] + (i < 2H ? b_hh[i] : 0), R = H
     const int H = J.R;
     for (long i = bid * blockDim.x + threadIdx.x; i < 3L * H; i += nb * blockDim.x)
@@ -258,6 +297,7 @@ void launch_pack_jobs(PackJobs& jobs, cudaStream_t st) {
     if (J.kind == 0) work = (long)((J.R + J.RB - 1) / J.RB) * J.RB * ((J.K + KCHUNK - 1) / KCHUNK) * 8;
     else if (J.kind == 1) work = (long)(J.R / 32) * 96 * ((J.R + KCHUNK - 1) / KCHUNK) * 8;
     else if (J.kind == 2) work = (long)(J.R / 32) * ((J.R + 127) / 128) * 128 * 16;
+    else if (J.kind == 4 || J.kind == 5) work = 4L * 3 * (J.R / 64) * 128 * 8;
     else work = 3L * J.R;
     long nb = (work + 255) / 256;
     if (nb > 96) nb = 96;
