@@ -15,9 +15,10 @@ from tests.test_gpu_model import GRAD_TOL, OUT_TOL, check_step, make, rel  # noq
 def lib():
     from vame_b200 import _lib
     L = _lib.lib()
-    old = L.vame_get_option(b"rw")
+    old, old2 = L.vame_get_option(b"rw"), L.vame_get_option(b"rw2")
     yield L
     L.vame_set_option(b"rw", old)
+    L.vame_set_option(b"rw2", old2)
 
 
 def _step(eng, x, xf, eps, fut, B, Z):
@@ -29,14 +30,17 @@ def _step(eng, x, xf, eps, fut, B, Z):
     return {k: v.clone() for k, v in out.items()}, {k: v.clone() for k, v in eng.views(eng.grad).items()}
 
 
-@pytest.mark.parametrize("H,B,T,F,Z,S,fut", [
-    (64, 48, 12, 10, 8, 5, True),
-    (128, 130, 9, 7, 12, 4, True),       # ragged: 130 rows -> B_pad 256, 16 clusters per direction
-    (192, 32, 6, 5, 6, 0, False),
-    (256, 256, 30, 24, 30, 0, False),    # BASELINE configs[1]
-    (256, 96, 30, 24, 30, 15, True),     # decoder + future decoder sweeps side by side
+@pytest.mark.parametrize("H,B,T,F,Z,S,fut,rw2", [
+    (64, 48, 12, 10, 8, 5, True, 0),
+    (128, 130, 9, 7, 12, 4, True, 0),       # ragged: 130 rows -> B_pad 256, 16 clusters per direction
+    (192, 32, 6, 5, 6, 0, False, 0),
+    (256, 256, 30, 24, 30, 0, False, 0),    # BASELINE configs[1], cluster-barrier kernels
+    (256, 256, 30, 24, 30, 0, False, 1),    # BASELINE configs[1], barrier-free kernels (bulk-copy / mbarrier exchange)
+    (256, 96, 30, 24, 30, 15, True, 1),     # decoder + future decoder sweeps side by side
+    (256, 200, 3, 12, 30, 1, True, 1),      # very short sweeps (1 and 3 steps), ragged batch
 ])
-def test_rw_sweeps_vs_oracle_and_slice_kernels(lib, H, B, T, F, Z, S, fut):
+def test_rw_sweeps_vs_oracle_and_slice_kernels(lib, H, B, T, F, Z, S, fut, rw2):
+    lib.vame_set_option(b"rw2", rw2)
     port, eng = make(T, Z, F, fut, S, H)
     x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z)
     xf = xf[:, :S] if fut else xf

@@ -16,6 +16,17 @@ __device__ __forceinline__ uint64_t desc_generic(uint32_t saddr, uint32_t lbo, u
   return d;
 }
 
+// A operand from tensor memory (K = 16 bf16 = 8 columns per k-step)
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+
 template <int N>
 __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int iters, int mode, int same_k, int nacc, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -44,6 +55,18 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int iters, int mode, 
       }
       const uint32_t d1 = tmem + (nacc > 1 ? N : 0);
       t0 = clock64();
+      if (mode == 2) {                      // A from TMEM columns [256, 256 + 32), B no-swizzle from shared memory
+        const uint32_t ta = tmem + 256;
+        for (int ks = 0; ks < 4; ++ks) db[ks] = desc_generic(sb + ks * 256, 128, 1024, 0);
+        umma_bf16_ta<0>(tmem, ta, db[0], idesc);
+        umma_bf16_ta<0>(d1, ta, db[0], idesc);
+        for (int i = 0; i < iters; i += 4) {
+          umma_bf16_ta<1>(tmem, ta, db[0], idesc);
+          umma_bf16_ta<1>(d1, ta + 8, db[1], idesc);
+          umma_bf16_ta<1>(tmem, ta + 16, db[2], idesc);
+          umma_bf16_ta<1>(d1, ta + 24, db[3], idesc);
+        }
+      } else {
       umma_bf16_c<0>(tmem, da[0], db[0], idesc);
       umma_bf16_c<0>(d1, da[0], db[0], idesc);
       for (int i = 0; i < iters; i += 4) {
@@ -51,6 +74,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int iters, int mode, 
         umma_bf16_c<1>(d1, da[1], db[1], idesc);
         umma_bf16_c<1>(tmem, da[2], db[2], idesc);
         umma_bf16_c<1>(d1, da[3], db[3], idesc);
+      }
       }
       t1 = clock64();
       umma_commit(&done);
@@ -77,7 +101,7 @@ void run(int mode, int same_k, long long* d_out, int nacc = 1) {
     if (e != cudaSuccess) { printf("N=%d mode=%d: %s\n", N, mode, cudaGetErrorString(e)); return; }
   }
   cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("M=128 N=%3d K=16 %-13s %s nacc=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (ideal %d)\n", N, mode ? "SWIZZLE_128B" : "SWIZZLE_NONE",
+  printf("M=128 N=%3d K=16 %-13s %s nacc=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (ideal %d)\n", N, mode == 2 ? "A-from-TMEM" : mode ? "SWIZZLE_128B" : "SWIZZLE_NONE",
          same_k ? "same-k " : "k-sweep", nacc, (double)h[0] / iters, (double)h[1] / iters, 128 * N / 256);
 }
 
@@ -85,8 +109,10 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, 16);
   for (int nacc = 1; nacc <= 2; ++nacc)
-    for (int mode = 0; mode < 2; ++mode) {
+    for (int mode = 0; mode < 3; ++mode) {
+      run<16>(mode, 0, d_out, nacc);
       run<32>(mode, 0, d_out, nacc);
+      run<64>(mode, 0, d_out, nacc);
       run<48>(mode, 0, d_out, nacc);
       run<96>(mode, 0, d_out, nacc);
       run<128>(mode, 0, d_out, nacc);

@@ -16,6 +16,7 @@ int g_opt_flags = 0;           // measured: no gain (the gpu-scope publish costs
 int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps as persistent cluster kernels
 int g_opt_rw = 3;              // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels when applicable
 int g_opt_rw_waves = 1;
+int g_opt_rw2 = 1;
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -43,6 +44,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "m64") == 0) return vb::g_opt_m64;
   if (strcmp(name, "rw") == 0) return vb::g_opt_rw;
   if (strcmp(name, "rw_waves") == 0) return vb::g_opt_rw_waves;
+  if (strcmp(name, "rw2") == 0) return vb::g_opt_rw2;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
   return -1;
 }
@@ -79,6 +81,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "rw") == 0) {
     vb::g_opt_rw = value & 3;
+    return 0;
+  }
+  if (strcmp(name, "rw2") == 0) {
+    vb::g_opt_rw2 = value ? 1 : 0;
     return 0;
   }
   if (strcmp(name, "rw_waves") == 0) {

@@ -56,9 +56,16 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 }
 // a wait that cannot hang the GPU: a protocol bug shows up as a counted time-out (and wrong numbers), not as a dead box
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
-  for (int i = 0; i < (1 << 24); ++i)
+  for (int i = 0; i < (1 << 18); ++i) {
     if (mbar_try_wait(bar, parity)) return;
+    if ((i & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(&g_rw_timeouts) != 0) return;   // someone already gave up
+  }
   atomicAdd(&g_rw_timeouts, 1u);
+}
+// all lanes of a warp wait, then reconverge (tcgen05.ld is .sync.aligned)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  mbar_wait_b(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 element-wise warps
 
@@ -252,17 +259,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
     uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
     if (epi) {
       float ar[8], az[8], an[8];
-      mbar_wait_b(&done[0], ph);
+      mbar_wait_warp(&done[0], ph);
       tc_fence_after();
       rw_reduce32(taddr, half, ar);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
-      mbar_wait_b(&done[1], ph);
+      mbar_wait_warp(&done[1], ph);
       tc_fence_after();
       rw_reduce32(taddr + 32, half, az);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
-      mbar_wait_b(&done[2], ph);
+      mbar_wait_warp(&done[2], ph);
       tc_fence_after();
       RW_STAMP(3);
       rw_reduce32(taddr + 64, half, an);
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
     if (ew) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        mbar_wait_b(&done[m], ph);
+        mbar_wait_warp(&done[m], ph);
         tc_fence_after();
         float part[8];
         rw_reduce32(taddr + m * 32, half, part);
@@ -575,6 +582,526 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
 }
 
 // =================================================================================================
+// version 2 (H = 256 only: the CTA's unit slice is exactly one 64-wide k chunk of the operand)
+// =================================================================================================
+// Same decomposition, but the cluster never executes barrier.cluster inside the sweep:
+//  * forward: a CTA writes its slice of h_t (one contiguous 4 KB k chunk, hi and lo rows) into its OWN operand buffer with
+//    plain st.shared; the MMA lane then copies that chunk into the three peers' buffers with the TMA engine
+//    (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the peer's mbarrier) and immediately starts the MMAs of
+//    its own chunk; the MMAs over the peers' chunks follow when the peers' copies have landed.  The element-wise warps do
+//    the global stores of step t while the exchange and the MMAs of step t + 1 run.
+//  * backward: accumulator tiles are issued peers-first; each tile's partial sums are pushed (st.shared::cluster) as soon as
+//    that tile completes and announced with one remote mbarrier arrive per warp; the CTA's own tile stays in registers.
+// Ordering without the cluster barrier: a CTA can only be one step ahead of a peer (it needs the peer's data of step t
+// to finish step t + 1), which together with the double-buffered operand / receive slots rules out overwrites of live data.
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < (1 << 18); ++i) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    if ((i & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(&g_rw_timeouts) != 0) return;
+  }
+  atomicAdd(&g_rw_timeouts, 1u);
+}
+
+__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
+  constexpr int NKC = 4, H = 256, UC = 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
+  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [2][NKC][RW_BTILE]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + 2 * NKC * RW_BTILE);
+  uint64_t* done = wbar + 1;                                      // [3]: accumulator of gate g complete
+  uint64_t* lfull = done + 3;                                     // [2]: own chunk of operand buffer b written (128 arrivals)
+  uint64_t* hfull = lfull + 2;                                    // [2]: the three peers' chunks of buffer b have landed (tx bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hfull + 2);
+
+  const uint32_t c = cluster_ctarank();
+  const GruSeqDirFwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
+  const bool epi = warp < 4;
+  const long Bp = (long)a.tiles * 128;
+  const int steps = a.steps;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int g = 0; g < 3; ++g) mbar_init(&done[g], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&lfull[b], 128);
+      mbar_init(&hfull[b], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_rw) + (size_t)c * 3 * NKC * (RW_ATILE / 2);
+      mbar_expect_tx(wbar, 3 * NKC * RW_ATILE);
+      for (int i = 0; i < 3 * NKC; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+    }
+    __syncwarp();
+  }
+
+  const int j = 16 * (q & 3) + (lane & 15);
+  const int u = (int)c * UC + j;
+  const long b0 = (long)blockIdx.y * 16 + 8 * half;
+  const int nrow = 8 * half + (lane & 7);
+  const int kloc = 16 * (q & 3) + 8 * oct;                        // k inside the CTA's own chunk after the transpose
+  float hprev[8], bhn = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
+  if (epi) {
+    bhn = d.b_hn[u];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {                               // initial state: every CTA builds the whole operand itself
+      float v[8];
+      ld8(d.h0 + (long)(cc * UC + j) * d.h0_ld + b0, v);
+      if (cc == (int)c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hprev[i] = v[i];
+      }
+      uint4 hi, lo;
+      rw_transpose_pack(v, lane, hi, lo);
+      *reinterpret_cast<uint4*>(sH + rw_b_off(nrow, cc * UC + kloc)) = hi;
+      *reinterpret_cast<uint4*>(sH + rw_b_off(16 + nrow, cc * UC + kloc)) = lo;
+    }
+    fence_proxy_async_smem();
+  }
+  // arm the receive barriers of the first two exchanges (buffer 1 is filled for step 1, buffer 0 for step 2); later phases are
+  // armed right after the previous phase has been waited for, so a peer's complete_tx never precedes the expect_tx
+  if (tid == 0) {
+    if (steps > 1) mbar_expect_tx(&hfull[1], 3 * RW_BTILE);
+    if (steps > 2) mbar_expect_tx(&hfull[0], 3 * RW_BTILE);
+  }
+  // all mbarriers of the cluster are initialised (and the h0 operands written) before any remote signal is sent
+  cluster_arrive_release();
+  cluster_wait_acquire();
+
+  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+  float gir[8], giz[8], gin[8];
+  if (epi) {
+    const int t0 = d.reverse ? steps - 1 : 0;
+    const float* gi_row = d.gi + (b0 * d.gi_bs + (long)t0 * d.gi_ts);
+    ld8(gi_row + (long)u * d.gi_ld, gir);
+    ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+    ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+  }
+
+  for (int s = 0; s < steps; ++s) {
+    const int t = d.reverse ? steps - 1 - s : s;
+    const int so = (d.out_slots == steps) ? t : (s & 1);
+    const int sp = (d.out_p_slots == steps) ? t : (s & 1);
+    const uint32_t ph = s & 1, b = s & 1;
+    RW_STAMP(0);
+    if (warp == 4) {
+      if (lane == 0) {
+        const uint32_t hb = smem_u32(sH) + b * NKC * RW_BTILE;
+        if (s == 0) {
+          mbar_wait_b(wbar, 0);
+        } else {
+          const uint32_t par = ((s - 1) >> 1) & 1;
+          mbar_wait_b(&lfull[b], par);                          // own chunk of h_{t-1} written (and TMEM drained) by the 4 warps
+          RW_STAMP_MMA(8);
+          const uint32_t src = hb + c * RW_BTILE;
+#pragma unroll
+          for (uint32_t r = 1; r < 4; ++r) {
+            const uint32_t peer = (c + r) & 3;
+            bulk_s2c(mapa_u32(src, peer), src, RW_BTILE, mapa_u32(smem_u32(&hfull[b]), peer));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(hb);
+        // own chunk first (all three gates), then the peers' chunks gate by gate
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ao = (g * NKC + c) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = c * RW_BTILE + ks * 2 * ATOM_BYTES;
+            if (ks == 0) umma_bf16_c<0>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            else umma_bf16_c<1>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+          }
+        }
+        if (s > 0) {
+          mbar_wait_b(&hfull[b], ((s - 1) >> 1) & 1);
+          if (s + 2 < steps) mbar_expect_tx(&hfull[b], 3 * RW_BTILE);     // arm the next use of this buffer (step s + 2)
+        }
+        RW_STAMP_MMA(9);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+          for (uint32_t r = 1; r < 4; ++r) {
+            const uint32_t kc = (c + r) & 3;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * RW_BTILE + ks * 2 * ATOM_BYTES;
+              umma_bf16_c<1>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            }
+          }
+          umma_commit(&done[g]);
+        }
+        RW_STAMP_MMA(2);
+      }
+      __syncwarp();
+    } else {
+      float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
+      uint4 phi, plo;
+      mbar_wait_warp(&done[0], ph);
+      tc_fence_after();
+      rw_reduce32(taddr, half, ar);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
+      mbar_wait_warp(&done[1], ph);
+      tc_fence_after();
+      rw_reduce32(taddr + 32, half, az);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
+      mbar_wait_warp(&done[2], ph);
+      tc_fence_after();
+      RW_STAMP(3);
+      rw_reduce32(taddr + 64, half, an);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] = an[i] + bhn;
+        sn[i] = rw_tanh(gin[i] + sr[i] * sg[i]);
+        hn[i] = (1.0f - sz[i]) * sn[i] + sz[i] * hprev[i];
+        hprev[i] = hn[i];
+      }
+      RW_STAMP(4);
+      rw_transpose_pack(hn, lane, phi, plo);
+      tc_fence_before();
+      if (s + 1 < steps) {                                        // own chunk of operand buffer (s + 1) & 1, then tell the MMA lane
+        uint8_t* own = sH + (b ^ 1u) * NKC * RW_BTILE + c * RW_BTILE;
+        *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(nrow, kloc)) = phi;
+        *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(16 + nrow, kloc)) = plo;
+        fence_proxy_async_smem();
+        mbar_arrive(&lfull[b ^ 1u]);
+      }
+      RW_STAMP(5);
+      // ---- off the recurrence (overlaps the exchange and the next step's MMAs) ----
+      st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
+      {
+        const long row = (long)blockIdx.y * 16 + nrow;
+        const int k0 = (int)c * UC + kloc;
+        __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                            ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
+        const int off = p16_in_tile((int)(row & 127), k0 & 63);
+        *reinterpret_cast<uint4*>(tl + off) = phi;
+        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
+      }
+      if (d.sv[0]) {
+        const long o = (long)u * d.sv_ld + (long)t * Bp + b0;
+        st8(d.sv[0] + o, sr);
+        st8(d.sv[1] + o, sz);
+        st8(d.sv[2] + o, sn);
+        st8(d.sv[3] + o, sg);
+      }
+      if (s + 1 < steps) {
+        const int tn = d.reverse ? t - 1 : t + 1;
+        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
+        ld8(gi_row + (long)u * d.gi_ld, gir);
+        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+      }
+      RW_STAMP(7);
+    }
+  }
+  // no CTA leaves while a peer may still be reading its shared memory (outgoing bulk copies) or signalling its barriers
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+template <bool SUM>
+__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
+  constexpr int NKC = 4, H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
+  constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
+  static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                                             // [MT][NKB][RW_ATILE]
+  uint8_t* sR = smem + MT * NKB * RW_ATILE;                       // [2][RSLOT]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sR + 2 * RSLOT);
+  uint64_t* done = wbar + 1;                                      // [4] accumulator tiles, in issue order
+  uint64_t* ofull = done + 4;                                     // operand of this step written (128 arrivals)
+  uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x 4 warps have landed in slot b
+  uint64_t* mfree = pfull + 2;                                    // all MMAs of the 3 peers' current step are complete (3 x 4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfree + 1);
+
+  const uint32_t c = cluster_ctarank();
+  const GruSeqDirBwd& d = a.d[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
+  const bool epi = warp < 4;
+  const long bpad = (long)a.tiles * 128;
+  const int steps = a.steps;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int m = 0; m < 4; ++m) mbar_init(&done[m], 1);
+    mbar_init(ofull, 128);
+    mbar_init(&pfull[0], 12);
+    mbar_init(&pfull[1], 12);
+    mbar_init(mfree, 12);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
+      mbar_expect_tx(wbar, MT * NKB * RW_ATILE);
+      for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+    }
+    __syncwarp();
+  }
+  cluster_arrive_release();
+  cluster_wait_acquire();
+
+  const int j = 16 * (q & 3) + (lane & 15);
+  const int u = (int)c * UC + j;
+  const long b0 = (long)blockIdx.y * 16 + 8 * half;
+  const int nrow = 8 * half + (lane & 7);
+  const int kq = 16 * (q & 3) + 8 * oct;
+  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+
+  float carry[8], own[8];
+  float sum_r[SUM ? 8 : 1], sum_z[SUM ? 8 : 1], sum_n[SUM ? 8 : 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) carry[i] = own[i] = 0.f;
+  if constexpr (SUM) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum_r[i] = sum_z[i] = sum_n[i] = 0.f;
+  }
+  float r[8], z[8], n[8], ghn[8], hp[8], dh[8];
+  auto load_step = [&](int s) {
+    const int t = d.reverse ? s : steps - 1 - s;
+    const bool first_fwd = d.reverse ? (t == steps - 1) : (t == 0);
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    const long so = (long)u * d.sv_ld + (long)t * bpad + b0;
+    ld8(d.sv[0] + so, r);
+    ld8(d.sv[1] + so, z);
+    ld8(d.sv[2] + so, n);
+    ld8(d.sv[3] + so, ghn);
+    if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
+    else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
+    if (d.dout) ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] = 0.f;
+    }
+  };
+  if (epi) {
+    if (d.dh_last) ld8(d.dh_last + (long)u * d.dh_last_ld + b0, carry);
+    load_step(0);
+  }
+
+  for (int s = 0; s < steps; ++s) {
+    const int t = d.reverse ? s : steps - 1 - s;
+    const uint32_t ph = s & 1;
+    uint8_t* rprev = sR + (ph ^ 1u) * RSLOT;                      // partial sums of step s - 1; then this step's operand
+    RW_STAMP(0);
+    if (warp == 4) {
+      if (lane == 0) {
+        if (s == 0) mbar_wait_b(wbar, 0);
+        mbar_wait_b(ofull, ph);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {                        // peers' tiles first, the own tile last
+          const uint32_t m = (c + 1 + i) & 3;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
+            const uint32_t bo = (ks >> 2) * RW_BTILE + (ks & 3) * 2 * ATOM_BYTES;
+            if (ks == 0) umma_bf16_c<0>(tmem + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            else umma_bf16_c<1>(tmem + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+          }
+          umma_commit(&done[i]);
+        }
+        RW_STAMP_MMA(3);
+      }
+      __syncwarp();
+    } else {
+      float dar[8], daz[8], dan[8], dgn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] += carry[i] + own[i];
+      if (s > 0) {
+        mbar_wait_cluster_b(&pfull[ph ^ 1u], ((s - 1) >> 1) & 1);   // the peers' partial sums of step s - 1 have landed
+        __syncwarp();
+        RW_STAMP(1);
+#pragma unroll
+        for (int src = 0; src < 3; ++src) {
+          float v[8];
+          ld8(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dh[i] += v[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dn = dh[i] * (1.0f - z[i]);
+        const float dz = dh[i] * (hp[i] - n[i]);
+        dan[i] = dn * (1.0f - n[i] * n[i]);
+        daz[i] = dz * z[i] * (1.0f - z[i]);
+        dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
+        dgn[i] = dan[i] * r[i];
+        carry[i] = dh[i] * z[i];
+        if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+      }
+      epi_bar_sync();                                             // everyone has consumed rprev before it becomes the operand
+      uint4 rhi, rlo, zhi, zlo, ghi, glo;
+      rw_transpose_pack(dar, lane, rhi, rlo);
+      rw_transpose_pack(daz, lane, zhi, zlo);
+      rw_transpose_pack(dgn, lane, ghi, glo);
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
+      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ofull);
+      RW_STAMP(2);
+      // ---- while the MMAs run: next step's inputs, then this step's outputs ----
+      if (s + 1 < steps) load_step(s + 1);
+      {
+        const long o = (long)t * bpad + b0;
+        st8(d.dgi + (long)u * d.dg_ld + o, dar);
+        st8(d.dgi + (long)(H + u) * d.dg_ld + o, daz);
+        st8(d.dgi + (long)(2 * H + u) * d.dg_ld + o, dan);
+        st8(d.dgh + (long)u * d.dg_ld + o, dar);
+        st8(d.dgh + (long)(H + u) * d.dg_ld + o, daz);
+        st8(d.dgh + (long)(2 * H + u) * d.dg_ld + o, dgn);
+        if (d.dgi_p) {
+          uint4 nhi, nlo;
+          rw_transpose_pack(dan, lane, nhi, nlo);
+          constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+          const long row = (long)blockIdx.y * 16 + nrow;
+          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
+                                (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+          const int rr = (int)(row & 127);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const int k = g * H + (int)c * UC + kq;
+            __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+            const int off = p16_in_tile(rr, k & 63);
+            *reinterpret_cast<uint4*>(tl + off) = g == 0 ? rhi : (g == 1 ? zhi : nhi);
+            *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = g == 0 ? rlo : (g == 1 ? zlo : nlo);
+          }
+        }
+      }
+      // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i) {
+        mbar_wait_warp(&done[i], ph);
+        tc_fence_after();
+        float part[8];
+        rw_reduce32(taddr + i * 32, half, part);
+        if (i == 0 && s > 0) {
+          // the receive slot written below is the peers' operand of step s - 1: their MMAs of that step must be complete
+          // (signalled long ago - this wait only makes the ordering a guarantee instead of a timing margin)
+          mbar_wait_cluster_b(mfree, (s - 1) & 1);
+          __syncwarp();
+        }
+        if (i < 3) {
+          const uint32_t owner = (c + 1 + i) & 3;
+          const uint32_t slot = (c - owner - 1) & 3;             // = 2 - i: position of this CTA among the owner's three peers
+          const uint32_t off = smem_u32(sR) + ph * RSLOT + (uint32_t)(((slot * UC + j) * 16 + 8 * half) * 4);
+          const uint32_t ra = mapa_u32(off, owner);
+          st_cluster_f4(ra, part[0], part[1], part[2], part[3]);
+          st_cluster_f4(ra + 16, part[4], part[5], part[6], part[7]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&pfull[ph]), owner));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) own[k] = part[k];
+          // commits complete in order: every MMA of this step has finished reading the operand
+          if (lane == 0 && s + 1 < steps) {
+#pragma unroll
+            for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote(mapa_u32(smem_u32(mfree), (c + r) & 3));
+          }
+        }
+      }
+      tc_fence_before();
+      RW_STAMP(4);
+    }
+  }
+  // gradient of the initial state: carry + own tile + the peers' partial sums of the last step
+  if (epi) {
+    mbar_wait_cluster_b(&pfull[(steps - 1) & 1], ((steps - 1) >> 1) & 1);
+    __syncwarp();
+    const uint8_t* rl = sR + ((steps - 1) & 1) * RSLOT;
+    float g0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g0[i] = carry[i] + own[i];
+#pragma unroll
+    for (int src = 0; src < 3; ++src) {
+      float v[8];
+      ld8(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g0[i] += v[i];
+    }
+    st8(d.dh0_out + (long)u * bpad + b0, g0);
+    if constexpr (SUM) {
+      st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
+      st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
+      st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
+      constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+      const long row = (long)blockIdx.y * 16 + nrow;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+      const int rr = (int)(row & 127);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        uint4 hi, lo;
+        rw_transpose_pack(g == 0 ? sum_r : (g == 1 ? sum_z : sum_n), lane, hi, lo);
+        const int k = g * H + (int)c * UC + kq;
+        __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+        const int off = p16_in_tile(rr, k & 63);
+        *reinterpret_cast<uint4*>(tl + off) = hi;
+        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+      }
+    }
+  }
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+// =================================================================================================
 // launchers
 // =================================================================================================
 bool rw_applicable(int H, int tiles) {
@@ -611,6 +1138,10 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   const int nkc = a.H / 64, groups = a.tiles * 8;
   const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
   count_launch();
+  if (nkc == 4 && g_opt_rw2) {
+    rw_launch(gru_rw2_fwd_kernel, a, smem, groups, a.ndir, st);
+    return;
+  }
   switch (nkc) {
     case 1: rw_launch(gru_rw_fwd_kernel<1>, a, smem, groups, a.ndir, st); break;
     case 2: rw_launch(gru_rw_fwd_kernel<2>, a, smem, groups, a.ndir, st); break;
@@ -625,6 +1156,10 @@ static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const int nkb = (3 * UC + KCHUNK - 1) / KCHUNK;
   const size_t rslot = (size_t)(4 * UC * 16 * 4 > nkb * RW_BTILE ? 4 * UC * 16 * 4 : nkb * RW_BTILE);
   const size_t smem = (size_t)nkc * nkb * RW_ATILE + 2 * rslot + 256;
+  if (nkc == 4 && g_opt_rw2) {
+    rw_launch(gru_rw2_bwd_kernel<SUM>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
+    return;
+  }
   switch (nkc) {
     case 1: rw_launch(gru_rw_bwd_kernel<1, SUM>, a, smem, groups, a.ndir, st); break;
     case 2: rw_launch(gru_rw_bwd_kernel<2, SUM>, a, smem, groups, a.ndir, st); break;

@@ -18,6 +18,7 @@ extern int g_opt_slice16;   // 1: forward step kernels own 16 hidden units per C
 extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurrent sweeps as one persistent cluster kernel
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 extern int g_opt_rw;         // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels (gru_rw.cu) when applicable
+extern int g_opt_rw2;        // 1: H = 256 sweeps use the barrier-free rw kernels (bulk-copy / mbarrier exchange)
 extern int g_opt_rw_waves;   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
