@@ -46,7 +46,8 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
         ts.run()
     e1.record()
     torch.cuda.synchronize()
-    print("[%s pdl=%d] RESULT %s ms/step %.3f  windows/s %.0f" % (mode, pdl, workload, e0.elapsed_time(e1) / n, B * n / e0.elapsed_time(e1) * 1e3), flush=True)
+    print("[%s pdl=%d] RESULT %s ms/step %.3f  windows/s %.0f  rw_timeouts=%d info=%s" % (mode, pdl, workload, e0.elapsed_time(e1) / n, B * n / e0.elapsed_time(e1) * 1e3,
+          lib.vame_get_option(b"rw_timeouts"), [lib.vame_get_option(b"rw_timeout_info%d" % i) for i in range(6)]), flush=True)
     if mode == "eager":
         # per-phase breakdown with events
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -100,7 +101,7 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
         if lib.vame_get_option(b"rw") & 1:
             # rw forward kernel, step 10 of CTA 0: 0 loop top, 1 after cluster wait, 2 MMAs issued (MMA lane), 3 last gate's MMAs done,
             # 4 gate math done, 5 h pushed to the peers, 6 after cluster arrive, 7 global stores + next gi loads issued
-            print("[%s pdl=%d] rw fwd stamps (ns since loop top): %s" % (mode, pdl, [st[i] - st[0] for i in range(8)]), flush=True)
+            print("[%s pdl=%d] rw fwd stamps (ns since loop top): %s" % (mode, pdl, [st[i] - st[0] for i in range(12)]), flush=True)
         dbg.zero_()
         lib.vame_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
         lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 1, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
@@ -115,7 +116,8 @@ def child(mode, pdl, workload, streams=1, persistent=1, flags=1):
             # rw backward kernel, step 10 of CTA 0: 0 loop top, 1 after cluster wait, 2 gate gradients + operand written,
             # 3 MMAs issued (MMA lane), 4 partial sums pushed, 5 after cluster arrive, 6 next step's loads issued
             print("[%s pdl=%d] rw bwd stamps (ns since loop top): %s" % (mode, pdl, [st[i] - st[0] for i in range(7)]), flush=True)
-        print("[%s pdl=%d] rw=%d rw_timeouts=%d" % (mode, pdl, lib.vame_get_option(b"rw"), lib.vame_get_option(b"rw_timeouts")), flush=True)
+        print("[%s pdl=%d] rw=%d rw2=%d rw_timeouts=%d info=%s" % (mode, pdl, lib.vame_get_option(b"rw"), lib.vame_get_option(b"rw2"), lib.vame_get_option(b"rw_timeouts"),
+              [lib.vame_get_option(b"rw_timeout_info%d" % i) for i in range(6)]), flush=True)
         e0.record()
         for _ in range(20):
             lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, 0, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())

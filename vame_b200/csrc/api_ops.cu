@@ -17,6 +17,7 @@ int g_opt_persistent = 2;      // bit 0: forward sweeps, bit 1: backward sweeps 
 int g_opt_rw = 3;              // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels when applicable
 int g_opt_rw_waves = 1;
 int g_opt_rw2 = 1;
+int g_opt_rw_exp = 0;
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -46,6 +47,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "rw_waves") == 0) return vb::g_opt_rw_waves;
   if (strcmp(name, "rw2") == 0) return vb::g_opt_rw2;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
+  if (strncmp(name, "rw_timeout_info", 15) == 0) return vb::rw_timeout_info(name[15] ? name[15] - '0' : 0);
   return -1;
 }
 
@@ -81,6 +83,14 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "rw") == 0) {
     vb::g_opt_rw = value & 3;
+    return 0;
+  }
+  if (strcmp(name, "rw_timeouts_reset") == 0) {
+    vb::rw_timeouts_reset();
+    return 0;
+  }
+  if (strcmp(name, "rw_exp") == 0) {
+    vb::g_opt_rw_exp = value;
     return 0;
   }
   if (strcmp(name, "rw2") == 0) {

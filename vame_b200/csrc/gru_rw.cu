@@ -25,6 +25,7 @@
 namespace vb {
 
 __device__ unsigned int g_rw_timeouts = 0;     // bounded mbarrier waits that gave up (must stay 0; read by vame_debug_rw_timeouts)
+__device__ int g_rw_timeout_site[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // first time-out: site id, parity, blockIdx.x/y/z, threadIdx.x
 
 #ifdef VAME_ACCURATE_MATH
 __device__ __forceinline__ float rw_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -55,16 +56,23 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // a wait that cannot hang the GPU: a protocol bug shows up as a counted time-out (and wrong numbers), not as a dead box
-__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
-  for (int i = 0; i < (1 << 18); ++i) {
+__device__ __noinline__ void rw_timeout(int site, uint32_t parity) {
+  if (atomicAdd(&g_rw_timeouts, 1u) == 0) {
+    g_rw_timeout_site[0] = site; g_rw_timeout_site[1] = (int)parity;
+    g_rw_timeout_site[2] = blockIdx.x; g_rw_timeout_site[3] = blockIdx.y; g_rw_timeout_site[4] = blockIdx.z;
+    g_rw_timeout_site[5] = threadIdx.x;
+  }
+}
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int site = 0) {
+  for (int i = 0; i < (1 << 20); ++i) {
     if (mbar_try_wait(bar, parity)) return;
     if ((i & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(&g_rw_timeouts) != 0) return;   // someone already gave up
   }
-  atomicAdd(&g_rw_timeouts, 1u);
+  rw_timeout(site, parity);
 }
 // all lanes of a warp wait, then reconverge (tcgen05.ld is .sync.aligned)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  mbar_wait_b(bar, parity);
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int site = 0) {
+  mbar_wait_b(bar, parity, site);
   __syncwarp();
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 element-wise warps
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
     RW_STAMP(1);
     if (warp == 4) {
       if (lane == 0) {
-        if (s == 0) mbar_wait_b(wbar, 0);
+        if (s == 0) mbar_wait_b(wbar, 0, 1);
         fence_proxy_async_smem();
         tc_fence_after();
         const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(sH) + ph * NKC * RW_BTILE);
@@ -259,17 +267,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
     uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
     if (epi) {
       float ar[8], az[8], an[8];
-      mbar_wait_warp(&done[0], ph);
+      mbar_wait_warp(&done[0], ph, 2);
       tc_fence_after();
       rw_reduce32(taddr, half, ar);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
-      mbar_wait_warp(&done[1], ph);
+      mbar_wait_warp(&done[1], ph, 3);
       tc_fence_after();
       rw_reduce32(taddr + 32, half, az);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
-      mbar_wait_warp(&done[2], ph);
+      mbar_wait_warp(&done[2], ph, 4);
       tc_fence_after();
       RW_STAMP(3);
       rw_reduce32(taddr + 64, half, an);
@@ -300,6 +308,13 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
     RW_STAMP(6);
     // ---- off the recurrence: sequence outputs, saved gates, next step's input projections ----
     if (epi) {
+      if (s + 1 < steps) {                                        // loads first: the LSU works in order and the stores below are many
+        const int tn = d.reverse ? t - 1 : t + 1;
+        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
+        ld8(gi_row + (long)u * d.gi_ld, gir);
+        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+      }
       st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
       {
         const long row = (long)blockIdx.y * 16 + nrow;            // batch row of the transposed vectors
@@ -316,13 +331,6 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
         st8(d.sv[1] + o, sz);
         st8(d.sv[2] + o, sn);
         st8(d.sv[3] + o, sg);
-      }
-      if (s + 1 < steps) {
-        const int tn = d.reverse ? t - 1 : t + 1;
-        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
-        ld8(gi_row + (long)u * d.gi_ld, gir);
-        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
-        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
       }
     }
     RW_STAMP(7);
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
     __syncthreads();
     if (warp == 4) {
       if (lane == 0) {
-        if (s == 0) mbar_wait_b(wbar, 0);
+        if (s == 0) mbar_wait_b(wbar, 0, 1);
         fence_proxy_async_smem();
         tc_fence_after();
         const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
     if (ew) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        mbar_wait_warp(&done[m], ph);
+        mbar_wait_warp(&done[m], ph, 5);
         tc_fence_after();
         float part[8];
         rw_reduce32(taddr + m * 32, half, part);
@@ -585,18 +593,30 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
 // version 2 (H = 256 only: the CTA's unit slice is exactly one 64-wide k chunk of the operand)
 // =================================================================================================
 // Same decomposition, but the cluster never executes barrier.cluster inside the sweep:
-//  * forward: a CTA writes its slice of h_t (one contiguous 4 KB k chunk, hi and lo rows) into its OWN operand buffer with
-//    plain st.shared; the MMA lane then copies that chunk into the three peers' buffers with the TMA engine
-//    (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the peer's mbarrier) and immediately starts the MMAs of
-//    its own chunk; the MMAs over the peers' chunks follow when the peers' copies have landed.  The element-wise warps do
+//  * forward: a CTA writes its slice of h_t (one 4 KB k chunk, hi and lo rows) into its OWN operand buffer with plain
+//    st.shared and into the three peers' buffers with st.async (16-byte asynchronous DSMEM stores that complete tx-bytes on
+//    the peer's mbarrier: no release fence, no acknowledgement on the push path); the MMA lane starts the MMAs of its own
+//    chunk at once and issues the MMAs over the peers' chunks when their 12 KB have landed.  The element-wise warps do
 //    the global stores of step t while the exchange and the MMAs of step t + 1 run.
 //  * backward: accumulator tiles are issued peers-first; each tile's partial sums are pushed (st.shared::cluster) as soon as
-//    that tile completes and announced with one remote mbarrier arrive per warp; the CTA's own tile stays in registers.
+//    that tile completes, again with st.async + complete_tx on the owner's mbarrier; the CTA's own tile stays in registers.
 // Ordering without the cluster barrier: a CTA can only be one step ahead of a peer (it needs the peer's data of step t
 // to finish step t + 1), which together with the double-buffered operand / receive slots rules out overwrites of live data.
 __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
                "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+// asynchronous 16-byte store into a peer's shared memory that completes 16 tx-bytes on the peer's mbarrier: data and
+// signal travel together, the issuing thread never waits for an acknowledgement (no release fence on the push path)
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, const uint4& v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float a, float b, float c, float d, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar_cluster)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
@@ -613,12 +633,12 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t parity) {
-  for (int i = 0; i < (1 << 18); ++i) {
+__device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t parity, int site = 0) {
+  for (int i = 0; i < (1 << 20); ++i) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     if ((i & 1023) == 1023 && *reinterpret_cast<volatile unsigned int*>(&g_rw_timeouts) != 0) return;
   }
-  atomicAdd(&g_rw_timeouts, 1u);
+  rw_timeout(site, parity);
 }
 
 __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
@@ -720,17 +740,11 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
       if (lane == 0) {
         const uint32_t hb = smem_u32(sH) + b * NKC * RW_BTILE;
         if (s == 0) {
-          mbar_wait_b(wbar, 0);
+          mbar_wait_b(wbar, 0, 10);
         } else {
           const uint32_t par = ((s - 1) >> 1) & 1;
-          mbar_wait_b(&lfull[b], par);                          // own chunk of h_{t-1} written (and TMEM drained) by the 4 warps
+          mbar_wait_b(&lfull[b], par, 11);                          // own chunk of h_{t-1} written (and TMEM drained) by the 4 warps
           RW_STAMP_MMA(8);
-          const uint32_t src = hb + c * RW_BTILE;
-#pragma unroll
-          for (uint32_t r = 1; r < 4; ++r) {
-            const uint32_t peer = (c + r) & 3;
-            bulk_s2c(mapa_u32(src, peer), src, RW_BTILE, mapa_u32(smem_u32(&hfull[b]), peer));
-          }
         }
         fence_proxy_async_smem();
         tc_fence_after();
@@ -746,8 +760,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
           }
         }
         if (s > 0) {
-          mbar_wait_b(&hfull[b], ((s - 1) >> 1) & 1);
+          mbar_wait_b(&hfull[b], ((s - 1) >> 1) & 1, 12);
           if (s + 2 < steps) mbar_expect_tx(&hfull[b], 3 * RW_BTILE);     // arm the next use of this buffer (step s + 2)
+          fence_proxy_async_smem();                                 // the peers' chunks were written through the generic proxy
         }
         RW_STAMP_MMA(9);
 #pragma unroll
@@ -769,17 +784,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
     } else {
       float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
       uint4 phi, plo;
-      mbar_wait_warp(&done[0], ph);
+      mbar_wait_warp(&done[0], ph, 13);
       tc_fence_after();
       rw_reduce32(taddr, half, ar);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
-      mbar_wait_warp(&done[1], ph);
+      mbar_wait_warp(&done[1], ph, 14);
       tc_fence_after();
       rw_reduce32(taddr + 32, half, az);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
-      mbar_wait_warp(&done[2], ph);
+      mbar_wait_warp(&done[2], ph, 15);
       tc_fence_after();
       RW_STAMP(3);
       rw_reduce32(taddr + 64, half, an);
@@ -795,15 +810,30 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
       tc_fence_before();
       if (s + 1 < steps) {                                        // own chunk of operand buffer (s + 1) & 1, then tell the MMA lane
         uint8_t* own = sH + (b ^ 1u) * NKC * RW_BTILE + c * RW_BTILE;
+        const uint32_t ohi = smem_u32(own) + 2u * p16_in_tile(nrow, kloc), olo = smem_u32(own) + 2u * p16_in_tile(16 + nrow, kloc);
+        const uint32_t hbar = smem_u32(&hfull[b ^ 1u]);
+#pragma unroll
+        for (uint32_t r = 1; r < 4; ++r) {                          // the same chunk position in the three peers' buffers
+          const uint32_t peer = (c + r) & 3, pbar = mapa_u32(hbar, peer);
+          st_async_v4(mapa_u32(ohi, peer), phi, pbar);
+          st_async_v4(mapa_u32(olo, peer), plo, pbar);
+        }
         *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(nrow, kloc)) = phi;
         *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(16 + nrow, kloc)) = plo;
         fence_proxy_async_smem();
         mbar_arrive(&lfull[b ^ 1u]);
       }
       RW_STAMP(5);
-      // ---- off the recurrence (overlaps the exchange and the next step's MMAs) ----
-      st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
-      {
+      // ---- off the recurrence (overlaps the exchange and the next step's MMAs); loads first: the LSU works in order ----
+      if (s + 1 < steps && !(a.exp & 2)) {
+        const int tn = d.reverse ? t - 1 : t + 1;
+        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
+        ld8(gi_row + (long)u * d.gi_ld, gir);
+        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
+        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+      }
+      if (!(a.exp & 1)) st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
+      if (!(a.exp & 4)) {
         const long row = (long)blockIdx.y * 16 + nrow;
         const int k0 = (int)c * UC + kloc;
         __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
@@ -812,19 +842,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         *reinterpret_cast<uint4*>(tl + off) = phi;
         *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
       }
-      if (d.sv[0]) {
+      if (d.sv[0] && !(a.exp & 1)) {
         const long o = (long)u * d.sv_ld + (long)t * Bp + b0;
         st8(d.sv[0] + o, sr);
         st8(d.sv[1] + o, sz);
         st8(d.sv[2] + o, sn);
         st8(d.sv[3] + o, sg);
-      }
-      if (s + 1 < steps) {
-        const int tn = d.reverse ? t - 1 : t + 1;
-        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
-        ld8(gi_row + (long)u * d.gi_ld, gir);
-        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
-        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
       }
       RW_STAMP(7);
     }
@@ -849,8 +872,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
   uint64_t* done = wbar + 1;                                      // [4] accumulator tiles, in issue order
   uint64_t* ofull = done + 4;                                     // operand of this step written (128 arrivals)
   uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x 4 warps have landed in slot b
-  uint64_t* mfree = pfull + 2;                                    // all MMAs of the 3 peers' current step are complete (3 x 4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfree + 1);
+  uint64_t* mfree = pfull + 2;                                    // [2]: all MMAs of the 3 peers' step s are complete (3 x 4 warps), slot s & 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfree + 2);   //      (a peer may signal step s + 1 before this CTA has looked at step s)
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirBwd& d = a.d[blockIdx.z];
@@ -864,9 +887,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
     mbar_init(wbar, 1);
     for (int m = 0; m < 4; ++m) mbar_init(&done[m], 1);
     mbar_init(ofull, 128);
-    mbar_init(&pfull[0], 12);
-    mbar_init(&pfull[1], 12);
-    mbar_init(mfree, 12);
+    mbar_init(&pfull[0], 1);
+    mbar_init(&pfull[1], 1);
+    mbar_init(&mfree[0], 12);
+    mbar_init(&mfree[1], 12);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(tmem_slot, 128);
@@ -882,6 +906,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
     }
     __syncwarp();
+  }
+  // arm the receive barriers of the first two steps' pushes (3 peers x 64 units x 16 rows x 4 B); later phases are armed by
+  // thread 0 right after it has consumed the previous phase of the same slot, i.e. before any peer can push into it again
+  if (tid == 0) {
+    mbar_expect_tx(&pfull[0], RSLOT);
+    if (steps > 1) mbar_expect_tx(&pfull[1], RSLOT);
   }
   cluster_arrive_release();
   cluster_wait_acquire();
@@ -932,8 +962,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
     RW_STAMP(0);
     if (warp == 4) {
       if (lane == 0) {
-        if (s == 0) mbar_wait_b(wbar, 0);
-        mbar_wait_b(ofull, ph);
+        if (s == 0) mbar_wait_b(wbar, 0, 20);
+        mbar_wait_b(ofull, ph, 21);
         fence_proxy_async_smem();
         tc_fence_after();
         const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
@@ -957,7 +987,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] += carry[i] + own[i];
       if (s > 0) {
-        mbar_wait_cluster_b(&pfull[ph ^ 1u], ((s - 1) >> 1) & 1);   // the peers' partial sums of step s - 1 have landed
+        mbar_wait_cluster_b(&pfull[ph ^ 1u], ((s - 1) >> 1) & 1, 22);   // the peers' partial sums of step s - 1 have landed
+        if (tid == 0 && s + 1 < steps) mbar_expect_tx(&pfull[ph ^ 1u], RSLOT);   // arm it for the pushes of step s + 1
         __syncwarp();
         RW_STAMP(1);
 #pragma unroll
@@ -994,8 +1025,42 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       tc_fence_before();
       mbar_arrive(ofull);
       RW_STAMP(2);
-      // ---- while the MMAs run: next step's inputs, then this step's outputs ----
+      // ---- while the MMAs run: next step's inputs ----
       if (s + 1 < steps) load_step(s + 1);
+      // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i) {
+        mbar_wait_warp(&done[i], ph, 24);
+        tc_fence_after();
+        float part[8];
+        rw_reduce32(taddr + i * 32, half, part);
+        if (i == 0 && s > 0) {
+          // the receive slot written below is the peers' operand of step s - 1: their MMAs of that step must be complete
+          // (signalled long ago - this wait only makes the ordering a guarantee instead of a timing margin)
+          mbar_wait_cluster_b(&mfree[ph ^ 1u], ((s - 1) >> 1) & 1, 23);
+          __syncwarp();
+        }
+        if (i < 3) {
+          const uint32_t owner = (c + 1 + i) & 3;
+          const uint32_t slot = (c - owner - 1) & 3;             // = 2 - i: position of this CTA among the owner's three peers
+          const uint32_t off = smem_u32(sR) + ph * RSLOT + (uint32_t)(((slot * UC + j) * 16 + 8 * half) * 4);
+          const uint32_t ra = mapa_u32(off, owner), pbar = mapa_u32(smem_u32(&pfull[ph]), owner);
+          st_async_f4(ra, part[0], part[1], part[2], part[3], pbar);
+          st_async_f4(ra + 16, part[4], part[5], part[6], part[7], pbar);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) own[k] = part[k];
+          // commits complete in order: every MMA of this step has finished reading the operand
+          if (lane == 0 && s + 1 < steps) {
+#pragma unroll
+            for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
+          }
+        }
+      }
+      tc_fence_before();
+      RW_STAMP(4);
+      // ---- this step's outputs (weight-gradient GEMMs, dx of the layer below): after the pushes, because a release at
+      //      cluster scope waits for every earlier store of the thread ----
       {
         const long o = (long)t * bpad + b0;
         st8(d.dgi + (long)u * d.dg_ld + o, dar);
@@ -1022,45 +1087,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
           }
         }
       }
-      // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
-#pragma unroll
-      for (uint32_t i = 0; i < 4; ++i) {
-        mbar_wait_warp(&done[i], ph);
-        tc_fence_after();
-        float part[8];
-        rw_reduce32(taddr + i * 32, half, part);
-        if (i == 0 && s > 0) {
-          // the receive slot written below is the peers' operand of step s - 1: their MMAs of that step must be complete
-          // (signalled long ago - this wait only makes the ordering a guarantee instead of a timing margin)
-          mbar_wait_cluster_b(mfree, (s - 1) & 1);
-          __syncwarp();
-        }
-        if (i < 3) {
-          const uint32_t owner = (c + 1 + i) & 3;
-          const uint32_t slot = (c - owner - 1) & 3;             // = 2 - i: position of this CTA among the owner's three peers
-          const uint32_t off = smem_u32(sR) + ph * RSLOT + (uint32_t)(((slot * UC + j) * 16 + 8 * half) * 4);
-          const uint32_t ra = mapa_u32(off, owner);
-          st_cluster_f4(ra, part[0], part[1], part[2], part[3]);
-          st_cluster_f4(ra + 16, part[4], part[5], part[6], part[7]);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&pfull[ph]), owner));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) own[k] = part[k];
-          // commits complete in order: every MMA of this step has finished reading the operand
-          if (lane == 0 && s + 1 < steps) {
-#pragma unroll
-            for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote(mapa_u32(smem_u32(mfree), (c + r) & 3));
-          }
-        }
-      }
-      tc_fence_before();
-      RW_STAMP(4);
+      RW_STAMP(5);
     }
   }
   // gradient of the initial state: carry + own tile + the peers' partial sums of the last step
   if (epi) {
-    mbar_wait_cluster_b(&pfull[(steps - 1) & 1], ((steps - 1) >> 1) & 1);
+    mbar_wait_cluster_b(&pfull[(steps - 1) & 1], ((steps - 1) >> 1) & 1, 25);
     __syncwarp();
     const uint8_t* rl = sR + ((steps - 1) & 1) * RSLOT;
     float g0[8];
@@ -1135,6 +1167,7 @@ static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, c
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   GruSeqFwdArgs a = a_in;
   a.dbg = g_dbg_buffer;
+  a.exp = g_opt_rw_exp;
   const int nkc = a.H / 64, groups = a.tiles * 8;
   const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
   count_launch();
@@ -1179,6 +1212,15 @@ unsigned int rw_timeouts() {
   unsigned int v = 0;
   cudaMemcpyFromSymbol(&v, g_rw_timeouts, sizeof(v));
   return v;
+}
+int rw_timeout_info(int i) {
+  int v[8];
+  cudaMemcpyFromSymbol(v, g_rw_timeout_site, sizeof(v));
+  return v[i & 7];
+}
+void rw_timeouts_reset() {
+  unsigned int z = 0;
+  cudaMemcpyToSymbol(g_rw_timeouts, &z, sizeof(z));
 }
 
 }  // namespace vb

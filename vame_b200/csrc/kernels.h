@@ -19,7 +19,8 @@ extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurr
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 extern int g_opt_rw;         // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels (gru_rw.cu) when applicable
 extern int g_opt_rw2;        // 1: H = 256 sweeps use the barrier-free rw kernels (bulk-copy / mbarrier exchange)
-extern int g_opt_rw_waves;   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
+extern int g_opt_rw_waves;
+extern int g_opt_rw_exp;      // measurement experiments (wrong results), see GruSeqFwdArgs::exp   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 // ---- pack.cu -------------------------------------------------------------------------------------
@@ -121,6 +122,7 @@ struct GruSeqFwdArgs {
   GruSeqDirFwd d[2];
   int ndir, H, tiles, steps;
   unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
+  int exp;                   // measurement experiments only (option "rw_exp", results become wrong): skip stores / loads
 };
 void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 
@@ -155,7 +157,9 @@ size_t rw_whh_bytes(int H);       // packed W_hh of one direction, forward forma
 size_t rw_whhT_bytes(int H);      // ... backward format
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 void launch_gru_rw_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
-unsigned int rw_timeouts();       // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)
+unsigned int rw_timeouts();
+int rw_timeout_info(int i);        // first time-out: 0 site id, 1 parity, 2-4 blockIdx, 5 threadIdx.x
+void rw_timeouts_reset();       // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)
 
 struct GruDirBwd {
   const void* wT_p;       // P16 (RB=128) [H/32 slices][rb: H_pad/128][KC=2][2][128x64]: B[n=u, k=g*32+j] = W_hh[g*H+32c+j, u]
