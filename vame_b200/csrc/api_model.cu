@@ -24,6 +24,8 @@ struct GruBuf {
   float* dgi[2]; float* dgh[2]; void* dgi_p[2];
   float* parts[2];
   int parts_n;                          // partial-sum slots that hold the final dh0 after the last backward sweep (1 after an rw sweep)
+  bool priv;                            // training sweeps use the private interchange layouts of the H = 256 rw kernels (kernels.h)
+  float* hfin[2];                       // priv: final hidden state, fp32 feature-major [H][B_pad]
   void* dghT_p[2]; void* dgiT_p[2]; void* outT_p[2]; void* h0T_p[2];
   unsigned int* flags;                  // [2 dirs][steps][tiles] hand-over counters of the per-step kernels
 };
@@ -70,6 +72,7 @@ static void carve_gru(Arena& A, GruBuf& g, int steps, int H, int In, int B_pad, 
   const size_t slotp = (size_t)tiles * nkc * p16_tile_bytes(128);
   const long rows = (long)steps * B_pad;
   g.steps = steps; g.H = H; g.In = In;
+  g.priv = training && rw_priv_mode(H, tiles);
   if (gi_full) {
     g.gi = A.f32((size_t)rows * 6 * H);
     g.gi_bs = 1; g.gi_ts = B_pad; g.gi_ld = rows;
@@ -88,6 +91,7 @@ static void carve_gru(Arena& A, GruBuf& g, int steps, int H, int In, int B_pad, 
       g.h0_p[d] = A.raw(slotp);
     }
     if (training) {
+      g.hfin[d] = A.f32(slotf);
       for (int i = 0; i < 4; ++i) g.sv[d][i] = A.f32(slotf * steps);
       g.dgi[d] = A.f32((size_t)rows * 3 * H);
       g.dgh[d] = A.f32((size_t)rows * 3 * H);
@@ -366,6 +370,9 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
       for (int i = 0; i < 4; ++i) D.sv[i] = save ? L.sv[d][i] : nullptr;
       D.sv_ld = (long)L.steps * Bp;
       D.reverse = d;
+      D.priv = (rw && save && L.priv) ? 1 : 0;
+      D.outT_p = L.outT_p[d]; D.outT_nk = (long)L.steps * Bp / KCHUNK;
+      D.hfin = L.hfin[d];
     }
     if (rw) launch_gru_rw_fwd(a, st);
     else launch_gru_seq_fwd(a, st);
@@ -420,11 +427,12 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
 }
 // location of the final hidden state of direction d after a forward sweep
 static inline const float* final_h(const GruBuf& L, int d, int tiles) {      // feature-major, ld = final_h_ld()
+  if (L.priv) return L.hfin[d];
   const int t = d == 0 ? L.steps - 1 : 0;
   const int so = (L.out_slots == L.steps) ? t : ((L.steps - 1) & 1);
   return L.out[d] + (size_t)so * tiles * 128;
 }
-static inline long final_h_ld(const GruBuf& L, int tiles) { return (long)L.out_slots * tiles * 128; }
+static inline long final_h_ld(const GruBuf& L, int tiles) { return L.priv ? (long)tiles * 128 : (long)L.out_slots * tiles * 128; }
 static inline const void* final_h_p(const GruBuf& L, int d, int tiles) {
   const size_t slotp = (size_t)tiles * nkc_of(L.H) * p16_tile_elems(128);
   const int t = d == 0 ? L.steps - 1 : 0;
@@ -438,7 +446,8 @@ static int g_bwd_concurrent = 1;     // backward sweeps that run side by side (2
 // dgi_sum / dgi_sum_p (optional, per direction): time sums of dgi written by the persistent kernel; returns true if they were produced
 static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float* dout0, const float* dout1, long dout_ld,
                           const float* dhl0, const float* dhl1, long dhl_ld, bool pdl, cudaStream_t st,
-                          float* const* dgi_sum = nullptr, void* const* dgi_sum_p = nullptr) {
+                          float* const* dgi_sum = nullptr, void* const* dgi_sum_p = nullptr, const GruOff* goff = nullptr,
+                          float* G = nullptr) {
   const int H = L.H, nsl = H / 32, nkc3 = nkc_of(3 * H);
   const long Bp = (long)tiles * 128;
   const size_t slotf = (size_t)Bp * H;
@@ -465,6 +474,9 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
       D.parts = L.parts[d];
       D.dgi = L.dgi[d]; D.dgh = L.dgh[d]; D.dg_ld = seq_ld;
       D.dgi_p = L.dgi_p[d]; D.dgi_p_slot_elems = (long)tiles * nkc3 * (long)p16_tile_elems(128);
+      D.priv = (rw && L.priv && goff && G) ? 1 : 0;
+      D.dghT_p = L.dghT_p[d]; D.dgiT_p = L.dgiT_p[d]; D.gT_nk = seq_ld / KCHUNK;
+      D.db_ih = G ? G + goff->bih[d] : nullptr; D.db_hh = G ? G + goff->bhh[d] : nullptr;
       D.dgi_sum = dgi_sum ? dgi_sum[d] : nullptr;
       D.dgi_sum_p = dgi_sum ? dgi_sum_p[d] : nullptr;
       if (dgi_sum && ((3 * H) % KCHUNK) != 0) cudaMemsetAsync(dgi_sum_p[d], 0, (size_t)tiles * nkc3 * p16_tile_bytes(128), st);
@@ -526,6 +538,7 @@ static inline const float* final_parts(const GruBuf& L, int d, int tiles) {
 //   dW_hh[d] = dgh[d]^T hprev[d],  db_hh[d] = colsum(dgh[d]),  db_ih[d] = colsum(dgi[d])
 static void pack_outT(GruBuf& L, int Bp, cudaStream_t st) {      // forward activations only: can run any time after the forward
   const long rows = (long)L.steps * Bp;
+  if (L.priv) return;                                                 // written by the forward sweep itself
   for (int d = 0; d < 2; ++d) pack_rows(L.out[d], rows, L.H, (int)rows, L.H, L.outT_p[d], st);   // out is already [H][rows]
 }
 // dgi_rowsum_fused: the caller packs dgi (encoder layers) and lets that pass produce db_ih
@@ -537,7 +550,7 @@ static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* 
   for (int d = 0; d < 2; ++d) {
     cudaStream_t st = (d == 1 && st1) ? st1 : st0;           // the two directions are independent
     // dgh is already [3H][rows]; its row sums (= db_hh) are accumulated by the same pass
-    launch_pack_p16_rowsum(L.dgh[d], rows, 3 * H, (int)rows, 3 * H, L.dghT_p[d], G + o.bhh[d], st);
+    if (!L.priv) launch_pack_p16_rowsum(L.dgh[d], rows, 3 * H, (int)rows, 3 * H, L.dghT_p[d], G + o.bhh[d], st);   // priv: by the sweep
     const void* h0T = d == 0 ? h0T0 : h0T1;
     GemmB gb;
     gb.A(L.dghT_p[d], nk, nk);
@@ -550,7 +563,7 @@ static void gru_recurrent_grads(const GruOff& o, GruBuf& L, int Bp, const void* 
       gb.Bm(h0T, cB, cB);
     }
     gb.run(3 * H, H, G + o.whh[d], H, nullptr, 1, splits_for(3 * H, H, nk), st);
-    if (!dgi_rowsum_fused) launch_rowsum_fm(L.dgi[d], rows, rows, 3 * H, G + o.bih[d], st);
+    if (!dgi_rowsum_fused && !L.priv) launch_rowsum_fm(L.dgi[d], rows, rows, 3 * H, G + o.bih[d], st);
   }
 }
 
@@ -844,7 +857,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     }
     g_bwd_concurrent = (ndec == 2 && g_opt_streams) ? 2 : 1;
     const bool have_sums = gru_sweep_bwd(Wg, D.g, w.tiles, D.ddec, D.ddec + (size_t)Hd * rows, rows, nullptr, nullptr, 0, true, sd,
-                                         D.dgi_sum, D.dgi_sum_p);
+                                         D.dgi_sum, D.dgi_sum_p, &o, G);
     g_bwd_concurrent = 1;
     if (i == 0) mark(st, "bwd:dec sweep");
     edge(sd, sw);                            // recurrent weight gradients start as soon as the sweep is done (beside the dz chain)
@@ -916,7 +929,8 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   // ---- encoder layer 1 (only h_n is used downstream, rnn_model.py:41-43: no per-step output gradient)
   const long rows = (long)T * Bp;
   const int nk = (int)(rows / KCHUNK), nkc3 = nkc_of(3 * H);
-  gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * Bp, w.dhidden + (size_t)3 * H * Bp, Bp, true, st);
+  gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * Bp, w.dhidden + (size_t)3 * H * Bp, Bp, true, st,
+                nullptr, nullptr, &L.e1, G);
   mark(st, "bwd:L1 sweep");
   // the weight gradients of the two directions are independent: one side stream each (their fixed per-kernel costs overlap)
   cudaStream_t sC = g_opt_streams ? side().s[3] : st;
@@ -929,7 +943,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
       .run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
   gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
-    launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sdir[dd]);
+    if (!w.e1.priv) launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sdir[dd]);
     for (int e = 0; e < 2; ++e)
       GemmB().A(w.e1.dgiT_p[dd], nk, nk).Bm(w.e0.outT_p[e], nk, nk)
           .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sdir[dd]);
@@ -937,13 +951,14 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   mark(sB, "side:L1 weight grads done");
   // ---- encoder layer 0
   mark(st, "bwd:dx1 gemm");
-  gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st);
+  gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st,
+                nullptr, nullptr, &L.e0, G);
   edge(st, sB);
   edge(st, sC);
   g_side_sms = g_opt_streams ? 74 : 148;     // nothing else runs beside the last block: half of the GPU per direction
   gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
-    launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sdir[dd]);
+    if (!w.e0.priv) launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sdir[dd]);
     GemmB().A(w.e0.dgiT_p[dd], nk, nk).Bm(w.xT_p, nk, nk)
         .run(3 * H, F, G + L.e0.wih[dd], F, nullptr, 1, splits_for(3 * H, F, nk), sdir[dd]);
   }
@@ -979,7 +994,8 @@ int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* 
   for (int dd = 0; dd < 2; ++dd) { w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p; }
   cudaStream_t st = (cudaStream_t)stream;
   if (which == 0) gru_sweep_fwd(W.e1, params + L.e1.bhh[0] + 2 * H, params + L.e1.bhh[1] + 2 * H, w.e1, w.tiles, true, true, st);
-  else gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * w.B_pad, w.dhidden + (size_t)3 * H * w.B_pad, w.B_pad, true, st);
+  else gru_sweep_bwd(W.e1, w.e1, w.tiles, nullptr, nullptr, 0, w.dhidden + (size_t)2 * H * w.B_pad, w.dhidden + (size_t)3 * H * w.B_pad, w.B_pad, true, st,
+                     nullptr, nullptr, &L.e1, w.dx1 /* scratch target of the bias-gradient sums (timing only) */);
   return check_launch("vame_debug_gru_sweep");
 }
 

@@ -619,6 +619,26 @@ __device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float a, float
                "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar_cluster)
                : "memory");
 }
+// private lane-major interchange layout of the H = 256 kernels: per (t, 16-row group g, CTA c, warp q) one 1 KB block
+// [k: 2][lane: 32][4 floats] holding values 4 k .. 4 k + 3 of every lane -> a warp instruction moves 512 contiguous bytes
+__device__ __forceinline__ long pv_block(long t, long groups, long g, uint32_t c, int q) { return (((t * groups + g) * 4 + c) * 4 + (q & 3)) * 256; }
+__device__ __forceinline__ void ld8p(const float* blk, int lane, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(blk + lane * 4), b = *reinterpret_cast<const float4*>(blk + 128 + lane * 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8p(float* blk, int lane, const float* v) {
+  *reinterpret_cast<float4*>(blk + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(blk + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// 8 consecutive k (= batch rows) of row `row` of a transposed P16 operand [rows, K]: one atom row per plane
+__device__ __forceinline__ void st8_T_p16(void* base, long nk, int row, long k, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(base) + ((size_t)(row >> 7) * nk + (k >> 6)) * p16_tile_elems(128);
+  const int off = p16_in_tile(row & 127, (int)(k & 63));
+  *reinterpret_cast<uint4*>(tl + off) = hi;
+  *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
@@ -641,6 +661,7 @@ __device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t pari
   rw_timeout(site, parity);
 }
 
+template <bool PRIV>
 __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
   constexpr int NKC = 4, H = 256, UC = 64;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -721,6 +742,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
 
   const uint32_t idesc = make_idesc_bf16(128, 32);
   const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+  const long groups = Bp / 16;
+  const bool gi_const = d.gi_ts == 0;                              // decoders: the input projection does not depend on t
   float gir[8], giz[8], gin[8];
   if (epi) {
     const int t0 = d.reverse ? steps - 1 : 0;
@@ -825,14 +848,25 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
       }
       RW_STAMP(5);
       // ---- off the recurrence (overlaps the exchange and the next step's MMAs); loads first: the LSU works in order ----
-      if (s + 1 < steps && !(a.exp & 2)) {
+      if (s + 1 < steps && !gi_const && !(a.exp & 2)) {
         const int tn = d.reverse ? t - 1 : t + 1;
         const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
         ld8(gi_row + (long)u * d.gi_ld, gir);
         ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
         ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
       }
-      if (!(a.exp & 1)) st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
+      if constexpr (PRIV) {
+        const long blk = pv_block(t, groups, blockIdx.y, c, q);
+        st8p(d.out + blk, lane, hn);
+        st8p(d.sv[0] + blk, lane, sr);
+        st8p(d.sv[1] + blk, lane, sz);
+        st8p(d.sv[2] + blk, lane, sn);
+        st8p(d.sv[3] + blk, lane, sg);
+        st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + b0, hn);
+        if (s + 1 == steps) st8(d.hfin + (long)u * Bp + b0, hn);
+      } else if (!(a.exp & 1)) {
+        st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
+      }
       if (!(a.exp & 4)) {
         const long row = (long)blockIdx.y * 16 + nrow;
         const int k0 = (int)c * UC + kloc;
@@ -842,7 +876,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         *reinterpret_cast<uint4*>(tl + off) = phi;
         *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
       }
-      if (d.sv[0] && !(a.exp & 1)) {
+      if (!PRIV && d.sv[0] && !(a.exp & 1)) {
         const long o = (long)u * d.sv_ld + (long)t * Bp + b0;
         st8(d.sv[0] + o, sr);
         st8(d.sv[1] + o, sz);
@@ -860,7 +894,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
   if (warp == 4) tmem_dealloc(tmem, 128);
 }
 
-template <bool SUM>
+template <bool SUM, bool PRIV>
 __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
   constexpr int NKC = 4, H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
   constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
@@ -926,6 +960,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
 
   float carry[8], own[8];
   float sum_r[SUM ? 8 : 1], sum_z[SUM ? 8 : 1], sum_n[SUM ? 8 : 1];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};                            // PRIV: bias gradients = sums over t and rows of dar, daz, dan, dgn
 #pragma unroll
   for (int i = 0; i < 8; ++i) carry[i] = own[i] = 0.f;
   if constexpr (SUM) {
@@ -937,13 +972,23 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
     const int t = d.reverse ? s : steps - 1 - s;
     const bool first_fwd = d.reverse ? (t == steps - 1) : (t == 0);
     const int tprev = d.reverse ? t + 1 : t - 1;
-    const long so = (long)u * d.sv_ld + (long)t * bpad + b0;
-    ld8(d.sv[0] + so, r);
-    ld8(d.sv[1] + so, z);
-    ld8(d.sv[2] + so, n);
-    ld8(d.sv[3] + so, ghn);
-    if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
-    else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
+    if constexpr (PRIV) {
+      const long blk = pv_block(t, bpad / 16, blockIdx.y, c, q);
+      ld8p(d.sv[0] + blk, lane, r);
+      ld8p(d.sv[1] + blk, lane, z);
+      ld8p(d.sv[2] + blk, lane, n);
+      ld8p(d.sv[3] + blk, lane, ghn);
+      if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
+      else ld8p(d.out + pv_block(tprev, bpad / 16, blockIdx.y, c, q), lane, hp);
+    } else {
+      const long so = (long)u * d.sv_ld + (long)t * bpad + b0;
+      ld8(d.sv[0] + so, r);
+      ld8(d.sv[1] + so, z);
+      ld8(d.sv[2] + so, n);
+      ld8(d.sv[3] + so, ghn);
+      if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
+      else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
+    }
     if (d.dout) ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
     else {
 #pragma unroll
@@ -1009,6 +1054,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
         dgn[i] = dan[i] * r[i];
         carry[i] = dh[i] * z[i];
         if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+        if constexpr (PRIV) { bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i]; }
       }
       epi_bar_sync();                                             // everyone has consumed rprev before it becomes the operand
       uint4 rhi, rlo, zhi, zlo, ghi, glo;
@@ -1063,12 +1109,23 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       //      cluster scope waits for every earlier store of the thread ----
       {
         const long o = (long)t * bpad + b0;
-        st8(d.dgi + (long)u * d.dg_ld + o, dar);
-        st8(d.dgi + (long)(H + u) * d.dg_ld + o, daz);
-        st8(d.dgi + (long)(2 * H + u) * d.dg_ld + o, dan);
-        st8(d.dgh + (long)u * d.dg_ld + o, dar);
-        st8(d.dgh + (long)(H + u) * d.dg_ld + o, daz);
-        st8(d.dgh + (long)(2 * H + u) * d.dg_ld + o, dgn);
+        if constexpr (PRIV) {
+          st8_T_p16(d.dghT_p, d.gT_nk, u, o, dar);
+          st8_T_p16(d.dghT_p, d.gT_nk, H + u, o, daz);
+          st8_T_p16(d.dghT_p, d.gT_nk, 2 * H + u, o, dgn);
+          if (d.dgiT_p) {
+            st8_T_p16(d.dgiT_p, d.gT_nk, u, o, dar);
+            st8_T_p16(d.dgiT_p, d.gT_nk, H + u, o, daz);
+            st8_T_p16(d.dgiT_p, d.gT_nk, 2 * H + u, o, dan);
+          }
+        } else {
+          st8(d.dgi + (long)u * d.dg_ld + o, dar);
+          st8(d.dgi + (long)(H + u) * d.dg_ld + o, daz);
+          st8(d.dgi + (long)(2 * H + u) * d.dg_ld + o, dan);
+          st8(d.dgh + (long)u * d.dg_ld + o, dar);
+          st8(d.dgh + (long)(H + u) * d.dg_ld + o, daz);
+          st8(d.dgh + (long)(2 * H + u) * d.dg_ld + o, dgn);
+        }
         if (d.dgi_p) {
           uint4 nhi, nlo;
           rw_transpose_pack(dan, lane, nhi, nlo);
@@ -1106,6 +1163,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       for (int i = 0; i < 8; ++i) g0[i] += v[i];
     }
     st8(d.dh0_out + (long)u * bpad + b0, g0);
+    if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
+      if (half == 0) {
+        atomicAdd(d.db_ih + u, bsum[0]); atomicAdd(d.db_ih + H + u, bsum[1]); atomicAdd(d.db_ih + 2 * H + u, bsum[2]);
+        atomicAdd(d.db_hh + u, bsum[0]); atomicAdd(d.db_hh + H + u, bsum[1]); atomicAdd(d.db_hh + 2 * H + u, bsum[3]);
+      }
+    }
     if constexpr (SUM) {
       st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
       st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
@@ -1136,6 +1201,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
 // =================================================================================================
 // launchers
 // =================================================================================================
+// private interchange layouts: both sweeps of the layer must run on the H = 256 barrier-free kernels
+bool rw_priv_mode(int H, int tiles) { return g_opt_rw_priv && g_opt_rw == 3 && g_opt_rw2 && H == 256 && rw_applicable(H, tiles); }
 bool rw_applicable(int H, int tiles) {
   // one wave: 2 directions x (B_pad / 16) clusters x 4 CTAs must fit the SMs a cluster-of-4 launch can use (132 of 148)
   return H >= 64 && H <= 256 && H % 64 == 0 && tiles >= 1 && tiles * 8 * 2 * 4 <= 132 * g_opt_rw_waves;
@@ -1172,7 +1239,8 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
   count_launch();
   if (nkc == 4 && g_opt_rw2) {
-    rw_launch(gru_rw2_fwd_kernel, a, smem, groups, a.ndir, st);
+    if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true>, a, smem, groups, a.ndir, st);
+    else rw_launch(gru_rw2_fwd_kernel<false>, a, smem, groups, a.ndir, st);
     return;
   }
   switch (nkc) {
@@ -1190,7 +1258,8 @@ static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const size_t rslot = (size_t)(4 * UC * 16 * 4 > nkb * RW_BTILE ? 4 * UC * 16 * 4 : nkb * RW_BTILE);
   const size_t smem = (size_t)nkc * nkb * RW_ATILE + 2 * rslot + 256;
   if (nkc == 4 && g_opt_rw2) {
-    rw_launch(gru_rw2_bwd_kernel<SUM>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
+    if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
+    else rw_launch(gru_rw2_bwd_kernel<SUM, false>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
     return;
   }
   switch (nkc) {

@@ -19,6 +19,7 @@ extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurr
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 extern int g_opt_rw;         // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels (gru_rw.cu) when applicable
 extern int g_opt_rw2;        // 1: H = 256 sweeps use the barrier-free rw kernels (bulk-copy / mbarrier exchange)
+extern int g_opt_rw_priv;   // 1: training sweeps of H = 256 layers use the private interchange layouts (needs rw = 3 and rw2 = 1)
 extern int g_opt_rw_waves;
 extern int g_opt_rw_exp;      // measurement experiments (wrong results), see GruSeqFwdArgs::exp   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
 inline void count_launch(int n = 1) { g_launch_count += n; }
@@ -117,6 +118,12 @@ struct GruSeqDirFwd {
   void* out_p; int out_p_slots; long out_p_slot_elems;  // P16 h sequence
   float* sv[4]; long sv_ld;                             // saved gates r,z,n,ghn (slot t) or nullptr
   int reverse;                                          // 1: processes t = steps-1 .. 0
+  // "private" training mode of the H = 256 rw kernels (both sweeps of a layer run on them): sv[] and out hold the
+  // lane-major layout shared by the forward and backward kernels (fully coalesced 512-byte accesses per warp instruction),
+  // the transposed P16 operand of the weight-gradient GEMMs is written directly, the final state also as fp32 feature-major
+  int priv;
+  void* outT_p; long outT_nk;                           // P16 [H rows, K = steps * B_pad], nk = K / 64
+  float* hfin;                                          // [H][B_pad]
 };
 struct GruSeqFwdArgs {
   GruSeqDirFwd d[2];
@@ -141,6 +148,11 @@ struct GruSeqDirBwd {
   void* dgi_p; long dgi_p_slot_elems;          // optional P16 copy of dgi per t
   float* dgi_sum; void* dgi_sum_p;             // optional: sum over t of dgi, feature-major [3H][B_pad] and P16 [B_pad rows, K = 3H]
                                                // (decoders: the GRU input is z at every step, so dz needs only the time sum)
+  // private mode (see GruSeqDirFwd): sv / out are read in the lane-major layout; instead of fp32 dgi / dgh the kernel writes the
+  // transposed P16 operands of the weight-gradient GEMMs and adds the bias gradients (sums over t and b) into db_ih / db_hh
+  int priv;
+  void* dghT_p; void* dgiT_p; long gT_nk;      // P16 [3H rows, K = steps * B_pad] (dgiT_p may be nullptr), nk = K / 64
+  float* db_ih; float* db_hh;                  // [3H] each, accumulated with atomicAdd
   int reverse;                                 // direction of the FORWARD recurrence (0: t ascending) -> BPTT runs the other way
 };
 struct GruSeqBwdArgs {
@@ -153,6 +165,7 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 
 // ---- gru_rw.cu: resident-weight sweeps (4-CTA clusters, swap-AB, h / partial sums exchanged through DSMEM) ----
 bool rw_applicable(int H, int tiles);
+bool rw_priv_mode(int H, int tiles);   // training sweeps use the private interchange layouts (see GruSeqDirFwd::priv)
 size_t rw_whh_bytes(int H);       // packed W_hh of one direction, forward format
 size_t rw_whhT_bytes(int H);      // ... backward format
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
