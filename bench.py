@@ -270,8 +270,13 @@ def main():
         ws = eng.workspace(B, True)
         res = {}
         pers = lib.vame_get_option(b"persistent")
-        names = ("gru_seq_fwd_kernel (per time step)" if pers & 1 else "gru_step_fwd_kernel",
-                 "gru_seq_bwd_kernel (per time step)" if pers & 2 else "gru_step_bwd_kernel")
+        rw, rw2 = lib.vame_get_option(b"rw"), lib.vame_get_option(b"rw2")
+        tiles = (B + 127) // 128
+        # same rule as rw_applicable() in csrc/gru_rw.cu: the resident-weight cluster kernels need their grid in one wave
+        rw_ok = H % 64 == 0 and 64 <= H <= 256 and tiles * 64 <= 132 * lib.vame_get_option(b"rw_waves")
+        rw_name = "gru_rw2_%s_kernel (per time step)" if (H == 256 and rw2) else "gru_rw_%s_kernel (per time step)"
+        names = (rw_name % "fwd" if (rw & 1) and rw_ok else "gru_seq_fwd_kernel (per time step)" if pers & 1 else "gru_step_fwd_kernel",
+                 rw_name % "bwd" if (rw & 2) and rw_ok else "gru_seq_bwd_kernel (per time step)" if pers & 2 else "gru_step_bwd_kernel")
         for which, name in ((0, names[0]), (1, names[1])):
             for _ in range(3):
                 L.check(lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, which, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream()), "sweep")
@@ -295,10 +300,11 @@ def main():
                 "traffic": traffic, "peak_source": how + ", burst figure (kernel timed alone)",
                 "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 4 * flops_launch,
                 "us_per_launch": {k: v * 1e6 for k, v in res.items()},
-                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 3-4x that in "
-                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/3 of the bf16 peak; the step is a serial "
-                        "chain of %d dependent time-step launches/phases on 64-128 of 148 SMs, latency-bound (about 1-2 us of MMA in a "
-                        "5-7 us step: cross-SM hand-over of h / partial sums, L2 round trips; DESIGN.md section 4)" % (6 * T),
+                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 4x that in "
+                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/4 of the bf16 peak; the step is a serial "
+                        "chain of %d dependent time steps, latency-bound: per step ~1.2 us of tcgen05.mma (48 MMAs of M=128 N=32 K=16 per "
+                        "CTA at the ~45-cycle issue floor), ~0.7 us gate math and ~1 us cluster exchange of h / partial sums "
+                        "(DESIGN.md section 4)" % (6 * T),
                 "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
                 "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
 

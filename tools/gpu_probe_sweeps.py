@@ -33,7 +33,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out = []
     for which in (0, 1):
-        dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+        dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
         lib.vame_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
         for _ in range(3):
             lib.vame_debug_gru_sweep(ctypes.byref(eng.dims), B, which, L.ptr(eng.flat), L.ptr(eng.packed), L.ptr(ws), ws.numel(), L.cur_stream())
@@ -47,6 +47,9 @@ def main():
         torch.cuda.synchronize()
         out.append("%s %.2f us/step stamps %s" % ("fwd" if which == 0 else "bwd", e0.elapsed_time(e1) * 1e3 / (20 * T),
                                                    [(st[i] - st[0]) if st[i] else None for i in range(12)]))
+        if any(st[16:48]):      # per-CTA stamps of one cluster (rw_exp & 32)
+            n = 4 if which == 0 else 8
+            out.append("per-CTA %s" % [[(st[16 + n * c + i] - st[0]) if st[16 + n * c + i] else None for i in range(n)] for c in range(4)])
     print(" ".join(sys.argv[1:]) or "defaults", "|", " | ".join(out), "| timeouts", lib.vame_get_option(b"rw_timeouts"), flush=True)
 
 

@@ -19,6 +19,7 @@ int g_opt_rw_waves = 1;
 int g_opt_rw2 = 1;
 int g_opt_rw_exp = 0;
 int g_opt_rw_priv = 1;
+int g_opt_rw_sw = 1;
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -48,6 +49,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "rw_waves") == 0) return vb::g_opt_rw_waves;
   if (strcmp(name, "rw2") == 0) return vb::g_opt_rw2;
   if (strcmp(name, "rw_priv") == 0) return vb::g_opt_rw_priv;
+  if (strcmp(name, "rw_sw") == 0) return vb::g_opt_rw_sw;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
   if (strncmp(name, "rw_timeout_info", 15) == 0) return vb::rw_timeout_info(name[15] ? name[15] - '0' : 0);
   return -1;
@@ -93,6 +95,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "rw_priv") == 0) {
     vb::g_opt_rw_priv = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(name, "rw_sw") == 0) {
+    vb::g_opt_rw_sw = value;
     return 0;
   }
   if (strcmp(name, "rw_exp") == 0) {

@@ -160,6 +160,23 @@ __device__ __forceinline__ void umma_bf16_c(uint32_t d_tmem, uint64_t adesc, uin
 // shared memory is < 256 KB)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
+
+
+// One lane of a converged warp (elect.sync).  MMA-issuing code is guarded by this instead of `lane == 0`: the compiler then
+// treats the region as single-lane code and keeps warp-uniform values (UMMA descriptors, barrier addresses) in uniform
+// registers.  Under `if (lane == 0)` every descriptor that depended on a loop variable was computed in vector registers and
+// each tcgen05.mma was preceded by an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 73 instead of 46 cycles per MMA in the
+// resident-weight GRU sweeps (measured, tools/bench_mma/mma_contention.cu gives the 46-cycle floor).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok));
+  return ok != 0;
+}
+
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int n_nb = (g.N + G_BN - 1) / G_BN, n_mb = (g.M + G_BM - 1) / G_BM;
   const int nkc_total = g.a[0].nkc + g.a[1].nkc + g.a[2].nkc + g.a[3].nkc;
   const int per = (nkc_total + g.splits - 1) / g.splits;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
 
   if (warp == 0) {
     // ===== producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it_global = 0;                                  // running stage counter across work items
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const WorkItem it = work_item(g, w, n_nb, nkc_total, per);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(G_BM, 2 * G_BN);          // one descriptor spans [B_hi ; B_lo]
       const uint64_t dA0 = make_desc(smem_u32(smem));
       constexpr uint32_t plane = 128 * KCHUNK * 2;                     // bytes between hi and lo planes

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
 
   const int c = blockIdx.x, tile = blockIdx.y / (128 / MT), hf = blockIdx.y % (128 / MT);
   const GruDirFwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
 
   if (tid == 0) {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
   // and starve the issuing lane.
   DBG_STAMP(0);
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p);
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_expect_tx(&wbar[kc], WT);
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128 * (UPC / UPT), 1) gru_step_fwd_kernel(cons
   DBG_STAMP(2);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       if (a.flags) {
         // flag hand-over: the previous step's CTAs (a still-running kernel) publish h and then bump the counter
         if (d.flag_in) {
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
 
   const int c = blockIdx.x, tile = blockIdx.y;          // cluster = all CTAs with the same (y, z): c is the cluster rank
   const GruSeqDirFwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
   const long Bp = (long)a.tiles * 128;
 
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_p);
       for (int kc = 0; kc < nkc; ++kc) {
         mbar_expect_tx(&wbar[kc], F_WTILE);
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256, 1) gru_seq_fwd_kernel(const GruSeqFwdArgs
     if (s > 0) cluster_wait_acquire();          // every CTA of the cluster has published its slice of h_{t-1}
     const uint32_t ph = s & 1;
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         fence_proxy_async_all();
         const __nv_bfloat16* hp = (s == 0 ? reinterpret_cast<const __nv_bfloat16*>(d.h0_p)
                                           : reinterpret_cast<const __nv_bfloat16*>(d.out_p) + (size_t)sp_prev * d.out_p_slot_elems) +
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
 
   const int c = blockIdx.x, tile = blockIdx.y;
   const GruDirBwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
   const uint32_t tmem_cols = (H <= 32) ? 32 : (H <= 64) ? 64 : (H <= 128) ? 128 : 256;
 
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
 
   // ---- prologue independent of the previous BPTT step: weights + saved forward activations ----
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // global layout: [slice c][rb][kc(2)][plane(2)][128x64]; shared layout per kc: hi[rb0..], lo[rb0..]
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
       mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(256, 1) gru_step_bwd_kernel(const GruBwdArgs a
   __syncthreads();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(wbar, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, H);
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
 
   const int c = blockIdx.x, tile = blockIdx.y / (128 / MT), hf = blockIdx.y % (128 / MT);
   const GruSeqDirBwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                 // half = which UPT-wide group of the slice's 32 units
   const uint32_t tmem_cols = (H <= 32) ? 32 : (H <= 64) ? 64 : (H <= 128) ? 128 : 256;
   const long bpad = (long)a.tiles * 128;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_p) + (size_t)c * nrb * 2 * p16_tile_elems(128);
       mbar_expect_tx(wbar, (uint32_t)(2 * wchunk));
       for (int kc = 0; kc < 2; ++kc)
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(32 * 4 * (32 / UPT), 1) gru_seq_bwd_kernel(con
     SEQ_STAMP(3);
     const uint32_t ph = s & 1;
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         if (s == 0) mbar_wait(wbar, 0);
         tc_fence_after();
         {

@@ -39,11 +39,9 @@ constexpr int RW_ATILE = 128 * KCHUNK * 2;     // 16384 B: 128 weight rows x 64 
 constexpr int RW_BTILE = 32 * KCHUNK * 2;      //  4096 B: [16 hi rows ; 16 lo rows] x 64 k (bf16)
 constexpr int RW_THREADS = 160;                // warps 0-3: element-wise work (one TMEM lane quarter each), warp 4: TMA + MMA issue
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
+// Rank of the CTA in its cluster: the rw grids are (4, groups, directions) with cluster dims (4, 1, 1), so the rank is
+// blockIdx.x (which the compiler knows to be warp-uniform, unlike a special register read through inline asm).
+__device__ __forceinline__ uint32_t cluster_ctarank() { return blockIdx.x & 3u; }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
@@ -79,6 +77,12 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 
 __device__ __forceinline__ void ld8(const float* p, float* v) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// streaming variants: L2 only (ld.global.cg) - with ~224 KB of shared memory per CTA the L1 is a few dozen lines, and the
+// default allocate-in-L1 loads of the sweeps (16 lines per warp instruction) serialise on it
+__device__ __forceinline__ void ld8cg(const float* p, float* v) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p + 4));
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 __device__ __forceinline__ void st8(float* p, const float* v) {
@@ -140,6 +144,23 @@ __device__ __forceinline__ uint32_t rw_b_off(int n, int k) { return (uint32_t)(k
       a.dbg[(i)] = t_;                                                                                        \
     }                                                                                                         \
   } while (0)
+// per-CTA stamps of cluster (y = 0, z = 0), step 10: dbg[16 + 4 * rank + i]
+#define RW_STAMP_CTA(i)                                                                                      \
+  do {                                                                                                        \
+    if (a.dbg && (a.exp & 32) && s == 10 && blockIdx.y == 0 && blockIdx.z == 0) {                             \
+      unsigned long long t_;                                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
+      a.dbg[16 + 4 * blockIdx.x + (i)] = t_;                                                                  \
+    }                                                                                                         \
+  } while (0)
+#define RW_STAMP_CTA8(i)                                                                                     \
+  do {                                                                                                        \
+    if (a.dbg && (a.exp & 32) && s == 10 && blockIdx.y == 0 && blockIdx.z == 0) {                             \
+      unsigned long long t_;                                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                  \
+      a.dbg[16 + 8 * blockIdx.x + (i)] = t_;                                                                  \
+    }                                                                                                         \
+  } while (0)
 #define RW_STAMP_MMA(i)                                                                                      \
   do {                                                                                                        \
     if (a.dbg && s == 10 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {                          \
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirFwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
   const bool epi = warp < 4 && q < NKC;                           // this warp owns 16 units of the slice
   const long Bp = (long)a.tiles * 128;
@@ -183,7 +204,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_rw) + (size_t)c * 3 * NKC * (RW_ATILE / 2);
       mbar_expect_tx(wbar, 3 * NKC * RW_ATILE);
       for (int i = 0; i < 3 * NKC; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_fwd_kernel(const GruSeqF
     if (s > 0) cluster_wait_acquire();                            // every CTA's slice of h_{t-1} has landed in buffer s & 1
     RW_STAMP(1);
     if (warp == 4) {
-      if (lane == 0) {
+      if (elect_one()) {
         if (s == 0) mbar_wait_b(wbar, 0, 1);
         fence_proxy_async_smem();
         tc_fence_after();
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirBwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
   const bool ew = warp < 4;                                       // element-wise warp (drains TMEM lane quarter q)
   const bool epi = ew && q < NKC;                                 // ... that also owns 16 units of the slice
@@ -379,7 +400,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
       mbar_expect_tx(wbar, MT * NKB * RW_ATILE);
       for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
     RW_STAMP(2);
     __syncthreads();
     if (warp == 4) {
-      if (lane == 0) {
+      if (elect_one()) {
         if (s == 0) mbar_wait_b(wbar, 0, 1);
         fence_proxy_async_smem();
         tc_fence_after();
@@ -642,6 +663,11 @@ __device__ __forceinline__ void st8_T_p16(void* base, long nk, int row, long k, 
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
+// relaxed variant: a pure "I am done reading" signal that publishes no data of this thread.  The release form made the warp
+// wait for all of its earlier stores (st.async pushes, global stores): ~1.3 us per step on the slowest CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -661,8 +687,34 @@ __device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t pari
   rw_timeout(site, parity);
 }
 
-template <bool PRIV>
-__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
+// TMEM <-> registers, 8 consecutive 32-bit columns of this thread's lane (staging of the store warps, see SW below)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+constexpr int RW_SW_THREADS = 288;             // + warps 5-8: store warps (SW kernels)
+
+// SW ("store warps", training sweeps in the private layouts): an SM drains its global stores at only ~18 B/cycle, so the 28 KB a
+// CTA writes per time step kept the four gate-math warps stuck in their store instructions for ~1 us of a 3.2 us step
+// (measured with the stores removed: 2.3 us).  With SW the gate-math warps hand h_t and the saved gates to four extra warps
+// through TENSOR MEMORY (tcgen05.st into spare columns, double-buffered, mbarrier handshake; warp 5 + i owns the TMEM lane
+// quarter (5 + i) % 4) and go straight back to the recurrence; the store warps do the bf16 splits / transposes and all global
+// stores of step t while step t + 1 is being computed.
+template <bool PRIV, bool SW>
+__global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
+  static_assert(PRIV || !SW, "store warps serve the private layouts only");
   constexpr int NKC = 4, H = 256, UC = 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
@@ -671,11 +723,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
   uint64_t* done = wbar + 1;                                      // [3]: accumulator of gate g complete
   uint64_t* lfull = done + 3;                                     // [2]: own chunk of operand buffer b written (128 arrivals)
   uint64_t* hfull = lfull + 2;                                    // [2]: the three peers' chunks of buffer b have landed (tx bytes)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hfull + 2);
+  uint64_t* sfull = hfull + 2;                                    // [2] SW: staging buffer b written by the 128 gate-math threads
+  uint64_t* sempty = sfull + 2;                                   // [2] SW: staging buffer b read back by the 128 store threads
+  uint64_t* gfull = sempty + 2;                                   // [3] SW: gi of step s (TMEM buffer s % 3) written by the store threads
+  uint64_t* gempty = gfull + 3;                                   // [3] SW: ... consumed by the gate-math threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty + 3);
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirFwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
   const bool epi = warp < 4;
   const long Bp = (long)a.tiles * 128;
@@ -687,17 +743,25 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
     for (int b = 0; b < 2; ++b) {
       mbar_init(&lfull[b], 128);
       mbar_init(&hfull[b], 1);
+      mbar_init(&sfull[b], 128);
+      mbar_init(&sempty[b], 128);
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&gfull[b], 128);
+      mbar_init(&gempty[b], 128);
     }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  constexpr uint32_t TCOLS = SW ? 256 : 128;                      // accumulators: columns 0-95; SW staging: 128 + 64 b + [0, 40),
+                                                                  // SW input projections: 3 buffers of 24 columns at 96 / 168 / 232
+  if (warp == 4) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_rw) + (size_t)c * 3 * NKC * (RW_ATILE / 2);
       mbar_expect_tx(wbar, 3 * NKC * RW_ATILE);
       for (int i = 0; i < 3 * NKC; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
@@ -732,9 +796,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
   }
   // arm the receive barriers of the first two exchanges (buffer 1 is filled for step 1, buffer 0 for step 2); later phases are
   // armed right after the previous phase has been waited for, so a peer's complete_tx never precedes the expect_tx
+  const uint32_t hx = (a.exp & 8) ? 3 * RW_BTILE / 2 : 3 * RW_BTILE;   // (experiment 8: only the hi plane is pushed)
   if (tid == 0) {
-    if (steps > 1) mbar_expect_tx(&hfull[1], 3 * RW_BTILE);
-    if (steps > 2) mbar_expect_tx(&hfull[0], 3 * RW_BTILE);
+    if (steps > 1) mbar_expect_tx(&hfull[1], hx);
+    if (steps > 2) mbar_expect_tx(&hfull[0], hx);
   }
   // all mbarriers of the cluster are initialised (and the h0 operands written) before any remote signal is sent
   cluster_arrive_release();
@@ -744,13 +809,38 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
   const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
   const long groups = Bp / 16;
   const bool gi_const = d.gi_ts == 0;                              // decoders: the input projection does not depend on t
-  float gir[8], giz[8], gin[8];
-  if (epi) {
-    const int t0 = d.reverse ? steps - 1 : 0;
-    const float* gi_row = d.gi + (b0 * d.gi_bs + (long)t0 * d.gi_ts);
-    ld8(gi_row + (long)u * d.gi_ld, gir);
-    ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
-    ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+  // input projections are prefetched TWO steps ahead (registers): under the write bursts of the sweep's own stores a load
+  // issued one step ahead came back too late for the next gate math (measured: 3.25 -> 2.5 us per step)
+  float gir[8], giz[8], gin[8], gir2[8], giz2[8], gin2[8];
+  auto load_gi = [&](int s_, float* r_, float* z_, float* n_) {
+    const int t_ = d.reverse ? steps - 1 - s_ : s_;
+    const float* gi_row = d.gi + (b0 * d.gi_bs + (long)t_ * d.gi_ts);
+    ld8(gi_row + (long)u * d.gi_ld, r_);          // (ld.global.cg instead: 3.9 instead of 3.3 us per step - the second
+    ld8(gi_row + (long)(H + u) * d.gi_ld, z_);    //  16 bytes of each sector are L1 hits with the default policy)
+    ld8(gi_row + (long)(2 * H + u) * d.gi_ld, n_);
+  };
+  // SW && !gi_const: the store warps fetch gi(s + 2) during step s and pass it on through tensor memory, so that the gate-math
+  // warps issue no global memory instruction at all
+  const bool gi_tmem = SW && !gi_const && !(a.exp & 2);
+  auto gi_col = [&](int s_) -> uint32_t { const int b_ = s_ % 3; return taddr + (b_ == 0 ? 96u : b_ == 1 ? 168u : 232u); };
+  auto gi_publish = [&](int s_, const float* r_, const float* z_, const float* n_) {   // store warps
+    const uint32_t gc = gi_col(s_);
+    tmem_st8(gc, r_);
+    tmem_st8(gc + 8, z_);
+    tmem_st8(gc + 16, n_);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&gfull[s_ % 3]);
+  };
+  if (epi && !gi_tmem) {
+    load_gi(0, gir, giz, gin);
+    if (steps > 1 && !gi_const) load_gi(1, gir2, giz2, gin2);
+  }
+  if (SW && warp >= 5 && gi_tmem) {
+    load_gi(0, gir, giz, gin);
+    if (steps > 1) load_gi(1, gir2, giz2, gin2);
+    gi_publish(0, gir, giz, gin);
+    if (steps > 1) gi_publish(1, gir2, giz2, gin2);
   }
 
   for (int s = 0; s < steps; ++s) {
@@ -760,7 +850,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
     const uint32_t ph = s & 1, b = s & 1;
     RW_STAMP(0);
     if (warp == 4) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t hb = smem_u32(sH) + b * NKC * RW_BTILE;
         if (s == 0) {
           mbar_wait_b(wbar, 0, 10);
@@ -784,10 +874,11 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         }
         if (s > 0) {
           mbar_wait_b(&hfull[b], ((s - 1) >> 1) & 1, 12);
-          if (s + 2 < steps) mbar_expect_tx(&hfull[b], 3 * RW_BTILE);     // arm the next use of this buffer (step s + 2)
+          if (s + 2 < steps) mbar_expect_tx(&hfull[b], hx);               // arm the next use of this buffer (step s + 2)
           fence_proxy_async_smem();                                 // the peers' chunks were written through the generic proxy
         }
         RW_STAMP_MMA(9);
+        RW_STAMP_CTA(0);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
 #pragma unroll
@@ -804,9 +895,66 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         RW_STAMP_MMA(2);
       }
       __syncwarp();
+    } else if (SW && warp >= 5) {                                   // ---- store warp of TMEM lane quarter q & 3 ----
+      float hn[8], sr[8], sz[8], sn[8], sg[8];
+      const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+      const bool fetch = gi_tmem && s + 2 < steps;
+      if (fetch) load_gi(s + 2, gir, giz, gin);
+      mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 17);
+      tc_fence_after();
+      tmem_ld8(stg, hn);
+      tmem_ld8(stg + 8, sr);
+      tmem_ld8(stg + 16, sz);
+      tmem_ld8(stg + 24, sn);
+      tmem_ld8(stg + 32, sg);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sempty[sb]);
+      if (a.exp & 16) {
+        if (fetch) {
+          if (s >= 1) mbar_wait_warp(&gempty[(s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
+          tc_fence_after();
+          gi_publish(s + 2, gir, giz, gin);
+        }
+        continue;
+      }
+      // (pacing these stores - one per warp every 256-384 cycles - changed nothing: 3.04 us per step either way)
+      uint4 phi, plo;
+      rw_transpose_pack(hn, lane, phi, plo);
+      const long row = (long)blockIdx.y * 16 + nrow;
+      const int k0 = (int)c * UC + kloc;
+      __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                          ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
+      const int off = p16_in_tile((int)(row & 127), k0 & 63);
+      const long blk = pv_block(t, groups, blockIdx.y, c, q);
+      st8p(d.out + blk, lane, hn);
+      st8p(d.sv[0] + blk, lane, sr);
+      st8p(d.sv[1] + blk, lane, sz);
+      st8p(d.sv[2] + blk, lane, sn);
+      st8p(d.sv[3] + blk, lane, sg);
+      st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + b0, hn);
+      if (s + 1 == steps) st8(d.hfin + (long)u * Bp + b0, hn);
+      *reinterpret_cast<uint4*>(tl + off) = phi;
+      *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
+      if (fetch) {                                                  // buffer (s + 2) % 3 was last read in step s - 1
+        if (s >= 1) mbar_wait_warp(&gempty[(s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
+        tc_fence_after();
+        gi_publish(s + 2, gir, giz, gin);
+      }
     } else {
       float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
       uint4 phi, plo;
+      if (gi_tmem) {                                                // this step's input projections (published >= 1 step ago)
+        mbar_wait_warp(&gfull[s % 3], (s / 3) & 1, 19);
+        tc_fence_after();
+        const uint32_t gc = gi_col(s);
+        tmem_ld8(gc, gir);
+        tmem_ld8(gc + 8, giz);
+        tmem_ld8(gc + 16, gin);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&gempty[s % 3]);
+      }
       mbar_wait_warp(&done[0], ph, 13);
       tc_fence_after();
       rw_reduce32(taddr, half, ar);
@@ -820,6 +968,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
       mbar_wait_warp(&done[2], ph, 15);
       tc_fence_after();
       RW_STAMP(3);
+      if (tid == 0) RW_STAMP_CTA(1);
       rw_reduce32(taddr + 64, half, an);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -839,7 +988,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         for (uint32_t r = 1; r < 4; ++r) {                          // the same chunk position in the three peers' buffers
           const uint32_t peer = (c + r) & 3, pbar = mapa_u32(hbar, peer);
           st_async_v4(mapa_u32(ohi, peer), phi, pbar);
-          st_async_v4(mapa_u32(olo, peer), plo, pbar);
+          if (!(a.exp & 8)) st_async_v4(mapa_u32(olo, peer), plo, pbar);
         }
         *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(nrow, kloc)) = phi;
         *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(16 + nrow, kloc)) = plo;
@@ -847,15 +996,30 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
         mbar_arrive(&lfull[b ^ 1u]);
       }
       RW_STAMP(5);
+      if (tid == 0) RW_STAMP_CTA(2);
+      if (tid == 96) RW_STAMP_CTA(3);
       // ---- off the recurrence (overlaps the exchange and the next step's MMAs); loads first: the LSU works in order ----
-      if (s + 1 < steps && !gi_const && !(a.exp & 2)) {
-        const int tn = d.reverse ? t - 1 : t + 1;
-        const float* gi_row = d.gi + (b0 * d.gi_bs + (long)tn * d.gi_ts);
-        ld8(gi_row + (long)u * d.gi_ld, gir);
-        ld8(gi_row + (long)(H + u) * d.gi_ld, giz);
-        ld8(gi_row + (long)(2 * H + u) * d.gi_ld, gin);
+      if (s + 1 < steps && !gi_const && !gi_tmem && !(a.exp & 2)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { gir[i] = gir2[i]; giz[i] = giz2[i]; gin[i] = gin2[i]; }
+        if (s + 2 < steps) load_gi(s + 2, gir2, giz2, gin2);
+      }
+      if constexpr (SW) {                                           // hand h_t and the saved gates to the store warps
+        const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+        if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 16);
+        tc_fence_after();
+        tmem_st8(stg, hn);
+        tmem_st8(stg + 8, sr);
+        tmem_st8(stg + 16, sz);
+        tmem_st8(stg + 24, sn);
+        tmem_st8(stg + 32, sg);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&sfull[sb]);
+        continue;
       }
       if constexpr (PRIV) {
+        if (a.exp & 16) continue;                                   // (experiment 16: no global stores)
         const long blk = pv_block(t, groups, blockIdx.y, c, q);
         st8p(d.out + blk, lane, hn);
         st8p(d.sv[0] + blk, lane, sr);
@@ -891,11 +1055,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeq
   cluster_wait_acquire();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 4) tmem_dealloc(tmem, TCOLS);
 }
 
-template <bool SUM, bool PRIV>
-__global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
+// SW: as in the forward kernel, four extra warps take over everything that is not on the recurrence - here the gate gradients
+// of step t travel through tensor memory (32 columns, double-buffered) and the store warps write the transposed P16 operands of
+// the weight-gradient GEMMs, the P16 copy for dx, and keep the bias-gradient / time sums.
+template <bool SUM, bool PRIV, bool SW>
+__global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
+  static_assert(PRIV || !SW, "store warps serve the private layouts only");
   constexpr int NKC = 4, H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
   constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
   static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
@@ -907,11 +1075,13 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
   uint64_t* ofull = done + 4;                                     // operand of this step written (128 arrivals)
   uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x 4 warps have landed in slot b
   uint64_t* mfree = pfull + 2;                                    // [2]: all MMAs of the 3 peers' step s are complete (3 x 4 warps), slot s & 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfree + 2);   //      (a peer may signal step s + 1 before this CTA has looked at step s)
+  uint64_t* sfull = mfree + 2;                                    // [2] SW: staging buffer b written by the 128 gate-math threads
+  uint64_t* sempty = sfull + 2;                                   // [2] SW: ... read back by the 128 store threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);  // (mfree: a peer may signal step s + 1 before this CTA has looked at step s)
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirBwd& d = a.d[blockIdx.z];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
   const bool epi = warp < 4;
   const long bpad = (long)a.tiles * 128;
@@ -925,16 +1095,21 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
     mbar_init(&pfull[1], 1);
     mbar_init(&mfree[0], 12);
     mbar_init(&mfree[1], 12);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sfull[b], 128);
+      mbar_init(&sempty[b], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  constexpr uint32_t TCOLS = SW ? 256 : 128;                      // accumulators: columns 0-127; SW staging: 128 + 64 b + [0, 32)
+  if (warp == 4) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
       mbar_expect_tx(wbar, MT * NKB * RW_ATILE);
       for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
@@ -1006,7 +1181,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
     uint8_t* rprev = sR + (ph ^ 1u) * RSLOT;                      // partial sums of step s - 1; then this step's operand
     RW_STAMP(0);
     if (warp == 4) {
-      if (lane == 0) {
+      if (elect_one()) {
         if (s == 0) mbar_wait_b(wbar, 0, 20);
         mbar_wait_b(ofull, ph, 21);
         fence_proxy_async_smem();
@@ -1027,6 +1202,50 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
         RW_STAMP_MMA(3);
       }
       __syncwarp();
+    } else if (SW && warp >= 5) {                                   // ---- store warp of TMEM lane quarter q & 3 ----
+      float dar[8], daz[8], dan[8], dgn[8];
+      const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+      mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 26);
+      tc_fence_after();
+      tmem_ld8(stg, dar);
+      tmem_ld8(stg + 8, daz);
+      tmem_ld8(stg + 16, dan);
+      tmem_ld8(stg + 24, dgn);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sempty[sb]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+        bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i];
+      }
+      if (a.exp & 16) continue;
+      const long o = (long)t * bpad + b0;
+      st8_T_p16(d.dghT_p, d.gT_nk, u, o, dar);
+      st8_T_p16(d.dghT_p, d.gT_nk, H + u, o, daz);
+      st8_T_p16(d.dghT_p, d.gT_nk, 2 * H + u, o, dgn);
+      if (d.dgiT_p) {
+        st8_T_p16(d.dgiT_p, d.gT_nk, u, o, dar);
+        st8_T_p16(d.dgiT_p, d.gT_nk, H + u, o, daz);
+        st8_T_p16(d.dgiT_p, d.gT_nk, 2 * H + u, o, dan);
+      }
+      if (d.dgi_p) {
+        constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+        const long row = (long)blockIdx.y * 16 + nrow;
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
+                              (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+        const int rr = (int)(row & 127);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          uint4 hi, lo;
+          rw_transpose_pack(g == 0 ? dar : (g == 1 ? daz : dan), lane, hi, lo);
+          const int k = g * H + (int)c * UC + kq;
+          __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+          const int off = p16_in_tile(rr, k & 63);
+          *reinterpret_cast<uint4*>(tl + off) = hi;
+          *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+        }
+      }
     } else {
       float dar[8], daz[8], dan[8], dgn[8];
 #pragma unroll
@@ -1036,6 +1255,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
         if (tid == 0 && s + 1 < steps) mbar_expect_tx(&pfull[ph ^ 1u], RSLOT);   // arm it for the pushes of step s + 1
         __syncwarp();
         RW_STAMP(1);
+        if (tid == 0) RW_STAMP_CTA8(0);
+        if (tid == 96) RW_STAMP_CTA8(1);
 #pragma unroll
         for (int src = 0; src < 3; ++src) {
           float v[8];
@@ -1053,8 +1274,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
         dar[i] = dan[i] * ghn[i] * r[i] * (1.0f - r[i]);
         dgn[i] = dan[i] * r[i];
         carry[i] = dh[i] * z[i];
-        if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
-        if constexpr (PRIV) { bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i]; }
+        if constexpr (SUM && !SW) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+        if constexpr (PRIV && !SW) { bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i]; }
       }
       epi_bar_sync();                                             // everyone has consumed rprev before it becomes the operand
       uint4 rhi, rlo, zhi, zlo, ghi, glo;
@@ -1071,13 +1292,16 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       tc_fence_before();
       mbar_arrive(ofull);
       RW_STAMP(2);
+      if (tid == 0) RW_STAMP_CTA8(2);
+      if (tid == 96) RW_STAMP_CTA8(3);
       // ---- while the MMAs run: next step's inputs ----
-      if (s + 1 < steps) load_step(s + 1);
+      if (s + 1 < steps && !(a.exp & 64)) load_step(s + 1);          // (experiment 64: no global loads)
       // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {
         mbar_wait_warp(&done[i], ph, 24);
         tc_fence_after();
+        RW_STAMP(6 + i);
         float part[8];
         rw_reduce32(taddr + i * 32, half, part);
         if (i == 0 && s > 0) {
@@ -1093,21 +1317,41 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
           const uint32_t ra = mapa_u32(off, owner), pbar = mapa_u32(smem_u32(&pfull[ph]), owner);
           st_async_f4(ra, part[0], part[1], part[2], part[3], pbar);
           st_async_f4(ra + 16, part[4], part[5], part[6], part[7], pbar);
+          if (i == 2 && tid == 0) RW_STAMP_CTA8(4);
+          if (i == 2 && tid == 96) RW_STAMP_CTA8(5);
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) own[k] = part[k];
           // commits complete in order: every MMA of this step has finished reading the operand
           if (lane == 0 && s + 1 < steps) {
 #pragma unroll
-            for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
+            for (uint32_t r = 1; r < 4; ++r) {
+              if (a.exp & 128) mbar_arrive_remote(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
+              else mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
+            }
           }
         }
       }
       tc_fence_before();
       RW_STAMP(4);
+      if (tid == 0) RW_STAMP_CTA8(6);
+      if (tid == 96) RW_STAMP_CTA8(7);
       // ---- this step's outputs (weight-gradient GEMMs, dx of the layer below): after the pushes, because a release at
       //      cluster scope waits for every earlier store of the thread ----
-      {
+      if constexpr (SW) {                                           // hand the gate gradients to the store warps
+        const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+        if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 27);
+        tc_fence_after();
+        tmem_st8(stg, dar);
+        tmem_st8(stg + 8, daz);
+        tmem_st8(stg + 16, dan);
+        tmem_st8(stg + 24, dgn);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&sfull[sb]);
+        continue;
+      }
+      if (!(a.exp & 16)) {                                         // (experiment 16: no global stores)
         const long o = (long)t * bpad + b0;
         if constexpr (PRIV) {
           st8_T_p16(d.dghT_p, d.gT_nk, u, o, dar);
@@ -1163,6 +1407,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
       for (int i = 0; i < 8; ++i) g0[i] += v[i];
     }
     st8(d.dh0_out + (long)u * bpad + b0, g0);
+  }
+  if (SW ? (warp >= 5) : epi) {
     if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
 #pragma unroll
       for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
@@ -1195,7 +1441,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeq
   cluster_wait_acquire();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 4) tmem_dealloc(tmem, TCOLS);
 }
 
 // =================================================================================================
@@ -1214,11 +1460,11 @@ size_t rw_whhT_bytes(int H) {
 }
 
 template <typename K, typename A>
-static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, cudaStream_t st) {
+static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, cudaStream_t st, int threads = RW_THREADS) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(4, groups, ndir);
-  cfg.blockDim = dim3(RW_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1239,8 +1485,9 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
   count_launch();
   if (nkc == 4 && g_opt_rw2) {
-    if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true>, a, smem, groups, a.ndir, st);
-    else rw_launch(gru_rw2_fwd_kernel<false>, a, smem, groups, a.ndir, st);
+    if (a.d[0].priv && (g_opt_rw_sw & 1)) rw_launch(gru_rw2_fwd_kernel<true, true>, a, smem, groups, a.ndir, st, RW_SW_THREADS);
+    else if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true, false>, a, smem, groups, a.ndir, st);
+    else rw_launch(gru_rw2_fwd_kernel<false, false>, a, smem, groups, a.ndir, st);
     return;
   }
   switch (nkc) {
@@ -1258,8 +1505,10 @@ static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const size_t rslot = (size_t)(4 * UC * 16 * 4 > nkb * RW_BTILE ? 4 * UC * 16 * 4 : nkb * RW_BTILE);
   const size_t smem = (size_t)nkc * nkb * RW_ATILE + 2 * rslot + 256;
   if (nkc == 4 && g_opt_rw2) {
-    if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
-    else rw_launch(gru_rw2_bwd_kernel<SUM, false>, a, (size_t)12 * RW_ATILE + 2 * 12288 + 256, groups, a.ndir, st);
+    const size_t sm2 = (size_t)12 * RW_ATILE + 2 * 12288 + 256;
+    if (a.d[0].priv && (g_opt_rw_sw & 2)) rw_launch(gru_rw2_bwd_kernel<SUM, true, true>, a, sm2, groups, a.ndir, st, RW_SW_THREADS);
+    else if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true, false>, a, sm2, groups, a.ndir, st);
+    else rw_launch(gru_rw2_bwd_kernel<SUM, false, false>, a, sm2, groups, a.ndir, st);
     return;
   }
   switch (nkc) {
@@ -1272,6 +1521,7 @@ static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
 void launch_gru_rw_bwd(const GruSeqBwdArgs& a_in, cudaStream_t st) {
   GruSeqBwdArgs a = a_in;
   a.dbg = g_dbg_buffer;
+  a.exp = g_opt_rw_exp;
   count_launch();
   if (a.d[0].dgi_sum) rw_launch_bwd<true>(a, st);
   else rw_launch_bwd<false>(a, st);

@@ -19,6 +19,7 @@ extern int g_opt_persistent; // bit 0 / bit 1: run the forward / backward recurr
                              // instead of one PDL-chained kernel per time step (measured: per-step wins forward, persistent backward)   // 1: run independent branches of a step on internal side streams
 extern int g_opt_rw;         // bit 0 / bit 1: forward / backward sweeps by the resident-weight cluster kernels (gru_rw.cu) when applicable
 extern int g_opt_rw2;        // 1: H = 256 sweeps use the barrier-free rw kernels (bulk-copy / mbarrier exchange)
+extern int g_opt_rw_sw;     // bit 0 / bit 1: forward / backward private-mode sweeps hand their global stores to extra store warps through tensor memory
 extern int g_opt_rw_priv;   // 1: training sweeps of H = 256 layers use the private interchange layouts (needs rw = 3 and rw2 = 1)
 extern int g_opt_rw_waves;
 extern int g_opt_rw_exp;      // measurement experiments (wrong results), see GruSeqFwdArgs::exp   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
@@ -160,6 +161,7 @@ struct GruSeqBwdArgs {
   int ndir, H, tiles, steps;
   int mt;                    // batch rows per CTA: 64 or 128 (0 = 128)
   unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
+  int exp;                   // measurement experiments only (option "rw_exp", results become wrong)
 };
 void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 
