@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
       tc_fence_after();
       const int row = it.mb * G_BM + q * 32 + lane;
       const uint32_t taddr = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+      const bool fm_vec = g.c_fm && !g.atomic && (g.M & 3) == 0 && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
 #pragma unroll 1
       for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 16) {
         float v[16], v2[16];
@@ -156,7 +157,37 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += v2[j];
         const int col = it.nb * G_BN + c0;
-        if (g.c_fm) {                       // feature-major output: C[n*ldc + m]; lanes (= rows m) are contiguous -> coalesced
+        if (g.c_fm && fm_vec) {
+          // feature-major output C[n*ldc + m], 16 bytes per lane: an SM retires one warp-level store instruction per ~25 cycles
+          // whatever its width (measured: 512 scalar stores per tile made the K = 64 input projection 43 us instead of ~12),
+          // so 4 x 4 blocks are transposed across 4 adjacent lanes first: lane 4g + r then holds rows 4g .. 4g+3 of column j4 + r
+          if (g.bias && it.split == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < g.N) v[j] += g.bias[col + j];
+          }
+          const int r = lane & 3;
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            float a0 = v[j4], a1 = v[j4 + 1], a2 = v[j4 + 2], a3 = v[j4 + 3];
+            {   // exchange 2 x 2 blocks with lane ^ 2
+              const bool up = (r & 2) != 0;
+              const float s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+              const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+              if (up) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
+            }
+            {   // exchange single elements with lane ^ 1
+              const bool up = (r & 1) != 0;
+              const float s0 = up ? a0 : a1, s1 = up ? a2 : a3;
+              const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+              if (up) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
+            }
+            // now (a0, a1, a2, a3) = column j4 + r of rows 4g, 4g+1, 4g+2, 4g+3
+            const int cj = col + j4 + r;
+            const int row4 = it.mb * G_BM + q * 32 + (lane & ~3);
+            if (cj < g.N && row4 < g.M) *reinterpret_cast<float4*>(g.C + (long)cj * g.ldc + row4) = make_float4(a0, a1, a2, a3);
+          }
+        } else if (g.c_fm) {                // feature-major output: C[n*ldc + m]; lanes (= rows m) are contiguous -> coalesced
           if (row < g.M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {

@@ -75,19 +75,24 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 element-wise warps
 
+// 8 consecutive floats of one thread as ONE 256-bit global access (sm_100: LDG/STG.E.ENL2.256): an SM retires about one
+// warp-level memory instruction per ~25 cycles whatever its width, so the instruction count is what the sweeps pay for.
+// All call sites are 32-byte aligned (batch offsets are multiples of 8 rows, leading dimensions multiples of 128).
 __device__ __forceinline__ void ld8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
+// the same from shared memory (generic address)
+__device__ __forceinline__ void ld8s(const float* p, float* v) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-// streaming variants: L2 only (ld.global.cg) - with ~224 KB of shared memory per CTA the L1 is a few dozen lines, and the
-// default allocate-in-L1 loads of the sweeps (16 lines per warp instruction) serialise on it
-__device__ __forceinline__ void ld8cg(const float* p, float* v) {
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
 __device__ __forceinline__ void st8(float* p, const float* v) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
 }
 
 // One accumulator block of 32 columns: this lane's row holds (plane of lane) x [h_hi rows 0-15 | h_lo rows 0-15].
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
 #pragma unroll
         for (int src = 0; src < 4; ++src) {
           float v[8];
-          ld8(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
+          ld8s(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dh[i] += v[i];
         }
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gru_rw_bwd_kernel(const GruSeqB
 #pragma unroll
     for (int src = 0; src < 4; ++src) {
       float v[8];
-      ld8(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
+      ld8s(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g0[i] += v[i];
     }
@@ -641,16 +646,10 @@ __device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float a, float
                : "memory");
 }
 // private lane-major interchange layout of the H = 256 kernels: per (t, 16-row group g, CTA c, warp q) one 1 KB block
-// [k: 2][lane: 32][4 floats] holding values 4 k .. 4 k + 3 of every lane -> a warp instruction moves 512 contiguous bytes
+// [lane: 32][8 floats] -> one 256-bit access per thread, a warp instruction moves 1 KB of contiguous memory
 __device__ __forceinline__ long pv_block(long t, long groups, long g, uint32_t c, int q) { return (((t * groups + g) * 4 + c) * 4 + (q & 3)) * 256; }
-__device__ __forceinline__ void ld8p(const float* blk, int lane, float* v) {
-  const float4 a = *reinterpret_cast<const float4*>(blk + lane * 4), b = *reinterpret_cast<const float4*>(blk + 128 + lane * 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void st8p(float* blk, int lane, const float* v) {
-  *reinterpret_cast<float4*>(blk + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(blk + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
+__device__ __forceinline__ void ld8p(const float* blk, int lane, float* v) { ld8(blk + lane * 8, v); }
+__device__ __forceinline__ void st8p(float* blk, int lane, const float* v) { st8(blk + lane * 8, v); }
 // 8 consecutive k (= batch rows) of row `row` of a transposed P16 operand [rows, K]: one atom row per plane
 __device__ __forceinline__ void st8_T_p16(void* base, long nk, int row, long k, const float* v) {
   uint4 hi, lo;
@@ -1260,7 +1259,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
 #pragma unroll
         for (int src = 0; src < 3; ++src) {
           float v[8];
-          ld8(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
+          ld8s(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dh[i] += v[i];
         }
@@ -1402,7 +1401,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
 #pragma unroll
     for (int src = 0; src < 3; ++src) {
       float v[8];
-      ld8(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
+      ld8s(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g0[i] += v[i];
     }
