@@ -77,6 +77,11 @@ long vame_param_layout(const vame_dims* d, long* offsets, long* sizes);
 /* bf16 hi/lo tensor-core copies of the weights; must be refreshed after every parameter update */
 size_t vame_packed_weights_bytes(const vame_dims* d);
 int vame_pack_weights(const vame_dims* d, const float* params, void* packed, void* stream);
+/* Same result, for the train loop: only the formats the forward pass reads first (encoder layer 0) are packed now, on
+ * `stream`; the rest is packed by the NEXT vame_forward (same params / packed pointers, which must stay valid until then) on a
+ * low-priority internal stream beside its first recurrent sweep.  Any other entry point that reads `packed` completes the
+ * re-pack on its own stream first.  Graph-capturable together with that vame_forward. */
+int vame_pack_weights_deferred(const vame_dims* d, const float* params, void* packed, void* stream);
 
 size_t vame_workspace_bytes(const vame_dims* d, int batch, int training);
 

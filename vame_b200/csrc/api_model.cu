@@ -83,13 +83,15 @@ static void carve_gru(Arena& A, GruBuf& g, int steps, int H, int In, int B_pad, 
   g.out_slots = training ? steps : 2;
   g.out_p_slots = per_t_p16 ? steps : 2;
   g.flags = (unsigned int*)A.raw((size_t)2 * steps * tiles * sizeof(unsigned int));
+  if (own_h0) {                               // both directions adjacent: written by ONE h0_prepare launch
+    g.h0[0] = A.f32(2 * slotf);
+    g.h0_p[0] = A.raw(2 * slotp);
+    g.h0[1] = g.h0[0] ? g.h0[0] + slotf : nullptr;
+    g.h0_p[1] = g.h0_p[0] ? (char*)g.h0_p[0] + slotp : nullptr;
+  }
   for (int d = 0; d < 2; ++d) {
     g.out[d] = A.f32(slotf * g.out_slots);
     g.out_p[d] = A.raw(slotp * g.out_p_slots);
-    if (own_h0) {
-      g.h0[d] = A.f32(slotf);
-      g.h0_p[d] = A.raw(slotp);
-    }
     if (training) {
       g.hfin[d] = A.f32(slotf);
       for (int i = 0; i < 4; ++i) g.sv[d][i] = A.f32(slotf * steps);
@@ -294,40 +296,101 @@ struct JobQ {
   void flush() { launch_pack_jobs(jobs, st); }
 };
 
-static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
+// formats the FORWARD pass of a bi-GRU layer reads / formats only the backward pass reads
+static void pack_gru_fwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
   const int H = o.H, In = o.In;
   for (int d = 0; d < 2; ++d) {
     q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
-    q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
-    if (W.whh_rw[d]) {
-      q.whh_rw(P + o.whh[d], H, 0, W.whh_rw[d]);
-      q.whh_rw(P + o.whh[d], H, 1, W.whhT_rw[d]);
-    }
-    q.T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d]);                 // [In rows, K = 3H]
+    if (W.whh_rw[d]) q.whh_rw(P + o.whh[d], H, 0, W.whh_rw[d]);
     q.bias(P + o.bih[d], P + o.bhh[d], H, W.bias_gi + (size_t)d * 3 * H);
   }
   // both directions' W_ih are adjacent in the flat buffer -> one [6H, In] matrix; K split in wih_nseg column blocks
   const int Ks = In / W.wih_nseg;
   for (int s = 0; s < W.wih_nseg; ++s) q.rows(P + o.wih[0] + (long)s * Ks, In, 6 * H, Ks, 6 * H, W.wih_p[s]);
 }
+static void pack_gru_bwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
+  const int H = o.H, In = o.In;
+  for (int d = 0; d < 2; ++d) {
+    q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
+    if (W.whh_rw[d]) q.whh_rw(P + o.whh[d], H, 1, W.whhT_rw[d]);
+    q.T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d]);                 // [In rows, K = 3H]
+  }
+}
+static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
+  pack_gru_fwd(P, o, W, q);
+  pack_gru_bwd(P, o, W, q);
+}
 
-static void pack_all_weights(const vame_dims& d, const float* P, const PackedWeights& W, cudaStream_t st) {
+// everything except the forward formats of encoder layer 0 (first = false), or only those (first = true), or all (both)
+static void pack_weights_part(const vame_dims& d, const float* P, const PackedWeights& W, bool first, bool rest, cudaStream_t st) {
   const ParamLayout L = param_layout(d);
   const int H = d.hidden_enc, F = d.num_features, Z = d.zdims;
   JobQ q(st);
-  pack_gru_weights(P, L.e0, W.e0, q);
-  pack_gru_weights(P, L.e1, W.e1, q);
-  for (int i = 0; i < 4; ++i) q.rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i]);
-  q.T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p);
-  for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
-    const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
-    pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, q);
-    q.rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i]);
-    q.T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i]);
-    for (int dd = 0; dd < 2; ++dd) q.rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd]);
-    q.T(P + L.h2o_w[i], 2 * Hd, 2 * Hd, F, F, W.h2oT_p[i]);
+  if (first) pack_gru_fwd(P, L.e0, W.e0, q);
+  if (rest) {
+    pack_gru_bwd(P, L.e0, W.e0, q);
+    pack_gru_weights(P, L.e1, W.e1, q);
+    for (int i = 0; i < 4; ++i) q.rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i]);
+    q.T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p);
+    for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
+      const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
+      pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, q);
+      q.rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i]);
+      q.T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i]);
+      for (int dd = 0; dd < 2; ++dd) q.rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd]);
+      q.T(P + L.h2o_w[i], 2 * Hd, 2 * Hd, F, F, W.h2oT_p[i]);
+    }
   }
   q.flush();
+}
+static void pack_all_weights(const vame_dims& d, const float* P, const PackedWeights& W, cudaStream_t st) {
+  pack_weights_part(d, P, W, true, true, st);
+}
+
+// Deferred re-pack (vame_pack_weights_deferred): the formats the forward pass needs first are packed on the caller's stream,
+// the other ~95 % on a low-priority internal stream while the first encoder sweep (latency-bound, 128 of 148 SMs) is running;
+// the next vame_forward on that stream joins it right after it has enqueued that sweep.
+struct DeferredPack {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, done = nullptr;
+  bool pending = false;
+  vame_dims dims{};
+  const float* params = nullptr;
+  void* packed = nullptr;
+};
+static DeferredPack& deferred_pack() {
+  static DeferredPack D;
+  if (!D.s) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = least priority (numerically greatest)
+    cudaStreamCreateWithPriority(&D.s, cudaStreamNonBlocking, lo);
+    cudaEventCreateWithFlags(&D.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&D.done, cudaEventDisableTiming);
+  }
+  return D;
+}
+// Call order in encoder_forward: deferred_pack_fork(st) BEFORE the first sweep is enqueued (the rest of the re-pack becomes
+// runnable together with the sweep, not earlier - it would only compete with the input-projection GEMM), then the sweep, then
+// deferred_pack_run(st): the pack kernels are submitted behind the sweep on the low-priority stream and joined back into st.
+static inline void deferred_pack_fork(cudaStream_t st) {
+  DeferredPack& D = deferred_pack();
+  if (D.pending) cudaEventRecord(D.fork, st);
+}
+static inline void deferred_pack_run(cudaStream_t st) {
+  DeferredPack& D = deferred_pack();
+  if (!D.pending) return;
+  D.pending = false;
+  cudaStreamWaitEvent(D.s, D.fork, 0);
+  pack_weights_part(D.dims, D.params, packed_layout(D.dims, D.packed), false, true, D.s);
+  cudaEventRecord(D.done, D.s);
+  cudaStreamWaitEvent(st, D.done, 0);
+}
+// any other consumer of the packed weights: finish a pending deferred re-pack on its own stream first
+static inline void join_deferred_pack(cudaStream_t st) {
+  DeferredPack& D = deferred_pack();
+  if (!D.pending) return;
+  D.pending = false;
+  pack_weights_part(D.dims, D.params, packed_layout(D.dims, D.packed), false, true, st);
 }
 
 // ================================================================================================
@@ -586,7 +649,9 @@ static void encoder_forward(const vame_dims& d, const float* P, const ParamLayou
   GemmB().A(w.x_p, nkc_of(F), nkc_of(F)).Bm(W.e0.wih_p[0], nkc_of(F), nkc_of(F))
       .run_fm(rows, 6 * H, w.e0.gi, rows, W.e0.bias_gi, st);
   mark(st, "enc:x pack + gi0 gemm");
+  deferred_pack_fork(st);
   gru_sweep_fwd(W.e0, P + L.e0.bhh[0] + 2 * H, P + L.e0.bhh[1] + 2 * H, w.e0, w.tiles, save, true, st);
+  deferred_pack_run(st);                     // the rest of a deferred weight re-pack runs beside the sweep
   mark(st, "enc:L0 sweep");
   // layer 1: input = [out_f(t), out_b(t)] (rnn_model.py:41, inter-layer dropout is 0 by default)
   GemmB().A(w.e0.out_p[0], nkcH, nkcH).A(w.e0.out_p[1], nkcH, nkcH)
@@ -603,7 +668,12 @@ static void lambda_linear(const vame_dims& d, const float* P, const ParamLayout&
   GemmB gb;
   for (int i = 0; i < 4; ++i) gb.A(hp[i], nkcH, nkcH);
   for (int i = 0; i < 4; ++i) gb.Bm(W.lam_p[i], nkcH, nkcH);
-  gb.run(w.B, 2 * Z, w.lin, 2 * Z, P + L.lam_b, 0, 1, st);
+  // 2 output tiles x K = 4H: split-K over 8 CTAs per tile (red.add into the zeroed output) instead of a 16-chunk serial loop
+  cudaMemsetAsync(w.lin, 0, (size_t)w.B * 2 * Z * sizeof(float), st);
+  const int keep = g_side_sms;
+  g_side_sms = 148;
+  gb.run(w.B, 2 * Z, w.lin, 2 * Z, P + L.lam_b, 1, 8, st);
+  g_side_sms = keep;
 }
 
 static void decoder_forward(const vame_dims& d, int which, const float* P, const ParamLayout& L, const PackedWeights& W, Ws& w,
@@ -615,11 +685,14 @@ static void decoder_forward(const vame_dims& d, int which, const float* P, const
   DecBuf& D = w.dec[which];
   const int steps = D.g.steps, nkcZ = nkc_of(Z), nkcH = nkc_of(Hd);
   // hidden = latent_to_hidden(z); h0 = hidden.view(2, B, H)  (raw reinterpretation, rnn_model.py:102-104)
+  // the decoder input is z at every time step (rnn_model.py:169-170): one projection per sample - independent of the h0
+  // chain, so it runs beside it on a side stream that is idle during the forward pass
+  cudaStream_t sg = g_opt_streams ? side().s[which == 0 ? 1 : 3] : st;
+  edge(st, sg);
+  GemmB().A(w.z_p, nkcZ, nkcZ).Bm(Wg.wih_p[0], nkcZ, nkcZ).run_fm(Bp, 6 * Hd, D.g.gi, Bp, Wg.bias_gi, sg);
   GemmB().A(w.z_p, nkcZ, nkcZ).Bm(W.l2h_p[which], nkcZ, nkcZ).run(w.B, 2 * Hd, D.hid, 2 * Hd, P + L.l2h_b[which], 0, 1, st);
-  for (int dd = 0; dd < 2; ++dd)
-    launch_h0_prepare(D.hid + (size_t)dd * w.B * Hd, 1, w.B, Bp, Hd, D.g.h0[dd], D.g.h0_p[dd], st);
-  // the decoder input is z at every time step (rnn_model.py:169-170): one projection per sample
-  GemmB().A(w.z_p, nkcZ, nkcZ).Bm(Wg.wih_p[0], nkcZ, nkcZ).run_fm(Bp, 6 * Hd, D.g.gi, Bp, Wg.bias_gi, st);
+  launch_h0_prepare(D.hid, 2, w.B, Bp, Hd, D.g.h0[0], D.g.h0_p[0], st);
+  edge(sg, st);
   g_fwd_concurrent = (d.future_decoder && g_opt_streams) ? 2 : 1;
   gru_sweep_fwd(Wg, P + o.bhh[0] + 2 * Hd, P + o.bhh[1] + 2 * Hd, D.g, w.tiles, save, true, st);
   g_fwd_concurrent = 1;
@@ -691,6 +764,17 @@ int vame_pack_weights(const vame_dims* d, const float* params, void* packed, voi
   VB_REQUIRE(params && packed, "vame_pack_weights: null pointer");
   pack_all_weights(*d, params, packed_layout(*d, packed), (cudaStream_t)stream);
   return check_launch("vame_pack_weights");
+}
+
+int vame_pack_weights_deferred(const vame_dims* d, const float* params, void* packed, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(params && packed, "vame_pack_weights_deferred: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DeferredPack& D = deferred_pack();
+  pack_weights_part(*d, params, packed_layout(*d, packed), true, false, st);
+  D.dims = *d; D.params = params; D.packed = packed;
+  D.pending = true;
+  return check_launch("vame_pack_weights_deferred");
 }
 
 size_t vame_workspace_bytes(const vame_dims* d, int batch, int training) {
@@ -792,6 +876,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   Ws w = carve_ws(*d, batch, true, ws);
   VB_REQUIRE(ws_bytes >= w.bytes, "vame_backward: workspace too small (forward must have used save_for_backward)");
   cudaStream_t st = (cudaStream_t)stream;
+  join_deferred_pack(st);
   // sA: the future decoder's backward; sB: weight-gradient work that is not on the data-gradient chain
   cudaStream_t sA = g_opt_streams ? side().s[0] : st;
   cudaStream_t sB = g_opt_streams ? side().s[1] : st;
@@ -1092,6 +1177,7 @@ int vame_embed_windows(const vame_dims* d, const float* params, const void* pack
   VB_REQUIRE(ws_bytes >= w.bytes, "vame_embed_windows: workspace too small (see vame_embed_workspace_bytes)");
   if (n_windows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  join_deferred_pack(st);
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int nkcF = nkc_of(F), nkcH = nkc_of(H);
@@ -1154,6 +1240,7 @@ int vame_lambda_forward(const vame_dims* d, int batch, const float* params, cons
   Ws w = carve_ws(*d, batch, false, ws);
   VB_REQUIRE(ws_bytes >= w.bytes, "vame_lambda_forward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  join_deferred_pack(st);
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int H = d->hidden_enc, Z = d->zdims;
@@ -1175,6 +1262,7 @@ int vame_decoder_forward(const vame_dims* d, int batch, int which, const float* 
   Ws w = carve_ws(*d, batch, false, ws);
   VB_REQUIRE(ws_bytes >= w.bytes, "vame_decoder_forward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  join_deferred_pack(st);
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   pack_rows(z, d->zdims, w.B_pad, d->zdims, batch, w.z_p, st);

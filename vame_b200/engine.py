@@ -3,6 +3,7 @@ C-ABI (include/vame_b200.h) through ctypes.  PyTorch is used for device memory, 
 every FLOP of the hot path runs in libvame_b200.so.  There is no CPU fallback.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -339,12 +340,17 @@ class TrainStep:
         self.betas, self.adam_eps = betas, eps
         self.graphs = None
         self.use_graph = use_graph
+        self.defer_repack = os.environ.get("VAME_B200_DEFER_REPACK", "0") != "0"
         eng.init_optimizer()
         if cfg.bsize == 0:
             cfg.bsize = float(batch)
 
     def _phase1(self):
         e = self.eng
+        if self.defer_repack:
+            # weights updated by the previous step's optimizer kernel: re-pack what the first sweep needs now, the rest beside it
+            L.check(e.lib.vame_pack_weights_deferred(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), L.cur_stream()),
+                    "vame_pack_weights_deferred")
         e.forward(self.x, self.eps, save=True, want=(), ensure_packed=False)
         self.cfg.defer_prior_join = 1        # the k-means prior overlaps the decoder BPTT; vame_backward joins it
         e.loss(self.cfg, self.fut if self.cfg.with_future else None, want_grads=True, use_hyper=True, out=self.losses)
@@ -352,7 +358,8 @@ class TrainStep:
         self.cfg.defer_prior_join = 0
 
     def _phase2(self):
-        self.eng.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=True)
+        # with defer_repack the packed copies are refreshed at the start of the next step (and by _ensure_packed for any other caller)
+        self.eng.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=not self.defer_repack)
 
     def capture(self):
         """Warm up eagerly (also refreshes the packed weights), then capture both phases."""
@@ -407,4 +414,6 @@ class TrainStep:
             self.graphs[1].replay()
         else:
             self._phase2()
+        if self.defer_repack:
+            self.eng.mark_dirty()            # (a graph replay does not run adam_step's Python side)
         return self.losses
