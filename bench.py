@@ -235,14 +235,19 @@ def main():
     xh, eh = x.pin_memory(), eps.pin_memory()
     fh = xf.pin_memory() if fut else None
     loss_h = torch.zeros(8).pin_memory()
+    # the host batch of step i+1 is handed to TrainStep.load() right after step i has been enqueued: it is uploaded on a copy
+    # stream while step i computes; every timed step still contains one H2D of a full batch and one D2H of the loss vector
     for _ in range(3):
         ts.load(xh, fh, eh)
         ts.run()
     barrier()
     e0.record()
-    for _ in range(K):
-        ts.load(xh, fh, eh)
-        loss_h.copy_(ts.run(), non_blocking=True)
+    ts.load(xh, fh, eh)
+    for i in range(K):
+        out = ts.run()
+        if i + 1 < K:
+            ts.load(xh, fh, eh)
+        loss_h.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the caller consumes the loss every step
     e1.record()
     barrier()

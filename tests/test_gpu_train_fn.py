@@ -41,3 +41,40 @@ def test_train_and_test_epoch_match_reference(golden_dir):
     ret_t = rv.test(batches, 3, model, opt, 1, ret[0], 2 * T, "sum", Z, 0.1, True, B)
     for a, b in zip(ret_t, g["test_ret"]):
         assert abs(float(a) - b) <= 5e-3 * max(abs(b), 1e-3), (ret_t, g["test_ret"])
+
+
+def test_trainstep_staged_host_batches_match_device_batches():
+    """TrainStep.load() with pinned HOST tensors (copy stream + staging sets, uploads issued one step ahead) must give the same
+    losses and weights as device-resident batches."""
+    from oracle import vame_oracle as vo
+    from vame_b200.engine import Engine, TrainStep
+    T, Z, F, H, B = 12, 8, 10, 64, 48
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, False, 0, hidden=H)
+    batches = [vo.synthetic_batch(B, T, F, 1, Z, seed=30 + i) for i in range(4)]
+    results = []
+    for staged in (False, True):
+        eng = Engine(F, T, Z, H, H, H, False, 0, False, device="cuda")
+        eng.load_state_dict(port.state_dict())
+        cfg = eng.loss_cfg(kmeans_loss=Z, kmeans_lambda=0.1, bsize=B, beta=1.0, kl_weight=1.0)
+        eng.set_hyper(lr=5e-4, kl_weight=1.0, beta=1.0, kmeans_lambda=0.1)
+        ts = TrainStep(eng, B, cfg, world=1)
+        ts.capture()
+        losses = []
+        if staged:
+            host = [(x.pin_memory(), eps.pin_memory()) for x, _, eps in batches]
+            ts.load(host[0][0], None, host[0][1])
+            for i in range(len(host)):
+                out = ts.run()
+                if i + 1 < len(host):
+                    ts.load(host[i + 1][0], None, host[i + 1][1])      # uploaded while step i computes
+                losses.append(out.clone())
+        else:
+            for x, _, eps in batches:
+                ts.load(x.cuda(), None, eps.cuda())
+                losses.append(ts.run().clone())
+        torch.cuda.synchronize()
+        results.append((torch.stack(losses).cpu(), eng.flat.detach().cpu().clone()))
+    # (split-K accumulation uses red.add, so two runs agree to rounding, not bit for bit)
+    assert torch.allclose(results[0][0], results[1][0], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(results[0][1], results[1][1], rtol=0, atol=2e-6)

@@ -340,6 +340,7 @@ class TrainStep:
         self.betas, self.adam_eps = betas, eps
         self.graphs = None
         self.use_graph = use_graph
+        self._stage, self._staged, self._k_load = None, [], 0
         self.defer_repack = os.environ.get("VAME_B200_DEFER_REPACK", "0") != "0"
         eng.init_optimizer()
         if cfg.bsize == 0:
@@ -396,13 +397,53 @@ class TrainStep:
         return self.graphs is not None
 
     def load(self, x, fut, eps):
-        self.x.copy_(x, non_blocking=True)
-        if self.fut is not None and fut is not None:
-            self.fut.copy_(fut, non_blocking=True)
-        self.eps.copy_(eps, non_blocking=True)
+        """Stage the next batch.  Device tensors are copied into the static buffers on the current stream.  HOST tensors (pinned)
+        go through a copy stream into one of two staging sets, so that the upload of batch i+1 overlaps the compute of batch i
+        when the caller issues it before synchronising on step i; run() moves the staged set in with a device-to-device copy."""
+        if x.is_cuda:
+            self.x.copy_(x, non_blocking=True)
+            if self.fut is not None and fut is not None:
+                self.fut.copy_(fut, non_blocking=True)
+            self.eps.copy_(eps, non_blocking=True)
+            return
+        if self._stage is None:
+            self._stage = [dict(x=torch.empty_like(self.x), fut=None if self.fut is None else torch.empty_like(self.fut),
+                                eps=torch.empty_like(self.eps), ready=torch.cuda.Event(), free=None) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.eng.device)
+            self._staged = []
+        k = self._k_load
+        st = self._stage[k]
+        cs = self._copy_stream
+        with torch.cuda.stream(cs):
+            if st["free"] is not None:
+                cs.wait_event(st["free"])            # run() has moved the previous contents of this set into the static buffers
+            st["x"].copy_(x, non_blocking=True)
+            if st["fut"] is not None and fut is not None:
+                st["fut"].copy_(fut, non_blocking=True)
+            st["eps"].copy_(eps, non_blocking=True)
+            st["ready"].record(cs)
+        self._staged.append((k, fut is not None))
+        self._k_load ^= 1
+
+    def _take_staged(self):
+        if not self._staged:
+            return
+        k, has_fut = self._staged.pop(0)
+        st = self._stage[k]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(st["ready"])
+        self.x.copy_(st["x"], non_blocking=True)
+        if self.fut is not None and has_fut:
+            self.fut.copy_(st["fut"], non_blocking=True)
+        self.eps.copy_(st["eps"], non_blocking=True)
+        if st["free"] is None:
+            st["free"] = torch.cuda.Event()
+        st["free"].record(cur)
 
     def run(self):
         """Executes one step on the static buffers; returns the device loss vector."""
+        if self._staged:
+            self._take_staged()
         if self.graphs is not None:
             self.graphs[0].replay()
         else:
