@@ -1,8 +1,9 @@
 // Generic fp32-accurate GEMM on tcgen05 tensor cores:  C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias)
 // Operands are P16 (bf16 hi/lo split, UMMA canonical K-major tiles, see common.cuh).  A 128 x 128 output tile is
-// accumulated as  D[:, 0:128] += a * b_hi ,  D[:, 128:256] += a * b_lo  for a in {a_lo, a_hi}: the hi and lo planes of a
-// B tile are contiguous row groups, so ONE N = 256 descriptor covers both (two 128-cycle MMAs per 16-wide k-step; a
-// tcgen05.mma costs max(~45, N/2) cycles, tools/bench_mma) and the epilogue adds the two column halves.
+// accumulated as  D[:, 0:128] += a_hi * b_hi + a_lo * b_hi ,  D[:, 128:256] += a_hi * b_lo : the hi and lo planes of a
+// B tile are contiguous row groups, so ONE N = 256 descriptor covers both for the a_hi pass (128 cycles per 16-wide k-step)
+// and the a_lo pass uses the first 128 rows only (64 cycles); a tcgen05.mma costs max(~45, N/2) cycles (tools/bench_mma).
+// The epilogue adds the two column halves.  (The a_lo * b_lo products are below the split's own 2^-17 representation error.)
 //
 // Persistent, warp-specialised (the canonical Blackwell GEMM shape):
 //   warp 0      producer : whole P16 tiles with the TMA engine (cp.async.bulk) into a 3-stage smem ring (full/empty mbarriers)
@@ -19,6 +20,7 @@
 namespace vb {
 
 constexpr int G_BM = 128, G_BN = 128, G_STAGES = 3;
+constexpr bool g_gemm_lolo = false;                      // true: also accumulate a_lo x B_lo (4 products instead of 3)
 constexpr int G_TILE_BYTES = 128 * KCHUNK * 2 * 2;       // 32 KB (hi + lo)
 constexpr int G_STAGE_BYTES = 2 * G_TILE_BYTES;          // A + B
 constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 256;
@@ -103,6 +105,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
     // ===== MMA issuer =====
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(G_BM, 2 * G_BN);          // one descriptor spans [B_hi ; B_lo]
+      // the a_lo pass multiplies B_hi only (N = 128: same descriptor, half the columns): the lo x lo products are ~2^-18 of a
+      // term, below the 2^-17 representation error of the hi/lo split itself, and cost 25 % of the tensor time
+      const uint32_t idesc_lo = g_gemm_lolo ? idesc : make_idesc_bf16(G_BM, G_BN);
       const uint64_t dA0 = make_desc(smem_u32(smem));
       constexpr uint32_t plane = 128 * KCHUNK * 2;                     // bytes between hi and lo planes
       uint32_t it_global = 0, n_items = 0;
@@ -123,9 +128,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
 #pragma unroll
           for (int ks = 0; ks < KCHUNK / 16; ++ks) {
             const uint32_t ko = ks * 2 * ATOM_BYTES;                 // 16 k-elements = 2 atoms
-            if (ks == 0 && i == 0) umma_bf16_c<0>(dcol, desc_advance(dA, plane + ko), desc_advance(dB, ko), idesc);
-            else umma_bf16_c<1>(dcol, desc_advance(dA, plane + ko), desc_advance(dB, ko), idesc);
-            umma_bf16_c<1>(dcol, desc_advance(dA, ko), desc_advance(dB, ko), idesc);
+            // a_hi x [B_hi ; B_lo] first (it initialises all 256 columns), then a_lo x B_hi into columns 0-127
+            if (ks == 0 && i == 0) umma_bf16_c<0>(dcol, desc_advance(dA, ko), desc_advance(dB, ko), idesc);
+            else umma_bf16_c<1>(dcol, desc_advance(dA, ko), desc_advance(dB, ko), idesc);
+            umma_bf16_c<1>(dcol, desc_advance(dA, plane + ko), desc_advance(dB, ko), idesc_lo);
           }
           umma_commit(&empty[s]);                                    // frees the smem stage once these MMAs retire
         }
