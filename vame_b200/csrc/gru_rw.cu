@@ -141,6 +141,23 @@ __device__ __forceinline__ void rw_transpose_pack(const float* v, int lane, uint
 // byte offset of (row n of the 32-row operand, k) inside an operand buffer of RW_BTILE-sized k chunks; k % 8 == 0
 __device__ __forceinline__ uint32_t rw_b_off(int n, int k) { return (uint32_t)(k >> 6) * RW_BTILE + 2u * (uint32_t)p16_in_tile(n, k & 63); }
 
+// MN-major B operand of the H = 256 kernels (tcgen05 instruction-descriptor bit 16): inside every 8 x 8 core matrix the 8 batch
+// rows of ONE k (hidden unit / gate row) are the contiguous 16 bytes, core matrices of consecutive k-groups 128 B apart (LBO),
+// of consecutive 8-row groups 1024 B apart (SBO) - the K-major tile with its core matrices transposed.  A thread owns one unit
+// and 8 consecutive batch rows, so it writes its operand rows as ONE 16-byte vector per plane: no 8 x 8 shuffle transpose on
+// the recurrence (24 shuffles per operand in the K-major form).
+#ifndef RW_MN_FWD
+#define RW_MN_FWD 0      // the forward kernel keeps the K-major operand: with MN-major the store-warp variant faults on the B200
+#endif                   // (the variants without store warps pass; not understood yet - see DESIGN.md, open items)
+#ifndef RW_MN_BWD
+#define RW_MN_BWD 1
+#endif
+__host__ __device__ constexpr uint32_t rw_idesc(bool mn) { return make_idesc_bf16(128, 32) | (mn ? (1u << 16) : 0u); }
+// byte offset of (rows n0 .. n0+7 of the 32-row operand, k) inside an operand buffer of RW_BTILE-sized 64-k chunks
+__device__ __forceinline__ uint32_t rw_mn_off(int n0, int k) {
+  return (uint32_t)(k >> 6) * RW_BTILE + (uint32_t)((n0 >> 3) * 1024 + ((k & 63) >> 3) * 128 + (k & 7) * 16);
+}
+
 #define RW_STAMP(i)                                                                                          \
   do {                                                                                                        \
     if (a.dbg && s == 10 && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {      \
@@ -714,6 +731,7 @@ constexpr int RW_SW_THREADS = 288;             // + warps 5-8: store warps (SW k
 template <bool PRIV, bool SW>
 __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
+  constexpr bool RW_MN = RW_MN_FWD != 0;
   constexpr int NKC = 4, H = 256, UC = 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
@@ -787,9 +805,15 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         for (int i = 0; i < 8; ++i) hprev[i] = v[i];
       }
       uint4 hi, lo;
-      rw_transpose_pack(v, lane, hi, lo);
-      *reinterpret_cast<uint4*>(sH + rw_b_off(nrow, cc * UC + kloc)) = hi;
-      *reinterpret_cast<uint4*>(sH + rw_b_off(16 + nrow, cc * UC + kloc)) = lo;
+      if constexpr (RW_MN) {
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sH + rw_mn_off(8 * half, cc * UC + j)) = hi;
+        *reinterpret_cast<uint4*>(sH + rw_mn_off(16 + 8 * half, cc * UC + j)) = lo;
+      } else {
+        rw_transpose_pack(v, lane, hi, lo);
+        *reinterpret_cast<uint4*>(sH + rw_b_off(nrow, cc * UC + kloc)) = hi;
+        *reinterpret_cast<uint4*>(sH + rw_b_off(16 + nrow, cc * UC + kloc)) = lo;
+      }
     }
     fence_proxy_async_smem();
   }
@@ -804,7 +828,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
   cluster_arrive_release();
   cluster_wait_acquire();
 
-  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t idesc = rw_idesc(RW_MN);
   const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
   const long groups = Bp / 16;
   const bool gi_const = d.gi_ts == 0;                              // decoders: the input projection does not depend on t
@@ -824,6 +848,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
   auto gi_col = [&](int s_) -> uint32_t { const int b_ = s_ % 3; return taddr + (b_ == 0 ? 96u : b_ == 1 ? 168u : 232u); };
   auto gi_publish = [&](int s_, const float* r_, const float* z_, const float* n_) {   // store warps
     const uint32_t gc = gi_col(s_);
+    __syncwarp();
     tmem_st8(gc, r_);
     tmem_st8(gc + 8, z_);
     tmem_st8(gc + 16, n_);
@@ -977,23 +1002,31 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         hprev[i] = hn[i];
       }
       RW_STAMP(4);
-      rw_transpose_pack(hn, lane, phi, plo);
+      uint4 ohv, olv;                                               // this thread's operand vectors (hi / lo plane)
+      if constexpr (RW_MN) split8(hn, ohv, olv);
+      else {
+        rw_transpose_pack(hn, lane, phi, plo);
+        ohv = phi; olv = plo;
+      }
       tc_fence_before();
       if (s + 1 < steps) {                                        // own chunk of operand buffer (s + 1) & 1, then tell the MMA lane
         uint8_t* own = sH + (b ^ 1u) * NKC * RW_BTILE + c * RW_BTILE;
-        const uint32_t ohi = smem_u32(own) + 2u * p16_in_tile(nrow, kloc), olo = smem_u32(own) + 2u * p16_in_tile(16 + nrow, kloc);
+        const uint32_t o_hi = RW_MN ? rw_mn_off(8 * half, j) : 2u * p16_in_tile(nrow, kloc);
+        const uint32_t o_lo = RW_MN ? rw_mn_off(16 + 8 * half, j) : 2u * p16_in_tile(16 + nrow, kloc);
+        const uint32_t ohi = smem_u32(own) + o_hi, olo = smem_u32(own) + o_lo;
         const uint32_t hbar = smem_u32(&hfull[b ^ 1u]);
 #pragma unroll
         for (uint32_t r = 1; r < 4; ++r) {                          // the same chunk position in the three peers' buffers
           const uint32_t peer = (c + r) & 3, pbar = mapa_u32(hbar, peer);
-          st_async_v4(mapa_u32(ohi, peer), phi, pbar);
-          if (!(a.exp & 8)) st_async_v4(mapa_u32(olo, peer), plo, pbar);
+          st_async_v4(mapa_u32(ohi, peer), ohv, pbar);
+          if (!(a.exp & 8)) st_async_v4(mapa_u32(olo, peer), olv, pbar);
         }
-        *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(nrow, kloc)) = phi;
-        *reinterpret_cast<uint4*>(own + 2 * p16_in_tile(16 + nrow, kloc)) = plo;
+        *reinterpret_cast<uint4*>(own + o_hi) = ohv;
+        *reinterpret_cast<uint4*>(own + o_lo) = olv;
         fence_proxy_async_smem();
         mbar_arrive(&lfull[b ^ 1u]);
       }
+      if constexpr (RW_MN && !SW) rw_transpose_pack(hn, lane, phi, plo);   // K-major P16 copy for the GEMMs (off the recurrence)
       RW_STAMP(5);
       if (tid == 0) RW_STAMP_CTA(2);
       if (tid == 96) RW_STAMP_CTA(3);
@@ -1006,6 +1039,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
       if constexpr (SW) {                                           // hand h_t and the saved gates to the store warps
         const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
         if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 16);
+        __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
         tmem_st8(stg, hn);
         tmem_st8(stg + 8, sr);
@@ -1063,6 +1097,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
 template <bool SUM, bool PRIV, bool SW>
 __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
+  constexpr bool RW_MN = RW_MN_BWD != 0;
   constexpr int NKC = 4, H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
   constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
   static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
@@ -1129,7 +1164,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
   const long b0 = (long)blockIdx.y * 16 + 8 * half;
   const int nrow = 8 * half + (lane & 7);
   const int kq = 16 * (q & 3) + 8 * oct;
-  const uint32_t idesc = make_idesc_bf16(128, 32);
+  const uint32_t idesc = rw_idesc(RW_MN);
   const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
 
   float carry[8], own[8];
@@ -1278,15 +1313,27 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       }
       epi_bar_sync();                                             // everyone has consumed rprev before it becomes the operand
       uint4 rhi, rlo, zhi, zlo, ghi, glo;
-      rw_transpose_pack(dar, lane, rhi, rlo);
-      rw_transpose_pack(daz, lane, zhi, zlo);
-      rw_transpose_pack(dgn, lane, ghi, glo);
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
-      *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
+      if constexpr (RW_MN) {
+        split8(dar, rhi, rlo);
+        split8(daz, zhi, zlo);
+        split8(dgn, ghi, glo);
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, j)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, j)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, UC + j)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, UC + j)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, 2 * UC + j)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, 2 * UC + j)) = glo;
+      } else {
+        rw_transpose_pack(dar, lane, rhi, rlo);
+        rw_transpose_pack(daz, lane, zhi, zlo);
+        rw_transpose_pack(dgn, lane, ghi, glo);
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ofull);
@@ -1340,6 +1387,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       if constexpr (SW) {                                           // hand the gate gradients to the store warps
         const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
         if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 27);
+        __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
         tmem_st8(stg, dar);
         tmem_st8(stg + 8, daz);
@@ -1372,6 +1420,10 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
         if (d.dgi_p) {
           uint4 nhi, nlo;
           rw_transpose_pack(dan, lane, nhi, nlo);
+          if constexpr (RW_MN) {                                    // the K-major P16 copy for the dx GEMM (off the recurrence)
+            rw_transpose_pack(dar, lane, rhi, rlo);
+            rw_transpose_pack(daz, lane, zhi, zlo);
+          }
           constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
           const long row = (long)blockIdx.y * 16 + nrow;
           __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
