@@ -98,6 +98,11 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
  * losses_out: device float[8] = {rec, fut, kl, kmeans, total, 0, 0, 0}. */
 /* target: optional [B, T, F] reconstruction target when it differs from the forward input (cfg['noise'], rnn_vae.py:116-124:
  * the model sees x + noise, the loss compares against the clean x); NULL = the forward input. */
+/* Optional, for the train loop: with a cfg armed, the next vame_forward(save_for_backward = 1) calls start the k-means prior
+ * (cluster_loss, rnn_vae.py:45-50) of THAT cfg / hyper on an internal stream as soon as z exists, and the vame_loss that
+ * follows (same cfg, want_grads = 1) uses it instead of launching its own.  cfg = NULL disarms.  Host-side state only. */
+int vame_arm_prior(const vame_loss_cfg* cfg, const float* hyper);
+
 int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const float* fut, long f_bs, long f_ts,
               const float* target, long t_bs, long t_ts, const float* hyper, float* losses_out, int want_grads, void* ws,
               size_t ws_bytes, void* stream);

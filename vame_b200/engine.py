@@ -342,6 +342,7 @@ class TrainStep:
         self.use_graph = use_graph
         self._stage, self._staged, self._k_load = None, [], 0
         self.defer_repack = os.environ.get("VAME_B200_DEFER_REPACK", "0") != "0"
+        self.early_prior = os.environ.get("VAME_B200_EARLY_PRIOR", "1") != "0"
         eng.init_optimizer()
         if cfg.bsize == 0:
             cfg.bsize = float(batch)
@@ -352,8 +353,18 @@ class TrainStep:
             # weights updated by the previous step's optimizer kernel: re-pack what the first sweep needs now, the rest beside it
             L.check(e.lib.vame_pack_weights_deferred(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), L.cur_stream()),
                     "vame_pack_weights_deferred")
-        e.forward(self.x, self.eps, save=True, want=(), ensure_packed=False)
-        self.cfg.defer_prior_join = 1        # the k-means prior overlaps the decoder BPTT; vame_backward joins it
+        # the k-means prior starts as soon as z exists (inside vame_forward), overlaps the decoders, the losses and the decoder
+        # BPTT, and is joined by vame_backward right before the Lambda backward
+        self.cfg.defer_prior_join = 1
+        if self.cfg.bsize == 0:
+            self.cfg.bsize = float(self.B)
+        if self.early_prior:
+            L.check(e.lib.vame_arm_prior(ctypes.byref(self.cfg), L.ptr(e.hyper)), "vame_arm_prior")
+        try:
+            e.forward(self.x, self.eps, save=True, want=(), ensure_packed=False)
+        finally:
+            if self.early_prior:
+                e.lib.vame_arm_prior(None, None)
         e.loss(self.cfg, self.fut if self.cfg.with_future else None, want_grads=True, use_hyper=True, out=self.losses)
         e.backward(self.cfg, use_hyper=True)
         self.cfg.defer_prior_join = 0
