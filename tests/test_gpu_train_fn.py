@@ -77,4 +77,7 @@ def test_trainstep_staged_host_batches_match_device_batches():
         results.append((torch.stack(losses).cpu(), eng.flat.detach().cpu().clone()))
     # (split-K accumulation uses red.add, so two runs agree to rounding, not bit for bit)
     assert torch.allclose(results[0][0], results[1][0], rtol=1e-5, atol=1e-5)
-    assert torch.allclose(results[0][1], results[1][1], rtol=0, atol=2e-6)
+    # AMSGrad moves a weight by ~lr whatever the size of its gradient, so elements with near-zero gradients amplify rounding
+    # differences: same criterion as the reference comparison above (almost all weights equal, none off by more than 4 steps of lr)
+    err = (results[0][1] - results[1][1]).abs()
+    assert float((err > 1e-5).float().mean()) <= 1e-3 and float(err.max()) <= 4 * 5e-4 + 1e-6

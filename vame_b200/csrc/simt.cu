@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
     __syncthreads();
     double dmax = 0;
     for (int i = 0; i < n; ++i) dmax = fmax(dmax, fabs(Acur[i][i]));
-    if (offmax <= 1e-14 * dmax || offmax == 0) break;      // eigenvalue error ~ off^2 / gap: far below fp32 resolution
+    // eigenvalue error ~ off^2 / gap, eigenvector error ~ off / gap: 1e-11 is far below fp32 resolution for both, and the
+    // quadratically convergent tail (... 1e-6, 1e-12, 1e-24) then stops one sweep (~34 us) earlier than with 1e-14
+    // (a rank-deficient Gram, B < Z, keeps the tight threshold: its null-space eigenvalues enter the gradient as 1/sqrt)
+    if (offmax <= (B < Z ? 1e-14 : 1e-11) * dmax || offmax == 0) break;
     for (int round = 0; round < n - 1; ++round) {
       if (tid < half) {
         // circle method: player n-1 fixed, the others rotate

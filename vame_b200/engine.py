@@ -390,12 +390,20 @@ class TrainStep:
                     self._phase2()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._phase1()
-            with torch.cuda.graph(g2):
-                self._phase2()
-            self.graphs = (g1, g2)
+            if self.world == 1:
+                # single GPU: nothing happens between the phases -> ONE graph (one launch instead of two per step)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._phase1()
+                    self._phase2()
+                self.graphs = (g1, None)
+            else:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._phase1()
+                with torch.cuda.graph(g2):
+                    self._phase2()
+                self.graphs = (g1, g2)
         except Exception as ex:      # capture is an optimisation; eager launches are the same kernels
             self.graphs = None
             self.capture_error = repr(ex)
@@ -463,7 +471,8 @@ class TrainStep:
             import torch.distributed as dist
             dist.all_reduce(self.eng.grad, op=dist.ReduceOp.SUM)
         if self.graphs is not None:
-            self.graphs[1].replay()
+            if self.graphs[1] is not None:
+                self.graphs[1].replay()
         else:
             self._phase2()
         if self.defer_repack:
