@@ -77,6 +77,11 @@ long vame_param_layout(const vame_dims* d, long* offsets, long* sizes);
 /* bf16 hi/lo tensor-core copies of the weights; must be refreshed after every parameter update */
 size_t vame_packed_weights_bytes(const vame_dims* d);
 int vame_pack_weights(const vame_dims* d, const float* params, void* packed, void* stream);
+/* Re-pack for a train loop with a fixed batch size: the W_hh formats that only the kernels for OTHER batch sizes read are
+ * skipped (at B <= 512, H = 256 the sweeps run on the resident-weight cluster kernels; the slice-kernel formats are ~40 % of
+ * the re-pack).  `packed` is then valid for vame_forward / vame_backward at that batch size only - call vame_pack_weights
+ * before anything else uses it (vame_b200.engine marks the copies dirty). */
+int vame_pack_weights_train(const vame_dims* d, const float* params, void* packed, int batch, void* stream);
 /* Same result, for the train loop: only the formats the forward pass reads first (encoder layer 0) are packed now, on
  * `stream`; the rest is packed by the NEXT vame_forward (same params / packed pointers, which must stay valid until then) on a
  * low-priority internal stream beside its first recurrent sweep.  Any other entry point that reads `packed` completes the

@@ -30,6 +30,7 @@ SIGNATURES = {
     "vame_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_pack_weights_deferred": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_arm_prior": (c_int, [c_void_p, c_void_p]),
+    "vame_pack_weights_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vame_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vame_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -21,6 +21,7 @@ struct GruBuf {
   void* out_p[2]; int out_p_slots;      // P16 h sequence [slots][tiles][nkc]
   float* sv[2][4];
   float* h0[2]; void* h0_p[2];          // initial state (zeros for the encoder)
+  bool dout_pv = false;                 // the upstream gradient of the per-step outputs was written in the lane-major block layout
   float* dgi[2]; float* dgh[2]; void* dgi_p[2];
   float* parts[2];
   int parts_n;                          // partial-sum slots that hold the final dh0 after the last backward sweep (1 after an rw sweep)
@@ -243,6 +244,11 @@ struct GemmB {
     g.c_fm = 1;
     run(M, N, C, ldc, bias, 0, 1, st);
   }
+  // feature-major planes of 256 features, each permuted into the lane-major blocks of the H = 256 rw sweeps (rows = t*Bp + b)
+  void run_pv(int M, int N, float* C, long ldc, int Bp, cudaStream_t st) {
+    g.c_fm = 2; g.pv_bp = Bp;
+    run(M, N, C, ldc, nullptr, 0, 1, st);
+  }
 };
 // plain (non-transposed) pack of a row-major [R_src, K] matrix into P16 with R rows (zero padded)
 static inline void pack_rows(const float* src, long ld, int R, int K, int R_src, void* out, cudaStream_t st) {
@@ -297,10 +303,12 @@ struct JobQ {
 };
 
 // formats the FORWARD pass of a bi-GRU layer reads / formats only the backward pass reads
-static void pack_gru_fwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
+// slices = false: skip the W_hh formats of the slice kernels (gru.cu) - the caller knows that the sweeps of this batch size run
+// on the resident-weight kernels (vame_pack_weights_train)
+static void pack_gru_fwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q, bool slices = true) {
   const int H = o.H, In = o.In;
   for (int d = 0; d < 2; ++d) {
-    q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
+    if (slices || !W.whh_rw[d]) q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
     if (W.whh_rw[d]) q.whh_rw(P + o.whh[d], H, 0, W.whh_rw[d]);
     q.bias(P + o.bih[d], P + o.bhh[d], H, W.bias_gi + (size_t)d * 3 * H);
   }
@@ -308,33 +316,37 @@ static void pack_gru_fwd(const float* P, const GruOff& o, const GruPacked& W, Jo
   const int Ks = In / W.wih_nseg;
   for (int s = 0; s < W.wih_nseg; ++s) q.rows(P + o.wih[0] + (long)s * Ks, In, 6 * H, Ks, 6 * H, W.wih_p[s]);
 }
-static void pack_gru_bwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
+static void pack_gru_bwd(const float* P, const GruOff& o, const GruPacked& W, JobQ& q, bool slices = true) {
   const int H = o.H, In = o.In;
   for (int d = 0; d < 2; ++d) {
-    q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
+    if (slices || !W.whhT_rw[d]) q.whh(P + o.whh[d], H, 1, W.whhT_p[d]);
     if (W.whh_rw[d]) q.whh_rw(P + o.whh[d], H, 1, W.whhT_rw[d]);
     q.T(P + o.wih[d], In, In, 3 * H, 3 * H, W.wihT_p[d]);                 // [In rows, K = 3H]
   }
 }
-static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, JobQ& q) {
-  pack_gru_fwd(P, o, W, q);
-  pack_gru_bwd(P, o, W, q);
+static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W, JobQ& q, bool slices = true) {
+  pack_gru_fwd(P, o, W, q, slices);
+  pack_gru_bwd(P, o, W, q, slices);
 }
 
 // everything except the forward formats of encoder layer 0 (first = false), or only those (first = true), or all (both)
-static void pack_weights_part(const vame_dims& d, const float* P, const PackedWeights& W, bool first, bool rest, cudaStream_t st) {
+static void pack_weights_part(const vame_dims& d, const float* P, const PackedWeights& W, bool first, bool rest, cudaStream_t st,
+                              int train_batch = 0) {
   const ParamLayout L = param_layout(d);
   const int H = d.hidden_enc, F = d.num_features, Z = d.zdims;
+  // train_batch > 0: formats of the slice kernels are skipped for the layers whose sweeps run on the rw kernels at that batch
+  const int tiles = train_batch > 0 ? pad128(train_batch) / 128 : 0;
+  auto slices_of = [&](int Hl) { return !(tiles > 0 && g_opt_rw == 3 && rw_applicable(Hl, tiles)); };
   JobQ q(st);
-  if (first) pack_gru_fwd(P, L.e0, W.e0, q);
+  if (first) pack_gru_fwd(P, L.e0, W.e0, q, slices_of(H));
   if (rest) {
-    pack_gru_bwd(P, L.e0, W.e0, q);
-    pack_gru_weights(P, L.e1, W.e1, q);
+    pack_gru_bwd(P, L.e0, W.e0, q, slices_of(H));
+    pack_gru_weights(P, L.e1, W.e1, q, slices_of(H));
     for (int i = 0; i < 4; ++i) q.rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i]);
     q.T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p);
     for (int i = 0; i < (d.future_decoder ? 2 : 1); ++i) {
       const int Hd = i == 0 ? d.hidden_rec : d.hidden_pred;
-      pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, q);
+      pack_gru_weights(P, i == 0 ? L.dec : L.fut, i == 0 ? W.dec : W.fut, q, slices_of(Hd));
       q.rows(P + L.l2h_w[i], Z, 2 * Hd, Z, 2 * Hd, W.l2h_p[i]);
       q.T(P + L.l2h_w[i], Z, Z, 2 * Hd, 2 * Hd, W.l2hT_p[i]);
       for (int dd = 0; dd < 2; ++dd) q.rows(P + L.h2o_w[i] + (long)dd * Hd, 2 * Hd, F, Hd, F, W.h2o_p[i][dd]);
@@ -538,6 +550,7 @@ static bool gru_sweep_bwd(const GruPacked& W, GruBuf& L, int tiles, const float*
       D.dgi = L.dgi[d]; D.dgh = L.dgh[d]; D.dg_ld = seq_ld;
       D.dgi_p = L.dgi_p[d]; D.dgi_p_slot_elems = (long)tiles * nkc3 * (long)p16_tile_elems(128);
       D.priv = (rw && L.priv && goff && G) ? 1 : 0;
+      D.dout_pv = (D.priv && L.dout_pv) ? 1 : 0;
       D.dghT_p = L.dghT_p[d]; D.dgiT_p = L.dgiT_p[d]; D.gT_nk = seq_ld / KCHUNK;
       D.db_ih = G ? G + goff->bih[d] : nullptr; D.db_hh = G ? G + goff->bhh[d] : nullptr;
       D.dgi_sum = dgi_sum ? dgi_sum[d] : nullptr;
@@ -766,6 +779,13 @@ int vame_pack_weights(const vame_dims* d, const float* params, void* packed, voi
   return check_launch("vame_pack_weights");
 }
 
+int vame_pack_weights_train(const vame_dims* d, const float* params, void* packed, int batch, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(params && packed && batch > 0, "vame_pack_weights_train: null pointer / empty batch");
+  pack_weights_part(*d, params, packed_layout(*d, packed), true, true, (cudaStream_t)stream, batch);
+  return check_launch("vame_pack_weights_train");
+}
+
 int vame_pack_weights_deferred(const vame_dims* d, const float* params, void* packed, void* stream) {
   if (check_dims(d)) return -1;
   VB_REQUIRE(params && packed, "vame_pack_weights_deferred: null pointer");
@@ -963,7 +983,9 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     // ---- data-gradient chain: hidden_to_output backward, BPTT, dz
     cudaMemsetAsync(D.dz, 0, (size_t)B * Z * 4, sd);                      // accumulated by the split-K dz GEMM after the sweep
     pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);
-    GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_fm((int)rows, 2 * Hd, D.ddec, rows, nullptr, sd);
+    D.g.dout_pv = D.g.priv && Hd == 256 && rw_priv_mode(Hd, w.tiles);
+    if (D.g.dout_pv) GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_pv((int)rows, 2 * Hd, D.ddec, rows, Bp, sd);
+    else GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_fm((int)rows, 2 * Hd, D.ddec, rows, nullptr, sd);
     if (i == 0) mark(st, "bwd:dec dpred pack + ddec gemm");
     {   // weight-gradient operands that only need the forward pass and dpred: packed on sw while the sweep runs
       edge(sd, sw);
@@ -1059,8 +1081,13 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   if (g_opt_streams) g_side_sms = side_total / 2;
   edge(st, sB);
   edge(st, sC);
-  GemmB().A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3)
-      .run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
+  w.e0.dout_pv = w.e0.priv && H == 256 && rw_priv_mode(H, w.tiles);
+  {
+    GemmB gb;
+    gb.A(w.e1.dgi_p[0], nkc3, nkc3).A(w.e1.dgi_p[1], nkc3, nkc3).Bm(W.e1.wihT_p[0], nkc3, nkc3).Bm(W.e1.wihT_p[1], nkc3, nkc3);
+    if (w.e0.dout_pv) gb.run_pv((int)rows, 2 * H, w.dx1, rows, Bp, st);
+    else gb.run_fm((int)rows, 2 * H, w.dx1, rows, nullptr, st);
+  }
   gru_recurrent_grads(L.e1, w.e1, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l1)[dd][:, e*H:(e+1)*H] = dgi1[dd]^T out0[e]
     if (!w.e1.priv) launch_pack_p16_rowsum(w.e1.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e1.dgiT_p[dd], G + L.e1.bih[dd], sdir[dd]);

@@ -191,7 +191,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_p16_kernel(const GemmArgs g
             // now (a0, a1, a2, a3) = column j4 + r of rows 4g, 4g+1, 4g+2, 4g+3
             const int cj = col + j4 + r;
             const int row4 = it.mb * G_BM + q * 32 + (lane & ~3);
-            if (cj < g.N && row4 < g.M) *reinterpret_cast<float4*>(g.C + (long)cj * g.ldc + row4) = make_float4(a0, a1, a2, a3);
+            if (cj < g.N && row4 < g.M) {
+              long off = (long)cj * g.ldc + row4;
+              if (g.c_fm == 2) {          // same plane, permuted into the rw sweeps' lane-major blocks
+                const int u = cj & 255, t = row4 / g.pv_bp, b = row4 - t * g.pv_bp;
+                const long blk = ((((long)t * (g.pv_bp >> 4) + (b >> 4)) * 4 + (u >> 6)) * 4 + ((u & 63) >> 4)) * 256;
+                off = (long)(cj >> 8) * 256 * g.ldc + blk + ((u & 15) + 16 * ((b & 15) >> 3)) * 8 + (b & 7);
+              }
+              *reinterpret_cast<float4*>(g.C + off) = make_float4(a0, a1, a2, a3);
+            }
           }
         } else if (g.c_fm) {                // feature-major output: C[n*ldc + m]; lanes (= rows m) are contiguous -> coalesced
           if (row < g.M) {

@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
       }
     } else {
       float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
-      uint4 phi, plo;
+      uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
       if (gi_tmem) {                                                // this step's input projections (published >= 1 step ago)
         mbar_wait_warp(&gfull[s % 3], (s / 3) & 1, 19);
         tc_fence_after();
@@ -1098,7 +1098,7 @@ template <bool SUM, bool PRIV, bool SW>
 __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
   constexpr bool RW_MN = RW_MN_BWD != 0;
-  constexpr int NKC = 4, H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
+  constexpr int H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
   constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
   static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1198,7 +1198,10 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
       else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
     }
-    if (d.dout) ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
+    if (d.dout) {
+      if (PRIV && d.dout_pv) ld8p(d.dout + pv_block(t, bpad / 16, blockIdx.y, c, q), lane, dh);
+      else ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
+    }
     else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] = 0.f;

@@ -66,7 +66,9 @@ struct GemmArgs {
   int M, N;             // logical output extent (rows >= M / cols >= N are masked)
   float* C;             // fp32 row-major (C[m*ldc + n]) or, with c_fm, feature-major (C[n*ldc + m])
   long ldc;
-  int c_fm;
+  int c_fm;             // 1: feature-major; 2: feature-major planes of 256 features in the lane-major blocks of the H = 256 rw
+                        //    sweeps ([t][16-row group][64-unit CTA][16-unit warp][lane][8 rows], gru_rw.cu pv_block), rows = t*pv_bp + b
+  int pv_bp;            // padded batch (c_fm == 2)
   const float* bias;    // [N] or nullptr (added only by split 0)
   int atomic;           // 1: red.add into C (split-K / accumulation), 0: plain store
   int splits;           // k splits (work items = tiles x splits)
@@ -130,7 +132,12 @@ struct GruSeqFwdArgs {
   GruSeqDirFwd d[2];
   int ndir, H, tiles, steps;
   unsigned long long* dbg;   // optional %globaltimer stamps of step 10 (filled in by the launcher)
-  int exp;                   // measurement experiments only (option "rw_exp", results become wrong): skip stores / loads
+  // Measurement experiments of the H = 256 rw kernels (option "rw_exp", tools/gpu_probe_sweeps.py; results become WRONG unless
+  // noted): 1 skip out / saved-gate stores (non-private path), 2 skip the input-projection loads, 4 skip the P16 h stores
+  // (non-private path), 8 push only the hi plane, 16 skip every global store, 32 per-CTA %globaltimer stamps (results
+  // stay right), 64 (BPTT) skip the saved-activation loads, 128 (BPTT) release instead of relaxed remote arrive (results
+  // stay right).  What they showed is summarised in DESIGN.md section 4.1.
+  int exp;
 };
 void launch_gru_seq_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 
@@ -152,6 +159,7 @@ struct GruSeqDirBwd {
   // private mode (see GruSeqDirFwd): sv / out are read in the lane-major layout; instead of fp32 dgi / dgh the kernel writes the
   // transposed P16 operands of the weight-gradient GEMMs and adds the bias gradients (sums over t and b) into db_ih / db_hh
   int priv;
+  int dout_pv;                                 // dout is in the lane-major block layout (GemmArgs::c_fm == 2): one coalesced 256-bit load
   void* dghT_p; void* dgiT_p; long gT_nk;      // P16 [3H rows, K = steps * B_pad] (dgiT_p may be nullptr), nk = K / 64
   float* db_ih; float* db_hh;                  // [3H] each, accumulated with atomicAdd
   int reverse;                                 // direction of the FORWARD recurrence (0: t ascending) -> BPTT runs the other way

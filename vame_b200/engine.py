@@ -371,7 +371,12 @@ class TrainStep:
 
     def _phase2(self):
         # with defer_repack the packed copies are refreshed at the start of the next step (and by _ensure_packed for any other caller)
-        self.eng.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=not self.defer_repack)
+        e = self.eng
+        e.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=False)
+        if not self.defer_repack:
+            # only the weight formats a step of THIS batch size reads; any other consumer re-packs everything (mark_dirty in run())
+            L.check(e.lib.vame_pack_weights_train(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), self.B, L.cur_stream()),
+                    "vame_pack_weights_train")
 
     def capture(self):
         """Warm up eagerly (also refreshes the packed weights), then capture both phases."""
@@ -475,6 +480,5 @@ class TrainStep:
                 self.graphs[1].replay()
         else:
             self._phase2()
-        if self.defer_repack:
-            self.eng.mark_dirty()            # (a graph replay does not run adam_step's Python side)
+        self.eng.mark_dirty()                # partial re-pack (and: a graph replay does not run adam_step's Python side)
         return self.losses
