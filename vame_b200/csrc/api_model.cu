@@ -656,8 +656,7 @@ static void encoder_forward(const vame_dims& d, const float* P, const ParamLayou
     w.e0.h0[dd] = w.zeros_f32; w.e0.h0_p[dd] = w.zeros_p;
     w.e1.h0[dd] = w.zeros_f32; w.e1.h0_p[dd] = w.zeros_p;
   }
-  launch_bt_to_tb(x, w.B, T, F, x_bs, x_ts, Bp, w.x_tb, st);
-  pack_rows(w.x_tb, F, rows, F, rows, w.x_p, st);
+  launch_bt_to_tb_p16(x, w.B, T, F, x_bs, x_ts, Bp, w.x_tb, w.x_p, st);     // time-major copy + its P16 operand in one pass
   // layer 0: gi = x W_ih^T + (b_ih + [b_hr, b_hz, 0]) for both directions at once
   GemmB().A(w.x_p, nkc_of(F), nkc_of(F)).Bm(W.e0.wih_p[0], nkc_of(F), nkc_of(F))
       .run_fm(rows, 6 * H, w.e0.gi, rows, W.e0.bias_gi, st);
@@ -842,8 +841,7 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
   const void* hp[4] = {final_h_p(w.e0, 0, w.tiles), final_h_p(w.e0, 1, w.tiles), final_h_p(w.e1, 0, w.tiles), final_h_p(w.e1, 1, w.tiles)};
   lambda_linear(*d, params, L, W, w, hp, st);
   if (eps) cudaMemcpyAsync(w.eps, eps, (size_t)batch * Z * 4, cudaMemcpyDeviceToDevice, st);
-  launch_lambda_fwd(w.lin, 2 * Z, eps ? w.eps : nullptr, batch, Z, d->softplus, w.z, w.mu, w.logvar, w.acc, st);
-  pack_rows(w.z, Z, w.B_pad, Z, batch, w.z_p, st);
+  launch_lambda_fwd_p16(w.lin, 2 * Z, eps ? w.eps : nullptr, batch, w.B_pad, Z, d->softplus, w.z, w.mu, w.logvar, w.acc, w.z_p, st);
   {
     ArmedPrior& A = armed_prior();
     A.inflight = false;
@@ -898,15 +896,24 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
     launch_bt_to_tb(target, batch, T, F, t_bs, t_ts, Bp, w.dec[0].target_tb, st);
     rec_target = w.dec[0].target_tb;
   }
-  launch_mse(w.dec[0].pred_tb, F, rec_target, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
-             training ? w.dec[0].dpred_tb : nullptr, w.acc, ACC_REC, st);
+  // training: the gradient is also written as the P16 operand of the hidden_to_output backward GEMM (vame_backward)
+  if (training)
+    launch_mse_p16(w.dec[0].pred_tb, F, rec_target, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f,
+                   w.dec[0].dpred_tb, w.acc, ACC_REC, w.dec[0].dpred_p, st);
+  else
+    launch_mse(w.dec[0].pred_tb, F, rec_target, T * Bp, batch, Bp, F, cfg->mse_red_mean ? (float)(2.0 / nrec) : 2.0f, nullptr, w.acc,
+               ACC_REC, st);
   double nfut = 1.0;
   if (with_fut) {
     const int S = d->future_steps;
     nfut = (double)batch * S * F;
     launch_bt_to_tb(fut, batch, S, F, f_bs, f_ts, Bp, w.dec[1].target_tb, st);
-    launch_mse(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f,
-               training ? w.dec[1].dpred_tb : nullptr, w.acc, ACC_FUT, st);
+    if (training)
+      launch_mse_p16(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f,
+                     w.dec[1].dpred_tb, w.acc, ACC_FUT, w.dec[1].dpred_p, st);
+    else
+      launch_mse(w.dec[1].pred_tb, F, w.dec[1].target_tb, S * Bp, batch, Bp, F, cfg->mse_pred_mean ? (float)(2.0 / nfut) : 2.0f, nullptr,
+                 w.acc, ACC_FUT, st);
   }
   if (training && cfg->defer_prior_join && g_opt_streams) {
     // the prior keeps running on sA while the caller's stream proceeds into vame_backward (which joins sA before the
@@ -982,7 +989,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     if (!use_loss_grads) launch_bt_to_tb(ext, B, steps, F, (long)steps * F, F, Bp, D.dpred_tb, sd);
     // ---- data-gradient chain: hidden_to_output backward, BPTT, dz
     cudaMemsetAsync(D.dz, 0, (size_t)B * Z * 4, sd);                      // accumulated by the split-K dz GEMM after the sweep
-    pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);
+    if (!use_loss_grads) pack_rows(D.dpred_tb, F, (int)rows, F, (int)rows, D.dpred_p, sd);   // (vame_loss wrote it already)
     D.g.dout_pv = D.g.priv && Hd == 256 && rw_priv_mode(Hd, w.tiles);
     if (D.g.dout_pv) GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_pv((int)rows, 2 * Hd, D.ddec, rows, Bp, sd);
     else GemmB().A(D.dpred_p, nkcF, nkcF).Bm(W.h2oT_p[i], nkcF, nkcF).run_fm((int)rows, 2 * Hd, D.ddec, rows, nullptr, sd);
@@ -1048,11 +1055,10 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     a.c_kl = use_loss_grads ? cfg->beta * cfg->kl_weight / (float)((long)B * Z) : 0.f;
     a.B = B; a.B_pad = Bp; a.Z = Z; a.softplus = d->softplus;
     a.dlin = w.dlin; a.ldd = 2 * Z;
-    launch_lambda_bwd(a, st);
+    launch_lambda_bwd_p16(a, w.dlin_p, st);            // dlin and its P16 copy for the dhidden GEMM
   }
   const int nkc2Z = nkc_of(2 * Z);
   edge(st, sB);
-  pack_rows(w.dlin, 2 * Z, Bp, 2 * Z, Bp, w.dlin_p, st);
   GemmB().A(w.dlin_p, nkc2Z, nkc2Z).Bm(W.lamT_p, nkc2Z, nkc2Z).run_fm(Bp, 4 * H, w.dhidden, Bp, nullptr, st);
   {   // Lambda weight gradients on sB
     pack_T(w.dlin, 2 * Z, 2 * Z, Bp, Bp, w.dlinT_p, sB);

@@ -53,6 +53,7 @@ void launch_pack_whh(const float* w_hh, int H, int mode, void* out, cudaStream_t
 void launch_bias_fuse(const float* b_ih0, const float* b_hh0, const float* b_ih1, const float* b_hh1, int H, float* out, cudaStream_t st);
 void launch_h0_prepare(const float* src, int D, int B, int B_pad, int H, float* h32, void* hp, cudaStream_t st);
 void launch_bt_to_tb(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, cudaStream_t st);
+void launch_bt_to_tb_p16(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, void* dst_p, cudaStream_t st);
 void launch_tb_to_bt(const float* src, int B, int T, int C, int B_pad, float* dst, cudaStream_t st);
 
 // ---- gemm.cu -------------------------------------------------------------------------------------

@@ -378,6 +378,41 @@ __global__ void tb_to_bt_kernel(const float* __restrict__ src, int B, int T, int
     dst[idx] = src[((long)t * B_pad + b) * C + c];
   }
 }
+// the same + the result as P16 [T*B_pad rows, K = C -> padded]: one thread per 8-wide k atom of one (t, b) row
+__global__ void bt_to_tb_p16_kernel(const float* __restrict__ src, int B, int T, int C, long src_bstride, long src_tstride, int B_pad,
+                                    float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_p) {
+  const int nkc = (C + KCHUNK - 1) / KCHUNK, apr = nkc * 8;
+  const long total = (long)T * B_pad * apr;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % apr) * 8;
+    const long r = idx / apr;
+    const int b = (int)(r % B_pad), t = (int)(r / B_pad);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = k0 + i;
+      v[i] = 0.f;
+      if (c < C) {
+        v[i] = (b < B) ? src[b * src_bstride + t * src_tstride + c] : 0.f;
+        dst[r * C + c] = v[i];
+      }
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    __nv_bfloat16* tile = dst_p + ((size_t)(r >> 7) * nkc + (k0 >> 6)) * p16_tile_elems(128);
+    const int off = p16_in_tile((int)(r & 127), k0 & 63);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
+  }
+}
+void launch_bt_to_tb_p16(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, void* dst_p, cudaStream_t st) {
+  const long total = (long)T * B_pad * ((C + KCHUNK - 1) / KCHUNK) * 8;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  count_launch();
+  bt_to_tb_p16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, B, T, C, bs, ts, B_pad, dst, (__nv_bfloat16*)dst_p);
+}
 void launch_bt_to_tb(const float* src, int B, int T, int C, long bs, long ts, int B_pad, float* dst, cudaStream_t st) {
   long total = (long)T * B_pad * C;
   long blocks = (total + 255) / 256;

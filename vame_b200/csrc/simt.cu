@@ -104,6 +104,129 @@ __global__ void mse_kernel(const float* __restrict__ pred, long ldp, const float
 constexpr int CP_MAXZ = 64;
 constexpr size_t CP_SMEM = 4 * CP_MAXZ * (CP_MAXZ + 1) * 8 + (3 * CP_MAXZ + 1) * 8 + (CP_MAXZ * 2) * 4 + 64 * (CP_MAXZ + 1) * 4 + 64;
 
+// ------------------------------------------------------------------------------------------------
+// Variants that also write the P16 operand of the GEMM that follows (one thread per 8-wide k atom of one row), so that the
+// train step's main chain needs no separate pack launch after them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_p16_atom(__nv_bfloat16* out, int nkc, long row, int k, const float* v) {   // k % 8 == 0
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  __nv_bfloat16* tile = out + ((size_t)(row >> 7) * nkc + (k >> 6)) * p16_tile_elems(128);
+  const int off = p16_in_tile((int)(row & 127), k & 63);
+  *reinterpret_cast<uint4*>(tile + off) = hi;
+  *reinterpret_cast<uint4*>(tile + 128 * KCHUNK + off) = lo;
+}
+// Lambda forward + z as P16 [B_pad rows, K = Z -> padded to 64-chunks]
+__global__ void lambda_fwd_p16_kernel(const float* __restrict__ lin, long ldl, const float* __restrict__ eps, int B, int B_pad, int Z,
+                                      int softplus, float* __restrict__ z, float* __restrict__ mu, float* __restrict__ logvar,
+                                      double* __restrict__ acc, __nv_bfloat16* __restrict__ z_p) {
+  const int nkc = (Z + KCHUNK - 1) / KCHUNK, apr = nkc * 8;
+  const long total = (long)B_pad * apr;
+  float part = 0.f;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % apr) * 8;
+    const long b = idx / apr;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = k0 + i;
+      v[i] = 0.f;
+      if (b < B && j < Z) {
+        const float m = lin[b * ldl + j];
+        float lv = lin[b * ldl + Z + j];
+        if (softplus) lv = (lv > 20.f) ? lv : log1pf(expf(lv));
+        const long o = b * Z + j;
+        mu[o] = m;
+        logvar[o] = lv;
+        v[i] = eps ? eps[o] * expf(0.5f * lv) + m : m;
+        z[o] = v[i];
+        part += 1.f + lv - m * m - expf(lv);
+      }
+    }
+    store_p16_atom(z_p, nkc, b, k0, v);
+  }
+  part = warp_sum(part);
+  if (acc && (threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(acc + ACC_KL, (double)part);
+}
+// Lambda backward + dlin as P16 [B_pad rows, K = 2Z -> padded]
+__global__ void lambda_bwd_p16_kernel(LambdaBwdArgs a, __nv_bfloat16* __restrict__ dlin_p) {
+  const int nkc = (2 * a.Z + KCHUNK - 1) / KCHUNK, apr = nkc * 8;
+  const long total = (long)a.B_pad * apr;
+  const float c_kl = a.hyper ? a.hyper[HY_BETA] * a.hyper[HY_KLW] / (float)((long)a.B * a.Z) : a.c_kl;
+  const bool use_eps = a.eps && (!a.use_eps_flag || *a.use_eps_flag != 0);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % apr) * 8;
+    const long b = idx / apr;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      v[i] = 0.f;
+      if (k < 2 * a.Z) {
+        const bool is_lv = k >= a.Z;
+        const int j = is_lv ? k - a.Z : k;
+        float g = 0.f;
+        if (b < a.B) {
+          const long o = b * a.Z + j;
+          float dz = 0.f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (a.dz[p]) dz += a.dz[p][o];
+          const float m = a.mu[o], lv = a.logvar[o];
+          if (!is_lv) {
+            g = dz + c_kl * m + (a.dmu_ext ? a.dmu_ext[o] : 0.f);
+          } else {
+            g = c_kl * 0.5f * (expf(lv) - 1.f) + (a.dlv_ext ? a.dlv_ext[o] : 0.f);
+            if (use_eps) g += dz * a.eps[o] * 0.5f * expf(0.5f * lv);
+            if (a.softplus) {
+              const float x = a.lin[b * a.ldl + a.Z + j];
+              g *= 1.f / (1.f + expf(-x));
+            }
+          }
+        }
+        a.dlin[b * a.ldd + k] = g;
+        v[i] = g;
+      }
+    }
+    store_p16_atom(dlin_p, nkc, b, k0, v);
+  }
+}
+// MSE + gradient + the gradient as P16 [rows, K = F -> padded]
+__global__ void mse_p16_kernel(const float* __restrict__ pred, long ldp, const float* __restrict__ target, int rows, int B, int B_pad,
+                               int F, float gscale, float* __restrict__ dpred, double* __restrict__ acc, int slot,
+                               __nv_bfloat16* __restrict__ dpred_p) {
+  const int nkc = (F + KCHUNK - 1) / KCHUNK, apr = nkc * 8;
+  const long total = (long)rows * apr;
+  float part = 0.f;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(idx % apr) * 8;
+    const long r = idx / apr;
+    const bool live = (int)(r % B_pad) < B;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = k0 + i;
+      v[i] = 0.f;
+      if (f < F) {
+        const float d = live ? pred[r * ldp + f] - target[r * F + f] : 0.f;
+        part += d * d;
+        v[i] = gscale * d;
+        dpred[r * F + f] = v[i];
+      }
+    }
+    store_p16_atom(dpred_p, nkc, r, k0, v);
+  }
+  __shared__ float wsum[8];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0 && acc) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += (double)wsum[i];
+    atomicAdd(acc + slot, t);
+  }
+}
+
 __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __restrict__ z, int B, int Z, int kloss,
                                                                 double lmbda, double bsize, double gcoef,
                                                                 const float* __restrict__ hyper,
@@ -465,6 +588,25 @@ void launch_lambda_fwd(const float* lin, long ldl, const float* eps, int B, int 
                        double* acc, cudaStream_t st) {
   count_launch();
   lambda_fwd_kernel<<<grid_for((long)B * Z, 256), 256, 0, st>>>(lin, ldl, eps, B, Z, softplus, z, mu, logvar, acc);
+}
+void launch_lambda_fwd_p16(const float* lin, long ldl, const float* eps, int B, int B_pad, int Z, int softplus, float* z, float* mu,
+                           float* logvar, double* acc, void* z_p, cudaStream_t st) {
+  count_launch();
+  const long total = (long)B_pad * ((Z + KCHUNK - 1) / KCHUNK) * 8;
+  lambda_fwd_p16_kernel<<<grid_for(total, 128), 128, 0, st>>>(lin, ldl, eps, B, B_pad, Z, softplus, z, mu, logvar, acc,
+                                                              (__nv_bfloat16*)z_p);
+}
+void launch_lambda_bwd_p16(const LambdaBwdArgs& a, void* dlin_p, cudaStream_t st) {
+  count_launch();
+  const long total = (long)a.B_pad * ((2 * a.Z + KCHUNK - 1) / KCHUNK) * 8;
+  lambda_bwd_p16_kernel<<<grid_for(total, 128), 128, 0, st>>>(a, (__nv_bfloat16*)dlin_p);
+}
+void launch_mse_p16(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
+                    double* acc, int slot, void* dpred_p, cudaStream_t st) {
+  count_launch();
+  const long total = (long)rows * ((F + KCHUNK - 1) / KCHUNK) * 8;
+  mse_p16_kernel<<<grid_for(total, 256, 296), 256, 0, st>>>(pred, ldp, target, rows, B, B_pad, F, gscale, dpred, acc, slot,
+                                                           (__nv_bfloat16*)dpred_p);
 }
 void launch_lambda_bwd(const LambdaBwdArgs& a, cudaStream_t st) {
   count_launch();

@@ -25,6 +25,12 @@ struct LambdaBwdArgs {
 void launch_lambda_fwd(const float* lin, long ldl, const float* eps, int B, int Z, int softplus, float* z, float* mu, float* logvar,
                        double* acc, cudaStream_t st);
 void launch_lambda_bwd(const LambdaBwdArgs& a, cudaStream_t st);
+// variants that also write the P16 operand of the GEMM that follows (z_p [B_pad, Z], dlin_p [B_pad, 2Z], dpred_p [rows, F])
+void launch_lambda_fwd_p16(const float* lin, long ldl, const float* eps, int B, int B_pad, int Z, int softplus, float* z, float* mu,
+                           float* logvar, double* acc, void* z_p, cudaStream_t st);
+void launch_lambda_bwd_p16(const LambdaBwdArgs& a, void* dlin_p, cudaStream_t st);
+void launch_mse_p16(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
+                    double* acc, int slot, void* dpred_p, cudaStream_t st);
 void launch_mse(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
                 double* acc, int slot, cudaStream_t st);
 // hyper != nullptr: lambda = hyper[HY_KMLAMBDA], gradient coefficient = hyper[HY_KLW]; else the scalar arguments
