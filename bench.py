@@ -61,9 +61,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0/t1 (time.time()): keep the samples that arrived inside the timed region; the sampler is started before the warm-up
+        steps (nvidia-smi needs ~0.1 s to come up, longer than a short timed region), so if none fell inside, the samples taken
+        under the same load during warm-up are used and `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -71,9 +74,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        window = "all"
+        lines = [ln for _, ln in self.lines]
+        if t0 is not None and t1 is not None:
+            inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.05]
+            window = "timed region" if inside else "warm-up + timed region (same load)"
+            lines = inside or lines
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -85,7 +94,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def usable_cpus():
@@ -210,19 +219,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                        # (comes up during the warm-up steps)
     for _ in range(W):
         ts.run()
     barrier()
     launches0 = lib.vame_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for _ in range(K):
         ts.run()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
     ms = e0.elapsed_time(e1) / K
     launches_eager = lib.vame_launch_count() - launches0
     if world > 1:
