@@ -159,6 +159,22 @@ int vame_debug_timeline_read(const char** names, float* ms, int max);
 int vame_cluster_loss(const float* latent, int batch, int zdims, int kloss, float lmbda, float bsize, float grad_coef,
                       double* loss_out, float* dlatent, void* stream);
 
+/* Training-set preparation (vame/model/create_training.py:94-264, traindata_aligned / traindata_fixed), float64 like the
+ * reference; series are (num_features, n_frames) row-major = the reference's <file>-PE-seq.npy layout.
+ * vame_trainset_zscore_clean: per-file stage (:106-137 / :204-232): z-score with the global mean / std of the file, and with
+ *   robust != 0 the IQR outlier removal (|x| > iqr_factor * scipy.stats.iqr -> NaN) followed by the reference's interpolation:
+ *   fixed != 0 every frame over the marker index (:231), else the 2-D interpol() of :137 (a NaN of marker f becomes the last
+ *   valid time sample of marker f).  stats_out (device, 5 doubles, may be NULL): mean, std, iqr, #outliers, #entries left NaN.
+ * vame_trainset_row_std: population std of every marker over time (anchor detection, :148).
+ * vame_trainset_savgol: scipy.signal.savgol_filter(X, window, order) along time with mode='interp' (:175-178); coeffs[window],
+ *   head / tail [window/2][window] are device arrays computed by the host mirror (vame_b200/create_training.py). */
+size_t vame_trainset_workspace_bytes(long n_frames, int num_features);
+int vame_trainset_zscore_clean(const double* data_fn, long n_frames, int num_features, int robust, double iqr_factor, int fixed,
+                               double* xz_fn, double* stats_out, void* ws, size_t ws_bytes, void* stream);
+int vame_trainset_row_std(const double* x_fn, long n_frames, int num_features, double* std_out, void* stream);
+int vame_trainset_savgol(const double* x_fn, long n_frames, int num_features, int window, const double* coeffs, const double* head,
+                         const double* tail, double* out_fn, void* stream);
+
 /* ---- k-means on the latent vectors ---------------------------------------------------------------------
  * Replaces sklearn.cluster.KMeans(init='k-means++', n_clusters, random_state, n_init).fit / .predict as called at
  * vame/analysis/pose_segmentation.py:141-143 and :183-185.  x is [n, dim] fp32 row-major on the device (dim <= 64,

@@ -222,6 +222,85 @@ def gen_kmeans(ps):
     print("kmeans_blobs: single inertia %.4f n_iter %d" % (km.inertia_, km.n_iter_))
 
 
+def gen_trainset():
+    """create_trainset step: outputs of the reference's own traindata_fixed / traindata_aligned
+    (vame/model/create_training.py:94-264) on small inputs: the first 1500 frames of examples/video-1.csv after the
+    reference's csv_to_numpy, and two synthetic two-file projects with injected outliers (so that the IQR cut-off and both
+    NaN-interpolation variants are exercised)."""
+    import shutil
+    import vame
+    from vame.util import auxiliary
+    from vame.model import create_training as ct
+    out = {}
+
+    def project(tmp, files, cfg_over):
+        proj = os.path.join(tmp, "proj")
+        for sub in ["videos/pose_estimation", "data/train", "model"] + ["data/" + f for f in files] + ["results/" + f for f in files]:
+            os.makedirs(os.path.join(proj, sub), exist_ok=True)
+        cfg_file, _ = auxiliary.create_config_template()
+        cfg_file["Project"] = "proj"
+        cfg_file["project_path"] = proj
+        cfg_file["video_sets"] = list(files)
+        cfg_file.update(cfg_over)
+        cfgp = os.path.join(proj, "config.yaml")
+        auxiliary.write_config(cfgp, cfg_file)
+        return proj, cfgp
+
+    def collect(tag, proj, files, raw):
+        out[tag + "/train"] = np.load(os.path.join(proj, "data", "train", "train_seq.npy"))
+        out[tag + "/test"] = np.load(os.path.join(proj, "data", "train", "test_seq.npy"))
+        for i, f in enumerate(files):
+            out["%s/raw%d" % (tag, i)] = raw[i]
+            out["%s/clean%d" % (tag, i)] = np.load(os.path.join(proj, "data", f, f + "-PE-seq-clean.npy"))
+
+    base = dict(num_features=12, time_window=30, zdims=30, test_fraction=0.1, pose_confidence=0.99, iqr_factor=4, savgol_filter=True,
+                savgol_length=5, savgol_order=2, robust=True, all_data="yes", batch_size=32)
+    # ---- video-1 through csv_to_numpy (egocentric_data = True -> traindata_fixed)
+    with tempfile.TemporaryDirectory() as tmp:
+        proj, cfgp = project(tmp, ["video-1"], dict(base, egocentric_data=True))
+        shutil.copy("/root/reference/examples/video-1.csv", os.path.join(proj, "videos", "pose_estimation", "video-1.csv"))
+        vame.csv_to_numpy(cfgp)
+        f = os.path.join(proj, "data", "video-1", "video-1-PE-seq.npy")
+        raw = np.load(f)[:, :1500].copy()
+        np.save(f, raw)
+        vame.create_trainset(cfgp, check_parameter=False)
+        collect("video1_fixed", proj, ["video-1"], [raw])
+    # ---- synthetic two-file projects with outliers
+    rng = np.random.RandomState(11)
+
+    def synth(F, N):
+        t = np.arange(N)
+        x = np.stack([np.sin(0.01 * (i + 1) * t + i) * (1 + 0.2 * i) + 0.05 * rng.randn(N) for i in range(F)])
+        idx = rng.choice(F * N, size=F * N // 150, replace=False)
+        x.reshape(-1)[idx] += rng.choice([-1.0, 1.0], size=idx.size) * rng.uniform(6, 20, size=idx.size)   # spikes beyond 4 x IQR
+        return x
+    for tag, fixed, sav in (("synth_fixed", True, True), ("synth_fixed_nosav", True, False)):
+        with tempfile.TemporaryDirectory() as tmp:
+            files = ["a", "b"]
+            proj, cfgp = project(tmp, files, dict(base, egocentric_data=fixed, num_features=10, savgol_filter=sav, savgol_length=7, savgol_order=3))
+            raw = [synth(10, 700), synth(10, 500)]
+            for f, r in zip(files, raw):
+                np.save(os.path.join(proj, "data", f, f + "-PE-seq.npy"), r)
+            vame.create_trainset(cfgp, check_parameter=False)
+            collect(tag, proj, files, raw)
+    # aligned path: two anchor rows of constant value (zero variance after alignment) that the reference removes
+    with tempfile.TemporaryDirectory() as tmp:
+        files = ["a", "b"]
+        proj, cfgp = project(tmp, files, dict(base, egocentric_data=False, num_features=10))
+        raw = []
+        for n in (700, 500):
+            r = synth(10, n)
+            r[3, :] = 0.25
+            r[7, :] = 0.25
+            raw.append(r)
+        for f, r in zip(files, raw):
+            np.save(os.path.join(proj, "data", f, f + "-PE-seq.npy"), r)
+        vame.create_trainset(cfgp, check_parameter=False)
+        collect("synth_aligned", proj, files, raw)
+    np.savez_compressed(os.path.join(OUT, "trainset.npz"), **out)
+    print("trainset:", {k: v.shape for k, v in out.items() if k.endswith("/train")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
@@ -230,12 +309,16 @@ def main():
     if "--only-kmeans" in sys.argv:
         gen_kmeans(ps)
         return
+    if "--only-trainset" in sys.argv:
+        gen_trainset()
+        return
     for name in CASES:
         gen_step_case(name, rm, rv)
     gen_train_fn(rm, rv)
     gen_embed_synth(rm, ps)
     gen_video1(rm, ps)
     gen_kmeans(ps)
+    gen_trainset()
 
 
 if __name__ == "__main__":

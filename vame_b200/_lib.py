@@ -30,6 +30,10 @@ SIGNATURES = {
     "vame_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_pack_weights_deferred": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_arm_prior": (c_int, [c_void_p, c_void_p]),
+    "vame_trainset_workspace_bytes": (c_size_t, [c_long, c_int]),
+    "vame_trainset_zscore_clean": (c_int, [c_void_p, c_long, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_trainset_row_std": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    "vame_trainset_savgol": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_pack_weights_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vame_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vame_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_int, c_void_p, c_void_p,

@@ -2,7 +2,8 @@
 
 ``install()`` rebinds, in the already-imported reference modules, exactly the names on the hot path
 (SURVEY.md §8b): the five model classes, the four loss functions, ``train`` / ``test`` and
-``load_model`` / ``embedd_latent_vectors``.  Everything else (config handling, data preparation, train_model's epoch
+``load_model`` / ``embedd_latent_vectors``, the k-means parameterization and the arithmetic of ``create_trainset``
+(``traindata_fixed`` / ``traindata_aligned``).  Everything else (config handling, csv / alignment preprocessing, train_model's epoch
 loop, checkpoint files, clustering, plotting) keeps running the reference's own code, so existing projects and
 ``.pkl`` checkpoints work unchanged.
 """
@@ -59,6 +60,22 @@ def install(verbose=False):
 
         ps.same_parameterization = same_parameterization
         done.append((ps.__name__, "same_parameterization"))
+    # training-set preparation (create_trainset step): the arithmetic runs on the device, files and formats are the reference's
+    ct = sys.modules.get("vame.model.create_training")
+    if ct is not None:
+        from . import create_training as _ct
+        if not hasattr(ct, "_ref_traindata_fixed"):
+            ct._ref_traindata_fixed, ct._ref_traindata_aligned = ct.traindata_fixed, ct.traindata_aligned
+
+        def _wrap(ours, ref):
+            def f(cfg, files, testfraction, num_features, savgol_filter, check_parameter):
+                if check_parameter:                      # the matplotlib inspection plots stay the reference's
+                    return ref(cfg, files, testfraction, num_features, savgol_filter, check_parameter)
+                return ours(cfg, files, testfraction, num_features, savgol_filter, check_parameter)
+            return f
+        ct.traindata_fixed = _wrap(_ct.traindata_fixed, ct._ref_traindata_fixed)
+        ct.traindata_aligned = _wrap(_ct.traindata_aligned, ct._ref_traindata_aligned)
+        done += [(ct.__name__, "traindata_fixed"), (ct.__name__, "traindata_aligned")]
     if verbose:
         for m, n in done:
             print("vame_b200: %s.%s -> B200 path" % (m, n))
