@@ -55,7 +55,7 @@ def test_install_rebinds_hot_path_names():
     from vame_b200 import install, rnn_model, rnn_vae, pose_segmentation
     saved = {}
     mods = ["vame.model.rnn_model", "vame.model.rnn_vae", "vame.analysis.pose_segmentation", "vame.model.evaluate",
-            "vame.analysis.generative_functions"]
+            "vame.analysis.generative_functions", "vame.model.create_training"]
     for m in mods:
         saved[m] = dict(sys.modules[m].__dict__)
     try:
@@ -67,6 +67,9 @@ def test_install_rebinds_hot_path_names():
         assert sys.modules["vame.analysis.pose_segmentation"].RNN_VAE is rnn_model.RNN_VAE
         assert sys.modules["vame.analysis.pose_segmentation"].load_model is pose_segmentation.load_model
         assert sys.modules["vame.model.evaluate"].RNN_VAE is rnn_model.RNN_VAE
+        ct = sys.modules["vame.model.create_training"]
+        assert ("vame.model.create_training", "traindata_fixed") in done and ct.traindata_fixed is not ct._ref_traindata_fixed
+        assert ct.create_trainset.__module__ == "vame.model.create_training"       # the driver function stays the reference's
     finally:
         for m in mods:
             sys.modules[m].__dict__.clear()
