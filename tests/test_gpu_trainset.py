@@ -31,7 +31,7 @@ def test_trainset_matches_reference_outputs(golden_dir, tag):
 def test_trainset_large_random_vs_oracle(fixed):
     from vame_b200 import create_training as ct
     rng = np.random.RandomState(5)
-    F, Ns = 24, (50_000, 30_011)
+    F, Ns = 24, (20_000, 10_011)
     raws = []
     for N in Ns:
         x = np.cumsum(rng.randn(F, N) * 0.05, axis=1) + rng.randn(F, 1)
