@@ -15,7 +15,7 @@ from tests.test_gpu_model import GRAD_TOL, OUT_TOL, check_step, make, rel  # noq
 def lib():
     from vame_b200 import _lib
     L = _lib.lib()
-    old = {k: L.vame_get_option(k) for k in (b"rw", b"rw2", b"rw_priv")}
+    old = {k: L.vame_get_option(k) for k in (b"rw", b"rw2", b"rw_priv", b"rw_ng")}
     yield L
     for k, v in old.items():
         L.vame_set_option(k, v)
@@ -30,20 +30,26 @@ def _step(eng, x, xf, eps, fut, B, Z):
     return {k: v.clone() for k, v in out.items()}, {k: v.clone() for k, v in eng.views(eng.grad).items()}
 
 
-@pytest.mark.parametrize("H,B,T,F,Z,S,fut,rw2,priv", [
-    (64, 48, 12, 10, 8, 5, True, 0, 0),
-    (128, 130, 9, 7, 12, 4, True, 0, 0),       # ragged: 130 rows -> B_pad 256, 16 clusters per direction
-    (192, 32, 6, 5, 6, 0, False, 0, 0),
-    (256, 256, 30, 24, 30, 0, False, 0, 0),    # BASELINE configs[1], cluster-barrier kernels
-    (256, 256, 30, 24, 30, 0, False, 1, 0),    # BASELINE configs[1], barrier-free kernels (st.async / mbarrier exchange)
-    (256, 256, 30, 24, 30, 0, False, 1, 1),    # ... with the private interchange layouts (the default)
-    (256, 96, 30, 24, 30, 15, True, 1, 1),     # decoder + future decoder sweeps side by side
-    (256, 96, 30, 24, 30, 15, True, 1, 0),
-    (256, 200, 3, 12, 30, 1, True, 1, 1),      # very short sweeps (1 and 3 steps), ragged batch
+@pytest.mark.parametrize("H,B,T,F,Z,S,fut,rw2,priv,ng", [
+    (64, 48, 12, 10, 8, 5, True, 0, 0, 0),
+    (128, 130, 9, 7, 12, 4, True, 0, 0, 0),       # ragged: 130 rows -> B_pad 256, 16 clusters per direction
+    (192, 32, 6, 5, 6, 0, False, 0, 0, 0),
+    (256, 256, 30, 24, 30, 0, False, 0, 0, 0),    # BASELINE configs[1], cluster-barrier kernels
+    (256, 256, 30, 24, 30, 0, False, 1, 0, 0),    # BASELINE configs[1], barrier-free kernels (st.async / mbarrier exchange)
+    (256, 256, 30, 24, 30, 0, False, 1, 1, 0),    # ... with the private interchange layouts (the default)
+    (256, 96, 30, 24, 30, 15, True, 1, 1, 0),     # decoder + future decoder sweeps side by side
+    (256, 96, 30, 24, 30, 15, True, 1, 0, 0),
+    (256, 200, 3, 12, 30, 1, True, 1, 1, 0),      # very short sweeps (1 and 3 steps), ragged batch
+    # two 16-row groups per cluster (32 rows on the N side of every MMA, single operand buffer, one BPTT A tile in tensor memory)
+    (256, 96, 5, 24, 30, 2, True, 1, 1, 2),       # forced at a small batch, decoder + future decoder side by side
+    (256, 200, 3, 12, 30, 1, True, 1, 0, 2),      # without the private layouts, ragged batch, 1- and 3-step sweeps
+    (256, 512, 30, 24, 30, 0, False, 1, 1, 0),    # BASELINE configs[4] per-GPU batch: chosen automatically (one wave of 32 clusters)
+    (256, 512, 12, 60, 50, 6, True, 1, 1, 0),     # BASELINE configs[2] shapes (shorter window)
 ])
-def test_rw_sweeps_vs_oracle_and_slice_kernels(lib, H, B, T, F, Z, S, fut, rw2, priv):
+def test_rw_sweeps_vs_oracle_and_slice_kernels(lib, H, B, T, F, Z, S, fut, rw2, priv, ng):
     lib.vame_set_option(b"rw2", rw2)
     lib.vame_set_option(b"rw_priv", priv)
+    lib.vame_set_option(b"rw_ng", ng)
     port, eng = make(T, Z, F, fut, S, H)
     x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z)
     xf = xf[:, :S] if fut else xf

@@ -1,5 +1,5 @@
 """Probe: time the encoder-layer-1 forward / backward sweeps alone (vame_debug_gru_sweep) for option variants given as
-name=value pairs on the command line, e.g.  python tools/gpu_probe_sweeps.py rw2=1 rw_exp=3"""
+name=value pairs on the command line, e.g.  python tools/gpu_probe_sweeps.py rw2=1 rw_exp=3  (wl=c5 selects the workload)"""
 import ctypes
 import os
 import sys
@@ -15,10 +15,14 @@ def main():
     from vame_b200.engine import Engine
     from vame_b200 import _lib as L
     lib = L.lib()
+    wl = "c2"
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
+        if k == "wl":
+            wl = v
+            continue
         lib.vame_set_option(k.encode(), int(v))
-    F, T, Z, H, fut, S, B = WORKLOADS["c2"]
+    F, T, Z, H, fut, S, B = WORKLOADS[wl]
     torch.manual_seed(19)
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
     eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda")

@@ -156,6 +156,17 @@ __device__ __forceinline__ void umma_bf16_c(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
       : "memory");
 }
+// A operand from tensor memory (lane r = row r of the M = 128 tile, 8 columns per k-step of 16: column i holds the bf16 pair
+// k = 2 i, 2 i + 1), B from shared memory; compile-time accumulate flag
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
+}
 // descriptor of the same tile `bytes` further into shared memory (the 14-bit start-address field cannot overflow:
 // shared memory is < 256 KB)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }

@@ -720,7 +720,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-constexpr int RW_SW_THREADS = 288;             // + warps 5-8: store warps (SW kernels)
 
 // SW ("store warps", training sweeps in the private layouts): an SM drains its global stores at only ~18 B/cycle, so the 28 KB a
 // CTA writes per time step kept the four gate-math warps stuck in their store instructions for ~1 us of a 3.2 us step
@@ -728,29 +727,41 @@ constexpr int RW_SW_THREADS = 288;             // + warps 5-8: store warps (SW k
 // through TENSOR MEMORY (tcgen05.st into spare columns, double-buffered, mbarrier handshake; warp 5 + i owns the TMEM lane
 // quarter (5 + i) % 4) and go straight back to the recurrence; the store warps do the bf16 splits / transposes and all global
 // stores of step t while step t + 1 is being computed.
-template <bool PRIV, bool SW>
-__global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
+// NG: 16-row groups per cluster.  NG = 2 puts 32 batch rows on the N side of every MMA (N = 64 instead of 32: the MMA costs the same
+// 46 cycles), so a 512-window batch runs in ONE wave of 32 clusters.  Every group has its own four gate-math warps (and store
+// warps), TMEM accumulator columns and operand rows; the operand buffer is single (2 x 32 KB do not fit beside the 192 KB of
+// weights), so a CTA pushes h_t to a peer only after that peer has signalled that its MMAs of step t are complete (ofree).
+template <bool PRIV, bool SW, int NG>
+__global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
+  static_assert(NG == 1 || NG == 2, "one or two 16-row groups per cluster");
   constexpr bool RW_MN = RW_MN_FWD != 0;
   constexpr int NKC = 4, H = 256, UC = 64;
+  constexpr int NGW = 4 * NG, NGT = 128 * NG;                      // gate-math warps / threads
+  constexpr int BT = RW_BTILE * NG;                                // one k chunk of the operand: [per group: 16 hi rows ; 16 lo rows] x 64 k
+  constexpr int NBUF = NG == 1 ? 2 : 1;                            // operand buffers
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
-  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [2][NKC][RW_BTILE]
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + 2 * NKC * RW_BTILE);
+  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [NBUF][NKC][BT]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + NBUF * NKC * BT);
   uint64_t* done = wbar + 1;                                      // [3]: accumulator of gate g complete
-  uint64_t* lfull = done + 3;                                     // [2]: own chunk of operand buffer b written (128 arrivals)
+  uint64_t* lfull = done + 3;                                     // [2]: own chunk of operand buffer b written (NGT arrivals)
   uint64_t* hfull = lfull + 2;                                    // [2]: the three peers' chunks of buffer b have landed (tx bytes)
-  uint64_t* sfull = hfull + 2;                                    // [2] SW: staging buffer b written by the 128 gate-math threads
-  uint64_t* sempty = sfull + 2;                                   // [2] SW: staging buffer b read back by the 128 store threads
+  uint64_t* sfull = hfull + 2;                                    // [2] SW: staging buffer b written by the NGT gate-math threads
+  uint64_t* sempty = sfull + 2;                                   // [2] SW: staging buffer b read back by the NGT store threads
   uint64_t* gfull = sempty + 2;                                   // [3] SW: gi of step s (TMEM buffer s % 3) written by the store threads
   uint64_t* gempty = gfull + 3;                                   // [3] SW: ... consumed by the gate-math threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gempty + 3);
+  uint64_t* ofree = gempty + 3;                                   // NBUF == 1: the 3 peers' MMAs of step s are complete (phase s)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofree + 1);
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirFwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
-  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
-  const bool epi = warp < 4;
+  const int q = warp & 3, half = lane >> 4, oct = (lane >> 3) & 1;  // q: TMEM lane quarter of this warp = its 16 units of the slice
+  const bool epi = warp < NGW;                                     // gate-math warp of group warp >> 2
+  const bool stw = SW && warp > NGW;                               // store warp of lane quarter q (serves every group in turn)
+  const int grp = epi ? (warp >> 2) : 0;
+  const long gidx = (long)blockIdx.y * NG + grp;                   // 16-row group of the batch (gate-math warps)
   const long Bp = (long)a.tiles * 128;
   const int steps = a.steps;
 
@@ -758,26 +769,30 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
     mbar_init(wbar, 1);
     for (int g = 0; g < 3; ++g) mbar_init(&done[g], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&lfull[b], 128);
+      mbar_init(&lfull[b], NGT);
       mbar_init(&hfull[b], 1);
-      mbar_init(&sfull[b], 128);
-      mbar_init(&sempty[b], 128);
+      mbar_init(&sfull[b], NGT);
+      mbar_init(&sempty[b], NGT);
     }
     for (int b = 0; b < 3; ++b) {
-      mbar_init(&gfull[b], 128);
-      mbar_init(&gempty[b], 128);
+      mbar_init(&gfull[b], NGT);
+      mbar_init(&gempty[b], NGT);
     }
+    mbar_init(ofree, 3);
     mbar_fence_init();
   }
-  constexpr uint32_t TCOLS = SW ? 256 : 128;                      // accumulators: columns 0-95; SW staging: 128 + 64 b + [0, 40),
-                                                                  // SW input projections: 3 buffers of 24 columns at 96 / 168 / 232
-  if (warp == 4) tmem_alloc(tmem_slot, TCOLS);
+  // tensor-memory columns: accumulator of gate g, group p at 32 (NG g + p); SW staging (h, r, z, n, gh_n: 40 columns) of group p,
+  // buffer b at SBASE + 40 (2 p + b); SW input projections (24 columns) of group p, buffer b at GBASE + 24 (3 p + b)
+  constexpr uint32_t SBASE = 96 * NG, GBASE = SBASE + 80 * NG;
+  constexpr uint32_t TCOLS = SW ? 256 * NG : 128 * NG;
+  static_assert(GBASE + 72 * NG <= 256 * NG, "tensor-memory budget");
+  if (warp == NGW) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == NGW) {
     if (elect_one()) {
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.w_rw) + (size_t)c * 3 * NKC * (RW_ATILE / 2);
       mbar_expect_tx(wbar, 3 * NKC * RW_ATILE);
@@ -786,11 +801,17 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
     __syncwarp();
   }
 
-  const int j = 16 * (q & 3) + (lane & 15);
+  const int j = 16 * q + (lane & 15);
   const int u = (int)c * UC + j;
-  const long b0 = (long)blockIdx.y * 16 + 8 * half;
-  const int nrow = 8 * half + (lane & 7);
-  const int kloc = 16 * (q & 3) + 8 * oct;                        // k inside the CTA's own chunk after the transpose
+  const long b0 = gidx * 16 + 8 * half;
+  const int nrow = 8 * half + (lane & 7);                         // row inside the group after the transpose
+  const int orow = 32 * grp;                                      // first operand row of the group ([16 hi ; 16 lo] per group)
+  const int kloc = 16 * q + 8 * oct;                              // k inside the CTA's own chunk after the transpose
+  // byte offset of (operand row n, k) inside an operand buffer of BT-sized 64-k chunks (K-major) / of rows n0 .. n0 + 7 (MN-major)
+  auto b_off = [&](int n, int k) -> uint32_t { return (uint32_t)(k >> 6) * BT + 2u * (uint32_t)p16_in_tile(n, k & 63); };
+  auto mn_off = [&](int n0, int k) -> uint32_t {
+    return (uint32_t)(k >> 6) * BT + (uint32_t)((n0 >> 3) * 1024 + ((k & 63) >> 3) * 128 + (k & 7) * 16);
+  };
   float hprev[8], bhn = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
@@ -807,37 +828,43 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
       uint4 hi, lo;
       if constexpr (RW_MN) {
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sH + rw_mn_off(8 * half, cc * UC + j)) = hi;
-        *reinterpret_cast<uint4*>(sH + rw_mn_off(16 + 8 * half, cc * UC + j)) = lo;
+        *reinterpret_cast<uint4*>(sH + mn_off(orow + 8 * half, cc * UC + j)) = hi;
+        *reinterpret_cast<uint4*>(sH + mn_off(orow + 16 + 8 * half, cc * UC + j)) = lo;
       } else {
         rw_transpose_pack(v, lane, hi, lo);
-        *reinterpret_cast<uint4*>(sH + rw_b_off(nrow, cc * UC + kloc)) = hi;
-        *reinterpret_cast<uint4*>(sH + rw_b_off(16 + nrow, cc * UC + kloc)) = lo;
+        *reinterpret_cast<uint4*>(sH + b_off(orow + nrow, cc * UC + kloc)) = hi;
+        *reinterpret_cast<uint4*>(sH + b_off(orow + 16 + nrow, cc * UC + kloc)) = lo;
       }
     }
     fence_proxy_async_smem();
   }
-  // arm the receive barriers of the first two exchanges (buffer 1 is filled for step 1, buffer 0 for step 2); later phases are
-  // armed right after the previous phase has been waited for, so a peer's complete_tx never precedes the expect_tx
-  const uint32_t hx = (a.exp & 8) ? 3 * RW_BTILE / 2 : 3 * RW_BTILE;   // (experiment 8: only the hi plane is pushed)
+  // arm the receive barriers of the first exchanges (two buffers: buffer 1 is filled for step 1, buffer 0 for step 2; one buffer:
+  // for step 1); later phases are armed right after the previous phase has been waited for, so a peer's complete_tx never
+  // precedes the expect_tx
+  const uint32_t hx = (a.exp & 8) ? 3 * BT / 2 : 3 * BT;           // (experiment 8: only the hi plane is pushed)
   if (tid == 0) {
-    if (steps > 1) mbar_expect_tx(&hfull[1], hx);
-    if (steps > 2) mbar_expect_tx(&hfull[0], hx);
+    if constexpr (NBUF == 2) {
+      if (steps > 1) mbar_expect_tx(&hfull[1], hx);
+      if (steps > 2) mbar_expect_tx(&hfull[0], hx);
+    } else {
+      if (steps > 1) mbar_expect_tx(&hfull[0], hx);
+    }
   }
   // all mbarriers of the cluster are initialised (and the h0 operands written) before any remote signal is sent
   cluster_arrive_release();
   cluster_wait_acquire();
 
-  const uint32_t idesc = rw_idesc(RW_MN);
-  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+  constexpr uint32_t idesc = make_idesc_bf16(128, 32 * NG) | (RW_MN ? (1u << 16) : 0u);
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
   const long groups = Bp / 16;
   const bool gi_const = d.gi_ts == 0;                              // decoders: the input projection does not depend on t
   // input projections are prefetched TWO steps ahead (registers): under the write bursts of the sweep's own stores a load
   // issued one step ahead came back too late for the next gate math (measured: 3.25 -> 2.5 us per step)
   float gir[8], giz[8], gin[8], gir2[8], giz2[8], gin2[8];
-  auto load_gi = [&](int s_, float* r_, float* z_, float* n_) {
+  float gsr[NG > 1 ? 8 : 1], gsz[NG > 1 ? 8 : 1], gsn[NG > 1 ? 8 : 1];   // store warps, NG = 2: fetched input projections of group 1
+  auto load_gi = [&](int g_, int s_, float* r_, float* z_, float* n_) {
     const int t_ = d.reverse ? steps - 1 - s_ : s_;
-    const float* gi_row = d.gi + (b0 * d.gi_bs + (long)t_ * d.gi_ts);
+    const float* gi_row = d.gi + ((((long)blockIdx.y * NG + g_) * 16 + 8 * half) * d.gi_bs + (long)t_ * d.gi_ts);
     ld8(gi_row + (long)u * d.gi_ld, r_);          // (ld.global.cg instead: 3.9 instead of 3.3 us per step - the second
     ld8(gi_row + (long)(H + u) * d.gi_ld, z_);    //  16 bytes of each sector are L1 hits with the default policy)
     ld8(gi_row + (long)(2 * H + u) * d.gi_ld, n_);
@@ -845,9 +872,9 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
   // SW && !gi_const: the store warps fetch gi(s + 2) during step s and pass it on through tensor memory, so that the gate-math
   // warps issue no global memory instruction at all
   const bool gi_tmem = SW && !gi_const && !(a.exp & 2);
-  auto gi_col = [&](int s_) -> uint32_t { const int b_ = s_ % 3; return taddr + (b_ == 0 ? 96u : b_ == 1 ? 168u : 232u); };
-  auto gi_publish = [&](int s_, const float* r_, const float* z_, const float* n_) {   // store warps
-    const uint32_t gc = gi_col(s_);
+  auto gi_col = [&](int g_, int s_) -> uint32_t { return taddr + GBASE + 24u * (uint32_t)(3 * g_ + s_ % 3); };
+  auto gi_publish = [&](int g_, int s_, const float* r_, const float* z_, const float* n_) {   // store warps
+    const uint32_t gc = gi_col(g_, s_);
     __syncwarp();
     tmem_st8(gc, r_);
     tmem_st8(gc + 8, z_);
@@ -857,30 +884,36 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
     mbar_arrive(&gfull[s_ % 3]);
   };
   if (epi && !gi_tmem) {
-    load_gi(0, gir, giz, gin);
-    if (steps > 1 && !gi_const) load_gi(1, gir2, giz2, gin2);
+    load_gi(grp, 0, gir, giz, gin);
+    if (steps > 1 && !gi_const) load_gi(grp, 1, gir2, giz2, gin2);
   }
-  if (SW && warp >= 5 && gi_tmem) {
-    load_gi(0, gir, giz, gin);
-    if (steps > 1) load_gi(1, gir2, giz2, gin2);
-    gi_publish(0, gir, giz, gin);
-    if (steps > 1) gi_publish(1, gir2, giz2, gin2);
+  if (stw && gi_tmem) {
+#pragma unroll
+    for (int g_ = 0; g_ < NG; ++g_) {
+      load_gi(g_, 0, gir, giz, gin);
+      if (steps > 1) load_gi(g_, 1, gir2, giz2, gin2);
+      gi_publish(g_, 0, gir, giz, gin);
+      if (steps > 1) gi_publish(g_, 1, gir2, giz2, gin2);
+    }
   }
 
   for (int s = 0; s < steps; ++s) {
     const int t = d.reverse ? steps - 1 - s : s;
     const int so = (d.out_slots == steps) ? t : (s & 1);
     const int sp = (d.out_p_slots == steps) ? t : (s & 1);
-    const uint32_t ph = s & 1, b = s & 1;
+    const uint32_t ph = s & 1;
+    const uint32_t b = NBUF == 2 ? (uint32_t)(s & 1) : 0u;         // operand buffer of this step
+    const uint32_t nb = NBUF == 2 ? (b ^ 1u) : 0u;                 // ... of the next step
+    // phase parity of the barriers of buffer b: two buffers - used every other step; one buffer - every step
+    const uint32_t bpar = NBUF == 2 ? (uint32_t)(((s - 1) >> 1) & 1) : (uint32_t)((s - 1) & 1);
     RW_STAMP(0);
-    if (warp == 4) {
+    if (warp == NGW) {
       if (elect_one()) {
-        const uint32_t hb = smem_u32(sH) + b * NKC * RW_BTILE;
+        const uint32_t hb = smem_u32(sH) + b * NKC * BT;
         if (s == 0) {
           mbar_wait_b(wbar, 0, 10);
         } else {
-          const uint32_t par = ((s - 1) >> 1) & 1;
-          mbar_wait_b(&lfull[b], par, 11);                          // own chunk of h_{t-1} written (and TMEM drained) by the 4 warps
+          mbar_wait_b(&lfull[b], bpar, 11);                         // own chunk of h_{t-1} written (and TMEM drained) by the gate warps
           RW_STAMP_MMA(8);
         }
         fence_proxy_async_smem();
@@ -891,14 +924,14 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         for (int g = 0; g < 3; ++g) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t ao = (g * NKC + c) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = c * RW_BTILE + ks * 2 * ATOM_BYTES;
-            if (ks == 0) umma_bf16_c<0>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
-            else umma_bf16_c<1>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            const uint32_t ao = (g * NKC + c) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = c * BT + ks * 2 * ATOM_BYTES;
+            if (ks == 0) umma_bf16_c<0>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            else umma_bf16_c<1>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
           }
         }
         if (s > 0) {
-          mbar_wait_b(&hfull[b], ((s - 1) >> 1) & 1, 12);
-          if (s + 2 < steps) mbar_expect_tx(&hfull[b], hx);               // arm the next use of this buffer (step s + 2)
+          mbar_wait_b(&hfull[b], bpar, 12);
+          if (s + NBUF < steps) mbar_expect_tx(&hfull[b], hx);     // arm the next use of this buffer (step s + NBUF)
           fence_proxy_async_smem();                                 // the peers' chunks were written through the generic proxy
         }
         RW_STAMP_MMA(9);
@@ -910,8 +943,8 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
             const uint32_t kc = (c + r) & 3;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * RW_BTILE + ks * 2 * ATOM_BYTES;
-              umma_bf16_c<1>(tmem + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * BT + ks * 2 * ATOM_BYTES;
+              umma_bf16_c<1>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
             }
           }
           umma_commit(&done[g]);
@@ -919,59 +952,60 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         RW_STAMP_MMA(2);
       }
       __syncwarp();
-    } else if (SW && warp >= 5) {                                   // ---- store warp of TMEM lane quarter q & 3 ----
-      float hn[8], sr[8], sz[8], sn[8], sg[8];
-      const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+    } else if (stw) {                                               // ---- store warp of TMEM lane quarter q ----
+      const uint32_t sb = s & 1;
       const bool fetch = gi_tmem && s + 2 < steps;
-      if (fetch) load_gi(s + 2, gir, giz, gin);
+      if (fetch) {                                                  // loads first: they are in flight while the warp waits below
+        load_gi(0, s + 2, gir, giz, gin);
+        if constexpr (NG > 1) load_gi(1, s + 2, gsr, gsz, gsn);
+      }
       mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 17);
       tc_fence_after();
-      tmem_ld8(stg, hn);
-      tmem_ld8(stg + 8, sr);
-      tmem_ld8(stg + 16, sz);
-      tmem_ld8(stg + 24, sn);
-      tmem_ld8(stg + 32, sg);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sempty[sb]);
-      if (a.exp & 16) {
-        if (fetch) {
-          if (s >= 1) mbar_wait_warp(&gempty[(s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
-          tc_fence_after();
-          gi_publish(s + 2, gir, giz, gin);
-        }
-        continue;
+#pragma unroll
+      for (int g_ = 0; g_ < NG; ++g_) {
+        float hn[8], sr[8], sz[8], sn[8], sg[8];
+        const uint32_t stg = taddr + SBASE + 40u * (uint32_t)(2 * g_ + (int)sb);
+        tmem_ld8(stg, hn);
+        tmem_ld8(stg + 8, sr);
+        tmem_ld8(stg + 16, sz);
+        tmem_ld8(stg + 24, sn);
+        tmem_ld8(stg + 32, sg);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sempty[sb]);
+        if (a.exp & 16) continue;
+        // (pacing these stores - one per warp every 256-384 cycles - changed nothing: 3.04 us per step either way)
+        uint4 phi, plo;
+        rw_transpose_pack(hn, lane, phi, plo);
+        const long gi_ = (long)blockIdx.y * NG + g_, bb = gi_ * 16 + 8 * half, row = gi_ * 16 + nrow;
+        const int k0 = (int)c * UC + kloc;
+        __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                            ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
+        const int off = p16_in_tile((int)(row & 127), k0 & 63);
+        const long blk = pv_block(t, groups, gi_, c, q);
+        st8p(d.out + blk, lane, hn);
+        st8p(d.sv[0] + blk, lane, sr);
+        st8p(d.sv[1] + blk, lane, sz);
+        st8p(d.sv[2] + blk, lane, sn);
+        st8p(d.sv[3] + blk, lane, sg);
+        st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + bb, hn);
+        if (s + 1 == steps) st8(d.hfin + (long)u * Bp + bb, hn);
+        *reinterpret_cast<uint4*>(tl + off) = phi;
+        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
       }
-      // (pacing these stores - one per warp every 256-384 cycles - changed nothing: 3.04 us per step either way)
-      uint4 phi, plo;
-      rw_transpose_pack(hn, lane, phi, plo);
-      const long row = (long)blockIdx.y * 16 + nrow;
-      const int k0 = (int)c * UC + kloc;
-      __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
-                          ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
-      const int off = p16_in_tile((int)(row & 127), k0 & 63);
-      const long blk = pv_block(t, groups, blockIdx.y, c, q);
-      st8p(d.out + blk, lane, hn);
-      st8p(d.sv[0] + blk, lane, sr);
-      st8p(d.sv[1] + blk, lane, sz);
-      st8p(d.sv[2] + blk, lane, sn);
-      st8p(d.sv[3] + blk, lane, sg);
-      st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + b0, hn);
-      if (s + 1 == steps) st8(d.hfin + (long)u * Bp + b0, hn);
-      *reinterpret_cast<uint4*>(tl + off) = phi;
-      *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
       if (fetch) {                                                  // buffer (s + 2) % 3 was last read in step s - 1
         if (s >= 1) mbar_wait_warp(&gempty[(s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
         tc_fence_after();
-        gi_publish(s + 2, gir, giz, gin);
+        gi_publish(0, s + 2, gir, giz, gin);
+        if constexpr (NG > 1) gi_publish(1, s + 2, gsr, gsz, gsn);
       }
-    } else {
+    } else if (epi) {
       float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
       uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
       if (gi_tmem) {                                                // this step's input projections (published >= 1 step ago)
         mbar_wait_warp(&gfull[s % 3], (s / 3) & 1, 19);
         tc_fence_after();
-        const uint32_t gc = gi_col(s);
+        const uint32_t gc = gi_col(grp, s);
         tmem_ld8(gc, gir);
         tmem_ld8(gc + 8, giz);
         tmem_ld8(gc + 16, gin);
@@ -979,21 +1013,30 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         tc_fence_before();
         mbar_arrive(&gempty[s % 3]);
       }
+      const uint32_t acc = taddr + 32u * (uint32_t)grp;             // this group's 32 columns inside every gate accumulator
       mbar_wait_warp(&done[0], ph, 13);
       tc_fence_after();
-      rw_reduce32(taddr, half, ar);
+      rw_reduce32(acc, half, ar);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
       mbar_wait_warp(&done[1], ph, 14);
       tc_fence_after();
-      rw_reduce32(taddr + 32, half, az);
+      rw_reduce32(acc + 32 * NG, half, az);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
       mbar_wait_warp(&done[2], ph, 15);
       tc_fence_after();
+      if constexpr (NBUF == 1) {
+        // every MMA of this step has finished reading the operand buffer (commits complete in order): tell the three peers that
+        // they may push h_t into it.  A pure "done reading" signal that publishes no data -> relaxed (see the BPTT kernel).
+        if (tid == 0 && s + 1 < steps) {
+#pragma unroll
+          for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(ofree), (c + r) & 3));
+        }
+      }
       RW_STAMP(3);
       if (tid == 0) RW_STAMP_CTA(1);
-      rw_reduce32(taddr + 64, half, an);
+      rw_reduce32(acc + 64 * NG, half, an);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         sg[i] = an[i] + bhn;
@@ -1009,12 +1052,16 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         ohv = phi; olv = plo;
       }
       tc_fence_before();
-      if (s + 1 < steps) {                                        // own chunk of operand buffer (s + 1) & 1, then tell the MMA lane
-        uint8_t* own = sH + (b ^ 1u) * NKC * RW_BTILE + c * RW_BTILE;
-        const uint32_t o_hi = RW_MN ? rw_mn_off(8 * half, j) : 2u * p16_in_tile(nrow, kloc);
-        const uint32_t o_lo = RW_MN ? rw_mn_off(16 + 8 * half, j) : 2u * p16_in_tile(16 + nrow, kloc);
+      if (s + 1 < steps) {                                        // own chunk of the next operand buffer, then tell the MMA lane
+        uint8_t* own = sH + nb * NKC * BT + c * BT;
+        const uint32_t o_hi = RW_MN ? mn_off(orow + 8 * half, j) : 2u * p16_in_tile(orow + nrow, kloc);
+        const uint32_t o_lo = RW_MN ? mn_off(orow + 16 + 8 * half, j) : 2u * p16_in_tile(orow + 16 + nrow, kloc);
         const uint32_t ohi = smem_u32(own) + o_hi, olo = smem_u32(own) + o_lo;
-        const uint32_t hbar = smem_u32(&hfull[b ^ 1u]);
+        const uint32_t hbar = smem_u32(&hfull[nb]);
+        if constexpr (NBUF == 1) {                                  // the peers' MMAs of this step are complete
+          mbar_wait_cluster_b(ofree, ph, 30);
+          __syncwarp();
+        }
 #pragma unroll
         for (uint32_t r = 1; r < 4; ++r) {                          // the same chunk position in the three peers' buffers
           const uint32_t peer = (c + r) & 3, pbar = mapa_u32(hbar, peer);
@@ -1024,7 +1071,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         *reinterpret_cast<uint4*>(own + o_hi) = ohv;
         *reinterpret_cast<uint4*>(own + o_lo) = olv;
         fence_proxy_async_smem();
-        mbar_arrive(&lfull[b ^ 1u]);
+        mbar_arrive(&lfull[nb]);
       }
       if constexpr (RW_MN && !SW) rw_transpose_pack(hn, lane, phi, plo);   // K-major P16 copy for the GEMMs (off the recurrence)
       RW_STAMP(5);
@@ -1034,10 +1081,10 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
       if (s + 1 < steps && !gi_const && !gi_tmem && !(a.exp & 2)) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { gir[i] = gir2[i]; giz[i] = giz2[i]; gin[i] = gin2[i]; }
-        if (s + 2 < steps) load_gi(s + 2, gir2, giz2, gin2);
+        if (s + 2 < steps) load_gi(grp, s + 2, gir2, giz2, gin2);
       }
       if constexpr (SW) {                                           // hand h_t and the saved gates to the store warps
-        const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+        const uint32_t sb = s & 1, stg = taddr + SBASE + 40u * (uint32_t)(2 * grp + (int)sb);
         if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 16);
         __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
@@ -1053,7 +1100,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
       }
       if constexpr (PRIV) {
         if (a.exp & 16) continue;                                   // (experiment 16: no global stores)
-        const long blk = pv_block(t, groups, blockIdx.y, c, q);
+        const long blk = pv_block(t, groups, gidx, c, q);
         st8p(d.out + blk, lane, hn);
         st8p(d.sv[0] + blk, lane, sr);
         st8p(d.sv[1] + blk, lane, sz);
@@ -1065,7 +1112,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
         st8(d.out + (long)u * d.out_ld + (long)so * Bp + b0, hn);
       }
       if (!(a.exp & 4)) {
-        const long row = (long)blockIdx.y * 16 + nrow;
+        const long row = gidx * 16 + nrow;
         const int k0 = (int)c * UC + kloc;
         __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
                             ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
@@ -1088,84 +1135,134 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_fw
   cluster_wait_acquire();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TCOLS);
+  if (warp == NGW) tmem_dealloc(tmem, TCOLS);
 }
 
 // SW: as in the forward kernel, four extra warps take over everything that is not on the recurrence - here the gate gradients
 // of step t travel through tensor memory (32 columns, double-buffered) and the store warps write the transposed P16 operands of
 // the weight-gradient GEMMs, the P16 copy for dx, and keep the bias-gradient / time sums.
-template <bool SUM, bool PRIV, bool SW>
-__global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
+// NG = 2 (see the forward kernel): 32 batch rows per cluster, N = 64 MMAs.  Two 24 KB receive slots no longer fit beside 192 KB
+// of weights, so the accumulator tile that is issued last (the CTA's own input units) takes its A operand from TENSOR MEMORY:
+// its 48 KB of W_hh^T (hi + lo rows x 192 k) are copied global -> registers -> tcgen05.st once before the sweep (96 columns,
+// column 8 ks + i of lane r = k elements 16 ks + 2 i, + 1 of tile row r) and only three tiles stay in shared memory.
+template <bool SUM, bool PRIV, bool SW, int NG>
+__global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
+  static_assert(NG == 1 || NG == 2, "one or two 16-row groups per cluster");
+  static_assert(!(SW && NG == 2), "the store-warp variant of the BPTT sweep (measured neutral) exists for 16-row clusters only");
   constexpr bool RW_MN = RW_MN_BWD != 0;
   constexpr int H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
-  constexpr int RSLOT = 3 * UC * 16 * 4;                          // 12288 B: 3 source slots = the 3 k chunks of the operand
-  static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
+  constexpr int NGW = 4 * NG, NGT = 128 * NG;                      // gate-math warps / threads
+  constexpr int RG = 16 * NG;                                      // batch rows of the cluster
+  constexpr int BT = RW_BTILE * NG;                                // one k chunk of the operand
+  constexpr int RSLOT = 3 * UC * RG * 4;                           // 3 source slots = the 3 k chunks of the operand
+  static_assert(RSLOT == NKB * BT, "receive slot and operand must have the same size");
+  constexpr bool WT = NG == 2;                                     // the own tile's A operand lives in tensor memory
+  constexpr int MS = WT ? 3 : 4;                                   // A tiles in shared memory
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sW = smem;                                             // [MT][NKB][RW_ATILE]
-  uint8_t* sR = smem + MT * NKB * RW_ATILE;                       // [2][RSLOT]
+  uint8_t* sW = smem;                                             // [MS][NKB][RW_ATILE]; WT: tile i = input units of CTA (c + 1 + i) & 3
+  uint8_t* sR = smem + MS * NKB * RW_ATILE;                       // [2][RSLOT]
   uint64_t* wbar = reinterpret_cast<uint64_t*>(sR + 2 * RSLOT);
   uint64_t* done = wbar + 1;                                      // [4] accumulator tiles, in issue order
-  uint64_t* ofull = done + 4;                                     // operand of this step written (128 arrivals)
-  uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x 4 warps have landed in slot b
-  uint64_t* mfree = pfull + 2;                                    // [2]: all MMAs of the 3 peers' step s are complete (3 x 4 warps), slot s & 1
-  uint64_t* sfull = mfree + 2;                                    // [2] SW: staging buffer b written by the 128 gate-math threads
-  uint64_t* sempty = sfull + 2;                                   // [2] SW: ... read back by the 128 store threads
+  uint64_t* ofull = done + 4;                                     // operand of this step written (NGT arrivals)
+  uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x NGW warps have landed in slot b
+  uint64_t* mfree = pfull + 2;                                    // [2]: all MMAs of the 3 peers' step s are complete (3 x NGW warps), slot s & 1
+  uint64_t* sfull = mfree + 2;                                    // [2] SW: staging buffer b written by the NGT gate-math threads
+  uint64_t* sempty = sfull + 2;                                   // [2] SW: ... read back by the NGT store threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);  // (mfree: a peer may signal step s + 1 before this CTA has looked at step s)
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirBwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
-  const int q = warp, half = lane >> 4, oct = (lane >> 3) & 1;
-  const bool epi = warp < 4;
+  const int q = warp & 3, half = lane >> 4, oct = (lane >> 3) & 1;
+  const bool epi = warp < NGW;
+  const bool stw = SW && warp > NGW;
+  const int grp = epi ? (warp >> 2) : (stw ? ((warp - NGW - 1) >> 2) : 0);
+  const long gidx = (long)blockIdx.y * NG + grp;
   const long bpad = (long)a.tiles * 128;
   const int steps = a.steps;
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int m = 0; m < 4; ++m) mbar_init(&done[m], 1);
-    mbar_init(ofull, 128);
+    mbar_init(ofull, NGT);
     mbar_init(&pfull[0], 1);
     mbar_init(&pfull[1], 1);
-    mbar_init(&mfree[0], 12);
-    mbar_init(&mfree[1], 12);
+    mbar_init(&mfree[0], 3 * NGW);
+    mbar_init(&mfree[1], 3 * NGW);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sfull[b], 128);
-      mbar_init(&sempty[b], 128);
+      mbar_init(&sfull[b], NGT);
+      mbar_init(&sempty[b], NGT);
     }
     mbar_fence_init();
   }
-  constexpr uint32_t TCOLS = SW ? 256 : 128;                      // accumulators: columns 0-127; SW staging: 128 + 64 b + [0, 32)
-  if (warp == 4) tmem_alloc(tmem_slot, TCOLS);
+  // tensor-memory columns: accumulator tile i, group p at 32 (NG i + p); WT: own A tile at WCOL + [0, 96); SW staging (32 columns)
+  // of group p, buffer b at SBASE + 32 (2 p + b)
+  constexpr uint32_t WCOL = 128 * NG, SBASE = WT ? WCOL + 96 : 128;
+  constexpr uint32_t TCOLS = WT ? 512 : (SW ? 256 : 128);
+  static_assert(!SW || SBASE + 64 * NG <= TCOLS, "tensor-memory budget");
+  if (warp == NGW) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
 
-  if (warp == 4) {
+  const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
+  if (warp == NGW) {
     if (elect_one()) {
-      const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(d.wT_rw) + (size_t)c * MT * NKB * (RW_ATILE / 2);
-      mbar_expect_tx(wbar, MT * NKB * RW_ATILE);
-      for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+      mbar_expect_tx(wbar, MS * NKB * RW_ATILE);
+      if constexpr (WT) {
+        for (uint32_t i = 0; i < 3; ++i) {
+          const uint32_t m = (c + 1 + i) & 3;
+          for (int kc = 0; kc < NKB; ++kc)
+            bulk_g2s(sW + (size_t)(i * NKB + kc) * RW_ATILE, wp + (size_t)(m * NKB + kc) * (RW_ATILE / 2), RW_ATILE, wbar);
+        }
+      } else {
+        for (int i = 0; i < MT * NKB; ++i) bulk_g2s(sW + (size_t)i * RW_ATILE, wp + (size_t)i * (RW_ATILE / 2), RW_ATILE, wbar);
+      }
     }
     __syncwarp();
   }
-  // arm the receive barriers of the first two steps' pushes (3 peers x 64 units x 16 rows x 4 B); later phases are armed by
+  if constexpr (WT) {
+    if (warp < 4) {                                               // tile row 32 q + lane -> the same tensor-memory lane
+      const int r = 32 * q + lane;
+      const uint8_t* tile = reinterpret_cast<const uint8_t*>(wp + (size_t)(c * NKB) * (RW_ATILE / 2));
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint8_t* src = tile + (size_t)(ks >> 2) * RW_ATILE + ((r >> 3) * 8 + (ks & 3) * 2) * 128 + (r & 7) * 16;
+        const uint4 v0 = *reinterpret_cast<const uint4*>(src), v1 = *reinterpret_cast<const uint4*>(src + 128);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + WCOL + ks * 8), "r"(v0.x),
+                     "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w)
+                     : "memory");
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+  }
+  // arm the receive barriers of the first two steps' pushes (3 peers x 64 units x RG rows x 4 B); later phases are armed by
   // thread 0 right after it has consumed the previous phase of the same slot, i.e. before any peer can push into it again
   if (tid == 0) {
     mbar_expect_tx(&pfull[0], RSLOT);
     if (steps > 1) mbar_expect_tx(&pfull[1], RSLOT);
   }
+  if constexpr (WT) __syncthreads();                              // the tensor-memory A tile is complete before the MMA lane starts
   cluster_arrive_release();
   cluster_wait_acquire();
 
-  const int j = 16 * (q & 3) + (lane & 15);
+  const int j = 16 * q + (lane & 15);
   const int u = (int)c * UC + j;
-  const long b0 = (long)blockIdx.y * 16 + 8 * half;
+  const long b0 = gidx * 16 + 8 * half;
   const int nrow = 8 * half + (lane & 7);
-  const int kq = 16 * (q & 3) + 8 * oct;
-  const uint32_t idesc = rw_idesc(RW_MN);
-  const uint32_t taddr = tmem + ((uint32_t)((q & 3) * 32) << 16);
+  const int orow = 32 * grp;                                      // first operand row of the group
+  const int kq = 16 * q + 8 * oct;
+  constexpr uint32_t idesc = make_idesc_bf16(128, 32 * NG) | (RW_MN ? (1u << 16) : 0u);
+  auto b_off = [&](int n, int k) -> uint32_t { return (uint32_t)(k >> 6) * BT + 2u * (uint32_t)p16_in_tile(n, k & 63); };
+  auto mn_off = [&](int n0, int k) -> uint32_t {
+    return (uint32_t)(k >> 6) * BT + (uint32_t)((n0 >> 3) * 1024 + ((k & 63) >> 3) * 128 + (k & 7) * 16);
+  };
+  // fp32 partial sums in a receive slot: [source slot: 3][unit: 64][row: RG]
+  auto part_off = [&](int slot, int unit) -> uint32_t { return (uint32_t)(((slot * UC + unit) * RG + 16 * grp + 8 * half) * 4); };
 
   float carry[8], own[8];
   float sum_r[SUM ? 8 : 1], sum_z[SUM ? 8 : 1], sum_n[SUM ? 8 : 1];
@@ -1182,13 +1279,13 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
     const bool first_fwd = d.reverse ? (t == steps - 1) : (t == 0);
     const int tprev = d.reverse ? t + 1 : t - 1;
     if constexpr (PRIV) {
-      const long blk = pv_block(t, bpad / 16, blockIdx.y, c, q);
+      const long blk = pv_block(t, bpad / 16, gidx, c, q);
       ld8p(d.sv[0] + blk, lane, r);
       ld8p(d.sv[1] + blk, lane, z);
       ld8p(d.sv[2] + blk, lane, n);
       ld8p(d.sv[3] + blk, lane, ghn);
       if (first_fwd) ld8(d.h0 + (long)u * d.h0_ld + b0, hp);
-      else ld8p(d.out + pv_block(tprev, bpad / 16, blockIdx.y, c, q), lane, hp);
+      else ld8p(d.out + pv_block(tprev, bpad / 16, gidx, c, q), lane, hp);
     } else {
       const long so = (long)u * d.sv_ld + (long)t * bpad + b0;
       ld8(d.sv[0] + so, r);
@@ -1199,7 +1296,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       else ld8(d.out + (long)u * d.out_ld + (long)tprev * bpad + b0, hp);
     }
     if (d.dout) {
-      if (PRIV && d.dout_pv) ld8p(d.dout + pv_block(t, bpad / 16, blockIdx.y, c, q), lane, dh);
+      if (PRIV && d.dout_pv) ld8p(d.dout + pv_block(t, bpad / 16, gidx, c, q), lane, dh);
       else ld8(d.dout + (long)u * d.dout_ld + (long)t * bpad + b0, dh);
     }
     else {
@@ -1217,7 +1314,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
     const uint32_t ph = s & 1;
     uint8_t* rprev = sR + (ph ^ 1u) * RSLOT;                      // partial sums of step s - 1; then this step's operand
     RW_STAMP(0);
-    if (warp == 4) {
+    if (warp == NGW) {
       if (elect_one()) {
         if (s == 0) mbar_wait_b(wbar, 0, 20);
         mbar_wait_b(ofull, ph, 21);
@@ -1226,22 +1323,27 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
         const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
 #pragma unroll
         for (uint32_t i = 0; i < 4; ++i) {                        // peers' tiles first, the own tile last
-          const uint32_t m = (c + 1 + i) & 3;
+          const uint32_t m = WT ? i : ((c + 1 + i) & 3);          // WT: shared memory holds the tiles in issue order
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
-            const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
-            const uint32_t bo = (ks >> 2) * RW_BTILE + (ks & 3) * 2 * ATOM_BYTES;
-            if (ks == 0) umma_bf16_c<0>(tmem + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
-            else umma_bf16_c<1>(tmem + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            const uint32_t bo = (ks >> 2) * BT + (ks & 3) * 2 * ATOM_BYTES;
+            if (WT && i == 3) {
+              if (ks == 0) umma_bf16_ta<0>(tmem + i * 32 * NG, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
+              else umma_bf16_ta<1>(tmem + i * 32 * NG, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
+            } else {
+              const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
+              if (ks == 0) umma_bf16_c<0>(tmem + i * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              else umma_bf16_c<1>(tmem + i * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+            }
           }
           umma_commit(&done[i]);
         }
         RW_STAMP_MMA(3);
       }
       __syncwarp();
-    } else if (SW && warp >= 5) {                                   // ---- store warp of TMEM lane quarter q & 3 ----
+    } else if (stw) {                                               // ---- store warp of TMEM lane quarter q, group grp ----
       float dar[8], daz[8], dan[8], dgn[8];
-      const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+      const uint32_t sb = s & 1, stg = taddr + SBASE + 32u * (uint32_t)(2 * grp + (int)sb);
       mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 26);
       tc_fence_after();
       tmem_ld8(stg, dar);
@@ -1268,7 +1370,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       }
       if (d.dgi_p) {
         constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
-        const long row = (long)blockIdx.y * 16 + nrow;
+        const long row = gidx * 16 + nrow;
         __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
                               (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
         const int rr = (int)(row & 127);
@@ -1283,7 +1385,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
           *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
         }
       }
-    } else {
+    } else if (epi) {
       float dar[8], daz[8], dan[8], dgn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] += carry[i] + own[i];
@@ -1297,7 +1399,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
 #pragma unroll
         for (int src = 0; src < 3; ++src) {
           float v[8];
-          ld8s(reinterpret_cast<const float*>(rprev) + ((src * UC + j) * 16 + 8 * half), v);
+          ld8s(reinterpret_cast<const float*>(rprev + part_off(src, j)), v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dh[i] += v[i];
         }
@@ -1314,28 +1416,28 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
         if constexpr (SUM && !SW) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
         if constexpr (PRIV && !SW) { bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i]; }
       }
-      epi_bar_sync();                                             // everyone has consumed rprev before it becomes the operand
+      asm volatile("bar.sync 1, %0;" ::"n"(NGT) : "memory");        // everyone has consumed rprev before it becomes the operand
       uint4 rhi, rlo, zhi, zlo, ghi, glo;
       if constexpr (RW_MN) {
         split8(dar, rhi, rlo);
         split8(daz, zhi, zlo);
         split8(dgn, ghi, glo);
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, j)) = rhi;
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, j)) = rlo;
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, UC + j)) = zhi;
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, UC + j)) = zlo;
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, 2 * UC + j)) = ghi;
-        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, 2 * UC + j)) = glo;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, j)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, j)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, UC + j)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, UC + j)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, 2 * UC + j)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, 2 * UC + j)) = glo;
       } else {
         rw_transpose_pack(dar, lane, rhi, rlo);
         rw_transpose_pack(daz, lane, zhi, zlo);
         rw_transpose_pack(dgn, lane, ghi, glo);
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
-        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, kq)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, kq)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, UC + kq)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, UC + kq)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, 2 * UC + kq)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, 2 * UC + kq)) = glo;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1346,13 +1448,14 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       // ---- while the MMAs run: next step's inputs ----
       if (s + 1 < steps && !(a.exp & 64)) load_step(s + 1);          // (experiment 64: no global loads)
       // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
+      const uint32_t acc = taddr + 32u * (uint32_t)grp;             // this group's 32 columns inside every accumulator tile
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {
         mbar_wait_warp(&done[i], ph, 24);
         tc_fence_after();
         RW_STAMP(6 + i);
         float part[8];
-        rw_reduce32(taddr + i * 32, half, part);
+        rw_reduce32(acc + i * 32 * NG, half, part);
         if (i == 0 && s > 0) {
           // the receive slot written below is the peers' operand of step s - 1: their MMAs of that step must be complete
           // (signalled long ago - this wait only makes the ordering a guarantee instead of a timing margin)
@@ -1362,7 +1465,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
         if (i < 3) {
           const uint32_t owner = (c + 1 + i) & 3;
           const uint32_t slot = (c - owner - 1) & 3;             // = 2 - i: position of this CTA among the owner's three peers
-          const uint32_t off = smem_u32(sR) + ph * RSLOT + (uint32_t)(((slot * UC + j) * 16 + 8 * half) * 4);
+          const uint32_t off = smem_u32(sR) + ph * RSLOT + part_off((int)slot, j);
           const uint32_t ra = mapa_u32(off, owner), pbar = mapa_u32(smem_u32(&pfull[ph]), owner);
           st_async_f4(ra, part[0], part[1], part[2], part[3], pbar);
           st_async_f4(ra + 16, part[4], part[5], part[6], part[7], pbar);
@@ -1388,7 +1491,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       // ---- this step's outputs (weight-gradient GEMMs, dx of the layer below): after the pushes, because a release at
       //      cluster scope waits for every earlier store of the thread ----
       if constexpr (SW) {                                           // hand the gate gradients to the store warps
-        const uint32_t sb = s & 1, stg = taddr + 128 + 64 * sb;
+        const uint32_t sb = s & 1, stg = taddr + SBASE + 32u * (uint32_t)(2 * grp + (int)sb);
         if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 27);
         __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
@@ -1428,7 +1531,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
             rw_transpose_pack(daz, lane, zhi, zlo);
           }
           constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
-          const long row = (long)blockIdx.y * 16 + nrow;
+          const long row = gidx * 16 + nrow;
           __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
                                 (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
           const int rr = (int)(row & 127);
@@ -1456,13 +1559,13 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
 #pragma unroll
     for (int src = 0; src < 3; ++src) {
       float v[8];
-      ld8s(reinterpret_cast<const float*>(rl) + ((src * UC + j) * 16 + 8 * half), v);
+      ld8s(reinterpret_cast<const float*>(rl + part_off(src, j)), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g0[i] += v[i];
     }
     st8(d.dh0_out + (long)u * bpad + b0, g0);
   }
-  if (SW ? (warp >= 5) : epi) {
+  if (SW ? stw : epi) {
     if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
 #pragma unroll
       for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
@@ -1476,7 +1579,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
       st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
       st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
       constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
-      const long row = (long)blockIdx.y * 16 + nrow;
+      const long row = gidx * 16 + nrow;
       __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
       const int rr = (int)(row & 127);
 #pragma unroll
@@ -1495,7 +1598,7 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
   cluster_wait_acquire();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TCOLS);
+  if (warp == NGW) tmem_dealloc(tmem, TCOLS);
 }
 
 // =================================================================================================
@@ -1503,9 +1606,16 @@ __global__ void __launch_bounds__(SW ? RW_SW_THREADS : RW_THREADS, 1) gru_rw2_bw
 // =================================================================================================
 // private interchange layouts: both sweeps of the layer must run on the H = 256 barrier-free kernels
 bool rw_priv_mode(int H, int tiles) { return g_opt_rw_priv && g_opt_rw == 3 && g_opt_rw2 && H == 256 && rw_applicable(H, tiles); }
+// 16-row groups per cluster of the H = 256 kernels: one while the sweep fits one wave of the SMs a cluster-of-4 launch can use
+// (132 of 148), otherwise two (32 rows per cluster, N = 64 MMAs at the cost of N = 32 ones); option rw_ng forces 1 or 2
+int rw_groups_per_cluster(int H, int tiles) {
+  if (H != 256 || !g_opt_rw2) return 1;
+  if (g_opt_rw_ng == 1 || g_opt_rw_ng == 2) return g_opt_rw_ng;
+  return tiles * 8 * 2 * 4 <= 132 ? 1 : 2;
+}
 bool rw_applicable(int H, int tiles) {
-  // one wave: 2 directions x (B_pad / 16) clusters x 4 CTAs must fit the SMs a cluster-of-4 launch can use (132 of 148)
-  return H >= 64 && H <= 256 && H % 64 == 0 && tiles >= 1 && tiles * 8 * 2 * 4 <= 132 * g_opt_rw_waves;
+  // 2 directions x (B_pad / 16 / groups per cluster) clusters x 4 CTAs must fit the allowed number of waves
+  return H >= 64 && H <= 256 && H % 64 == 0 && tiles >= 1 && tiles * 8 / rw_groups_per_cluster(H, tiles) * 2 * 4 <= 132 * g_opt_rw_waves;
 }
 size_t rw_whh_bytes(int H) { return (size_t)4 * 3 * (H / 64) * RW_ATILE; }
 size_t rw_whhT_bytes(int H) {
@@ -1531,6 +1641,15 @@ static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, c
   cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+template <int NG>
+static void rw2_launch_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
+  const int groups = a.tiles * 8 / NG;
+  const size_t smem = (size_t)12 * RW_ATILE + (size_t)(NG == 1 ? 2 : 1) * 4 * RW_BTILE * NG + 256;
+  if (a.d[0].priv && (g_opt_rw_sw & 1)) rw_launch(gru_rw2_fwd_kernel<true, true, NG>, a, smem, groups, a.ndir, st, (4 * NG + 5) * 32);
+  else if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true, false, NG>, a, smem, groups, a.ndir, st, (4 * NG + 1) * 32);
+  else rw_launch(gru_rw2_fwd_kernel<false, false, NG>, a, smem, groups, a.ndir, st, (4 * NG + 1) * 32);
+}
+
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   GruSeqFwdArgs a = a_in;
   a.dbg = g_dbg_buffer;
@@ -1539,9 +1658,8 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   const size_t smem = (size_t)3 * nkc * RW_ATILE + (size_t)2 * nkc * RW_BTILE + 256;
   count_launch();
   if (nkc == 4 && g_opt_rw2) {
-    if (a.d[0].priv && (g_opt_rw_sw & 1)) rw_launch(gru_rw2_fwd_kernel<true, true>, a, smem, groups, a.ndir, st, RW_SW_THREADS);
-    else if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true, false>, a, smem, groups, a.ndir, st);
-    else rw_launch(gru_rw2_fwd_kernel<false, false>, a, smem, groups, a.ndir, st);
+    if (rw_groups_per_cluster(a.H, a.tiles) == 2) rw2_launch_fwd<2>(a, st);
+    else rw2_launch_fwd<1>(a, st);
     return;
   }
   switch (nkc) {
@@ -1552,6 +1670,20 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
   }
 }
 
+template <bool SUM, int NG>
+static void rw2_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
+  const int groups = a.tiles * 8 / NG;
+  const size_t sm2 = (size_t)(NG == 2 ? 9 : 12) * RW_ATILE + (size_t)2 * 12288 * NG + 256;
+  if constexpr (NG == 1) {
+    if (a.d[0].priv && (g_opt_rw_sw & 2)) {
+      rw_launch(gru_rw2_bwd_kernel<SUM, true, true, 1>, a, sm2, groups, a.ndir, st, 9 * 32);
+      return;
+    }
+  }
+  if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true, false, NG>, a, sm2, groups, a.ndir, st, (4 * NG + 1) * 32);
+  else rw_launch(gru_rw2_bwd_kernel<SUM, false, false, NG>, a, sm2, groups, a.ndir, st, (4 * NG + 1) * 32);
+}
+
 template <bool SUM>
 static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const int nkc = a.H / 64, groups = a.tiles * 8, UC = a.H / 4;
@@ -1559,10 +1691,8 @@ static void rw_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const size_t rslot = (size_t)(4 * UC * 16 * 4 > nkb * RW_BTILE ? 4 * UC * 16 * 4 : nkb * RW_BTILE);
   const size_t smem = (size_t)nkc * nkb * RW_ATILE + 2 * rslot + 256;
   if (nkc == 4 && g_opt_rw2) {
-    const size_t sm2 = (size_t)12 * RW_ATILE + 2 * 12288 + 256;
-    if (a.d[0].priv && (g_opt_rw_sw & 2)) rw_launch(gru_rw2_bwd_kernel<SUM, true, true>, a, sm2, groups, a.ndir, st, RW_SW_THREADS);
-    else if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true, false>, a, sm2, groups, a.ndir, st);
-    else rw_launch(gru_rw2_bwd_kernel<SUM, false, false>, a, sm2, groups, a.ndir, st);
+    if (rw_groups_per_cluster(a.H, a.tiles) == 2) rw2_launch_bwd<SUM, 2>(a, st);
+    else rw2_launch_bwd<SUM, 1>(a, st);
     return;
   }
   switch (nkc) {

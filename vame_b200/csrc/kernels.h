@@ -22,6 +22,7 @@ extern int g_opt_rw2;        // 1: H = 256 sweeps use the barrier-free rw kernel
 extern int g_opt_rw_sw;     // bit 0 / bit 1: forward / backward private-mode sweeps hand their global stores to extra store warps through tensor memory
 extern int g_opt_rw_priv;   // 1: training sweeps of H = 256 layers use the private interchange layouts (needs rw = 3 and rw2 = 1)
 extern int g_opt_rw_waves;
+extern int g_opt_rw_ng;      // 16-row groups per cluster of the H = 256 rw kernels (0 = automatic)
 extern int g_opt_rw_exp;      // measurement experiments (wrong results), see GruSeqFwdArgs::exp   // rw kernels are used while their grid fits this many waves of the 132 cluster-schedulable SMs
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
@@ -176,6 +177,7 @@ void launch_gru_seq_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 
 // ---- gru_rw.cu: resident-weight sweeps (4-CTA clusters, swap-AB, h / partial sums exchanged through DSMEM) ----
 bool rw_applicable(int H, int tiles);
+int rw_groups_per_cluster(int H, int tiles);   // 1 or 2 (H = 256: 32 rows per cluster when one wave of 16-row clusters does not fit)
 bool rw_priv_mode(int H, int tiles);   // training sweeps use the private interchange layouts (see GruSeqDirFwd::priv)
 size_t rw_whh_bytes(int H);       // packed W_hh of one direction, forward format
 size_t rw_whhT_bytes(int H);      // ... backward format

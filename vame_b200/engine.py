@@ -91,6 +91,9 @@ class Engine:
         self.grad = None
         self.packed = None
         self._packed_version = None
+        self._external_dirty = True        # weights changed outside TrainStep since the last FULL re-pack
+        self._watched = ()                 # tensors whose version counters are part of the weight version (nn.Parameters bound to flat)
+        self._train_gen = {}               # batch size -> generation of the saved activations in the training workspace
         self._ws = {}
         self.hyper = None
         self.opt_state = None
@@ -125,21 +128,36 @@ class Engine:
     def state_dict(self):
         return OrderedDict((k, t.detach().clone()) for k, t in self.views().items())
 
-    def mark_dirty(self):
-        self._packed_version = None
+    def _dev(self):
+        """Every C-ABI call is enqueued on the current stream of the ENGINE's device, whatever the caller's current device is."""
+        return torch.cuda.device(self.device)
 
-    def _ensure_packed(self):
-        ver = self.flat._version
-        if self._packed_version != ver:
-            L.check(self.lib.vame_pack_weights(ctypes.byref(self.dims), L.ptr(self.flat), L.ptr(self.packed), L.cur_stream()),
-                    "vame_pack_weights")
-            self._packed_version = ver
+    def watch(self, tensors):
+        """Tensors that alias ``flat`` but keep their own version counters (``p.data = view`` gives the nn.Parameter its own
+        counter: optimizer.step() / p.copy_() bump p._version, not flat._version).  Their counters become part of the version
+        that decides whether the packed tensor-core copies are stale."""
+        self._watched = tuple(tensors)
+
+    def _version(self):
+        return (self.flat._version,) + tuple(t._version for t in self._watched)
+
+    def mark_dirty(self):
+        """The fp32 weights changed behind the engine's back (load_state_dict, manual edits): full re-pack on next use."""
+        self._packed_version = None
+        self._external_dirty = True
+
+    def _ensure_packed(self, force=False):
+        ver = self._version()
+        if force or self._packed_version != ver:
+            self.pack_weights()
 
     def pack_weights(self):
         """Unconditionally refresh the tensor-core weight copies on the current stream (graph-capturable)."""
-        L.check(self.lib.vame_pack_weights(ctypes.byref(self.dims), L.ptr(self.flat), L.ptr(self.packed), L.cur_stream()),
-                "vame_pack_weights")
-        self._packed_version = self.flat._version
+        with self._dev():
+            L.check(self.lib.vame_pack_weights(ctypes.byref(self.dims), L.ptr(self.flat), L.ptr(self.packed), L.cur_stream()),
+                    "vame_pack_weights")
+        self._packed_version = self._version()
+        self._external_dirty = False
 
     def workspace(self, batch, training):
         key = (int(batch), bool(training))
@@ -173,11 +191,14 @@ class Engine:
                 out[k] = torch.empty(B, d.zdims, device=self.device)
         if eps is not None:
             eps = eps.contiguous()
-        L.check(self.lib.vame_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(x), x.stride(0), x.stride(1),
-                                      L.ptr(eps), int(save), L.ptr(out.get("pred")), L.ptr(out.get("future")), L.ptr(out.get("z")),
-                                      L.ptr(out.get("mu")), L.ptr(out.get("logvar")), L.ptr(ws), ws.numel(), L.cur_stream()),
-                "vame_forward")
+        with self._dev():
+            L.check(self.lib.vame_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(x), x.stride(0), x.stride(1),
+                                          L.ptr(eps), int(save), L.ptr(out.get("pred")), L.ptr(out.get("future")), L.ptr(out.get("z")),
+                                          L.ptr(out.get("mu")), L.ptr(out.get("logvar")), L.ptr(ws), ws.numel(), L.cur_stream()),
+                    "vame_forward")
         self._last = (B, bool(save))
+        if save:                             # the training workspace of this batch size now holds THIS forward's activations
+            self._train_gen[B] = self._train_gen.get(B, 0) + 1
         return out
 
     def loss_cfg(self, mse_red="sum", mse_pred="sum", kmeans_loss=None, kmeans_lambda=0.1, bsize=None, beta=1.0, kl_weight=1.0,
@@ -205,24 +226,32 @@ class Engine:
             if target.stride(2) != 1:
                 target = target.contiguous()
             ts0, ts1 = target.stride(0), target.stride(1)
-        L.check(self.lib.vame_loss(ctypes.byref(self.dims), B, ctypes.byref(cfg), L.ptr(fut), fs0, fs1, L.ptr(target), ts0, ts1,
-                                   L.ptr(self.hyper) if use_hyper else None, L.ptr(out), int(want_grads), L.ptr(ws), ws.numel(),
-                                   L.cur_stream()), "vame_loss")
+        with self._dev():
+            L.check(self.lib.vame_loss(ctypes.byref(self.dims), B, ctypes.byref(cfg), L.ptr(fut), fs0, fs1, L.ptr(target), ts0, ts1,
+                                       L.ptr(self.hyper) if use_hyper else None, L.ptr(out), int(want_grads), L.ptr(ws), ws.numel(),
+                                       L.cur_stream()), "vame_loss")
         return out
 
-    def backward(self, cfg=None, use_loss_grads=True, use_hyper=False, dpred=None, dfuture=None, dz=None, dmu=None, dlogvar=None):
-        """loss.backward(): fills self.grad (flat, overwritten)."""
-        B, save = self._last
-        assert save, "backward needs forward(save=True)"
+    def backward(self, cfg=None, use_loss_grads=True, use_hyper=False, dpred=None, dfuture=None, dz=None, dmu=None, dlogvar=None,
+                 batch=None):
+        """loss.backward(): fills self.grad (flat, overwritten).  ``batch``: batch size of the forward(save=True) whose saved
+        activations are to be used (default: the last forward, which must have been a saving one)."""
+        if batch is None:
+            B, save = self._last
+            assert save, "backward needs forward(save=True)"
+        else:
+            B = int(batch)
+            assert B in self._train_gen, "backward needs forward(save=True) of this batch size"
         ws = self.workspace(B, True)
 
         def c(t):
             return None if t is None else t.contiguous()
         dpred, dfuture, dz, dmu, dlogvar = c(dpred), c(dfuture), c(dz), c(dmu), c(dlogvar)
-        L.check(self.lib.vame_backward(ctypes.byref(self.dims), B, L.ptr(self.flat), L.ptr(self.packed), int(use_loss_grads),
-                                       ctypes.byref(cfg) if cfg is not None else None, L.ptr(self.hyper) if use_hyper else None,
-                                       L.ptr(dpred), L.ptr(dfuture), L.ptr(dz), L.ptr(dmu), L.ptr(dlogvar), L.ptr(self.grad), L.ptr(ws),
-                                       ws.numel(), L.cur_stream()), "vame_backward")
+        with self._dev():
+            L.check(self.lib.vame_backward(ctypes.byref(self.dims), B, L.ptr(self.flat), L.ptr(self.packed), int(use_loss_grads),
+                                           ctypes.byref(cfg) if cfg is not None else None, L.ptr(self.hyper) if use_hyper else None,
+                                           L.ptr(dpred), L.ptr(dfuture), L.ptr(dz), L.ptr(dmu), L.ptr(dlogvar), L.ptr(self.grad), L.ptr(ws),
+                                           ws.numel(), L.cur_stream()), "vame_backward")
         return self.grad
 
     def init_optimizer(self):
@@ -236,14 +265,15 @@ class Engine:
     def adam_step(self, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, use_hyper=False, repack=True):
         """torch.optim.Adam(amsgrad=True).step() on the flat buffers (+ refresh of the packed weights)."""
         s = self.init_optimizer()
-        L.check(self.lib.vame_adam_step(L.ptr(self.flat), L.ptr(self.grad), L.ptr(s["exp_avg"]), L.ptr(s["exp_avg_sq"]),
-                                        L.ptr(s["max_exp_avg_sq"]), self.n_flat, float(lr), L.ptr(self.hyper) if use_hyper else None,
-                                        L.ptr(s["step"]), L.ptr(s["scratch"]), float(betas[0]), float(betas[1]), float(eps),
-                                        float(grad_scale), L.cur_stream()), "vame_adam_step")
+        with self._dev():
+            L.check(self.lib.vame_adam_step(L.ptr(self.flat), L.ptr(self.grad), L.ptr(s["exp_avg"]), L.ptr(s["exp_avg_sq"]),
+                                            L.ptr(s["max_exp_avg_sq"]), self.n_flat, float(lr), L.ptr(self.hyper) if use_hyper else None,
+                                            L.ptr(s["step"]), L.ptr(s["scratch"]), float(betas[0]), float(betas[1]), float(eps),
+                                            float(grad_scale), L.cur_stream()), "vame_adam_step")
         if repack:
             self.pack_weights()
         else:
-            self.mark_dirty()
+            self._packed_version = None      # (the caller re-packs what it needs; any other consumer re-packs fully)
 
     def set_hyper(self, lr=None, kl_weight=None, beta=None, kmeans_lambda=None):
         vals = self.hyper.tolist() if any(v is None for v in (lr, kl_weight, beta, kmeans_lambda)) else [0.0] * 8
@@ -261,8 +291,9 @@ class Engine:
         self._ensure_packed()
         ws = self.workspace(B, False)
         hidden = torch.empty(B, 4 * d.hidden_enc, device=self.device)
-        L.check(self.lib.vame_encoder_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(x), x.stride(0), x.stride(1),
-                                              L.ptr(hidden), L.ptr(ws), ws.numel(), L.cur_stream()), "vame_encoder_forward")
+        with self._dev():
+            L.check(self.lib.vame_encoder_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(x), x.stride(0), x.stride(1),
+                                                  L.ptr(hidden), L.ptr(ws), ws.numel(), L.cur_stream()), "vame_encoder_forward")
         return hidden
 
     def lambda_forward(self, hidden, eps=None):
@@ -272,9 +303,10 @@ class Engine:
         self._ensure_packed()
         ws = self.workspace(B, False)
         z, mu, lv = (torch.empty(B, d.zdims, device=self.device) for _ in range(3))
-        L.check(self.lib.vame_lambda_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(hidden),
-                                             L.ptr(eps.contiguous()) if eps is not None else None, L.ptr(z), L.ptr(mu), L.ptr(lv),
-                                             L.ptr(ws), ws.numel(), L.cur_stream()), "vame_lambda_forward")
+        with self._dev():
+            L.check(self.lib.vame_lambda_forward(ctypes.byref(d), B, L.ptr(self.flat), L.ptr(self.packed), L.ptr(hidden),
+                                                 L.ptr(eps.contiguous()) if eps is not None else None, L.ptr(z), L.ptr(mu), L.ptr(lv),
+                                                 L.ptr(ws), ws.numel(), L.cur_stream()), "vame_lambda_forward")
         return z, mu, lv
 
     def decoder_forward(self, z, which=0):
@@ -285,8 +317,9 @@ class Engine:
         ws = self.workspace(B, False)
         steps = d.time_window if which == 0 else d.future_steps
         pred = torch.empty(B, steps, d.num_features, device=self.device)
-        L.check(self.lib.vame_decoder_forward(ctypes.byref(d), B, int(which), L.ptr(self.flat), L.ptr(self.packed), L.ptr(z), L.ptr(pred),
-                                              L.ptr(ws), ws.numel(), L.cur_stream()), "vame_decoder_forward")
+        with self._dev():
+            L.check(self.lib.vame_decoder_forward(ctypes.byref(d), B, int(which), L.ptr(self.flat), L.ptr(self.packed), L.ptr(z), L.ptr(pred),
+                                                  L.ptr(ws), ws.numel(), L.cur_stream()), "vame_decoder_forward")
         return pred
 
     def embed(self, series_nf, first_window=0, n_windows=None, chunk=8192, out=None):
@@ -309,8 +342,9 @@ class Engine:
         if out is None:
             out = torch.empty(n_windows, d.zdims, device=self.device)
         if n_windows > 0:
-            L.check(self.lib.vame_embed_windows(ctypes.byref(d), L.ptr(self.flat), L.ptr(self.packed), L.ptr(series_nf), N, int(first_window),
-                                                n_windows, chunk, L.ptr(out), L.ptr(ws), ws.numel(), L.cur_stream()), "vame_embed_windows")
+          with self._dev():
+              L.check(self.lib.vame_embed_windows(ctypes.byref(d), L.ptr(self.flat), L.ptr(self.packed), L.ptr(series_nf), N, int(first_window),
+                                                    n_windows, chunk, L.ptr(out), L.ptr(ws), ws.numel(), L.cur_stream()), "vame_embed_windows")
         return out
 
     def cluster_loss(self, latent, kloss, lmbda, bsize, grad_coef=1.0, want_grad=False):
@@ -318,8 +352,9 @@ class Engine:
         B, Z = latent.shape
         loss = torch.zeros(1, dtype=torch.float64, device=latent.device)
         dl = torch.empty_like(latent) if want_grad else None
-        L.check(self.lib.vame_cluster_loss(L.ptr(latent), B, Z, int(kloss), float(lmbda), float(bsize), float(grad_coef), L.ptr(loss),
-                                           L.ptr(dl), L.cur_stream()), "vame_cluster_loss")
+        with self._dev():
+            L.check(self.lib.vame_cluster_loss(L.ptr(latent), B, Z, int(kloss), float(lmbda), float(bsize), float(grad_coef), L.ptr(loss),
+                                               L.ptr(dl), L.cur_stream()), "vame_cluster_loss")
         return loss, dl
 
 
@@ -466,6 +501,8 @@ class TrainStep:
 
     def run(self):
         """Executes one step on the static buffers; returns the device loss vector."""
+        if self.eng._external_dirty:         # load_state_dict / manual weight edits since the last full re-pack
+            self.eng.pack_weights()
         if self._staged:
             self._take_staged()
         if self.graphs is not None:
@@ -480,5 +517,7 @@ class TrainStep:
                 self.graphs[1].replay()
         else:
             self._phase2()
-        self.eng.mark_dirty()                # partial re-pack (and: a graph replay does not run adam_step's Python side)
+        # partial re-pack (only the formats this batch size reads): any other consumer re-packs fully (_ensure_packed); an
+        # EXTERNAL weight change is tracked separately (Engine._external_dirty) and picked up at the top of run()
+        self.eng._packed_version = None
         return self.losses

@@ -110,13 +110,20 @@ def _engine_of(sub):
 
 
 class _RNNVAEFunction(torch.autograd.Function):
-    """Whole-model autograd node: forward and backward both run in the CUDA library."""
+    """Whole-model autograd node: forward and backward both run in the CUDA library.
+
+    The saved activations live in the engine's training workspace of this batch size (one set per batch size, 1.2 GB at
+    B = 256), not in ``ctx``: the node records the workspace generation and ``backward`` refuses to run when a later saving
+    forward of the same batch size has overwritten it (two forwards before one backward) instead of returning wrong gradients.
+    Evaluation / no-grad forwards use a separate workspace and never disturb it."""
 
     @staticmethod
     def forward(ctx, owner, x, eps, *params):
         eng = owner._engine
         out = eng.forward(x, eps, save=True)
         ctx.owner = owner
+        ctx.batch = int(x.shape[0])
+        ctx.gen = eng._train_gen[ctx.batch]
         ctx.has_future = "future" in out
         res = (out["pred"],) + ((out["future"],) if ctx.has_future else ()) + (out["z"], out["mu"], out["logvar"])
         return res
@@ -124,14 +131,19 @@ class _RNNVAEFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         eng = ctx.owner._engine
+        if eng is None or eng._train_gen.get(ctx.batch) != ctx.gen:
+            raise RuntimeError("vame_b200: the activations saved by this forward were overwritten by a later forward of the same batch "
+                               "size (the engine keeps ONE set of saved activations per batch size); call backward() before the next "
+                               "training forward, or run the second forward under torch.no_grad()")
         if ctx.has_future:
             dpred, dfut, dz, dmu, dlv = grads
         else:
             dpred, dz, dmu, dlv = grads
             dfut = None
-        g = eng.backward(cfg=None, use_loss_grads=False, dpred=dpred, dfuture=dfut, dz=dz, dmu=dmu, dlogvar=dlv)
+        g = eng.backward(cfg=None, use_loss_grads=False, dpred=dpred, dfuture=dfut, dz=dz, dmu=dmu, dlogvar=dlv, batch=ctx.batch)
         views = eng.views(g.clone())
-        return (None, None, None) + tuple(views[n] for n in eng.names)
+        need = ctx.needs_input_grad[3:]
+        return (None, None, None) + tuple(views[n] if need[i] else None for i, n in enumerate(eng.names))
 
 
 class RNN_VAE(nn.Module):
@@ -185,12 +197,17 @@ class RNN_VAE(nn.Module):
         for name, p in self.named_parameters():
             p.data = views[name]
             p.grad = None
+        # p.data = view gives every parameter its OWN version counter: optimizer.step() / p.copy_() never touch flat._version,
+        # so the engine watches the parameters' counters to know when its packed tensor-core copies are stale
+        eng.watch([p for _, p in self.named_parameters()])
         self._grad_views = gviews
         self._engine = eng
+        self.__dict__.pop("_b200_steps", None)      # captured train-step graphs belong to the previous engine
 
     def _sync_engine(self):
-        """Parameters are views of engine.flat; in-place edits (optimizer.step, load_state_dict) bump its version counter,
-        which makes the engine refresh the packed tensor-core copies lazily."""
+        """Parameters alias engine.flat; the engine compares their version counters (Engine.watch) before every forward and
+        re-packs the tensor-core copies when any of them changed (optimizer.step, load_state_dict, p.copy_).  Edits through
+        ``p.data`` bump no counter at all: with autograd enabled the forward therefore always re-packs (30 us)."""
         return self._engine
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -218,6 +235,7 @@ class RNN_VAE(nn.Module):
         eps = torch.randn(B, self._cfg["zdims"], device=x.device, dtype=torch.float32) if self.training else None
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad:
+            eng._ensure_packed(force=True)           # (see _sync_engine: p.data edits are invisible to version counters)
             out = _RNNVAEFunction.apply(self, x.detach(), eps, *list(self.parameters()))
             if self.FUTURE_DECODER:
                 pred, fut, z, mu, lv = out
