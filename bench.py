@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for experiments (vame_set_option), recorded in config.options")
     args = ap.parse_args()
     F, T, Z, H, fut, S, B = WORKLOADS[args.workload]
     if args.per_gpu_batch:
@@ -200,6 +202,11 @@ def main():
     from vame_b200 import _lib as L
     import ctypes
 
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        L.check(L.lib().vame_set_option(k_.encode(), int(v_)), "vame_set_option")
+    if args.opt:
+        cfg_desc["options"] = list(args.opt)
     torch.manual_seed(19)
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)                  # reference default init under seed 19 (rnn_vae.py:292)
     eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda:%d" % local_rank)
@@ -288,8 +295,12 @@ def main():
         pers = lib.vame_get_option(b"persistent")
         rw, rw2 = lib.vame_get_option(b"rw"), lib.vame_get_option(b"rw2")
         tiles = (B + 127) // 128
-        # same rule as rw_applicable() in csrc/gru_rw.cu: the resident-weight cluster kernels need their grid in one wave
-        rw_ok = H % 64 == 0 and 64 <= H <= 256 and tiles * 64 <= 132 * lib.vame_get_option(b"rw_waves")
+        # same rule as rw_applicable() / rw_groups_per_cluster() in csrc/gru_rw.cu: 16-row clusters while they fit one wave,
+        # otherwise (H = 256) two interleaved 16-row groups per cluster
+        ng = lib.vame_get_option(b"rw_ng")
+        ng = ng if ng in (1, 2) else (1 if tiles * 64 <= 132 else 2)
+        ng = ng if (H == 256 and rw2) else 1
+        rw_ok = H % 64 == 0 and 64 <= H <= 256 and tiles * 64 // ng <= 132 * lib.vame_get_option(b"rw_waves")
         rw_name = "gru_rw2_%s_kernel (per time step)" if (H == 256 and rw2) else "gru_rw_%s_kernel (per time step)"
         names = (rw_name % "fwd" if (rw & 1) and rw_ok else "gru_seq_fwd_kernel (per time step)" if pers & 1 else "gru_step_fwd_kernel",
                  rw_name % "bwd" if (rw & 2) and rw_ok else "gru_seq_bwd_kernel (per time step)" if pers & 2 else "gru_step_bwd_kernel")
@@ -315,7 +326,7 @@ def main():
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
                 "traffic": traffic, "peak_source": how + ", burst figure (kernel timed alone)",
                 "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 4 * flops_launch,
-                "us_per_launch": {k: v * 1e6 for k, v in res.items()},
+                "us_per_launch": {k: v * 1e6 for k, v in res.items()}, "row_groups_per_cluster": ng,
                 "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 4x that in "
                         "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/4 of the bf16 peak; the step is a serial "
                         "chain of %d dependent time steps, latency-bound: per step ~1.2 us of tcgen05.mma (48 MMAs of M=128 N=32 K=16 per "

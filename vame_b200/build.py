@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvame_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177",
               "-Xcompiler", "-fPIC"] + (["-DVAME_ACCURATE_MATH=1"] if os.environ.get("VAME_ACCURATE_MATH") else [])
 
 

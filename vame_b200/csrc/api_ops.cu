@@ -20,7 +20,7 @@ int g_opt_rw2 = 1;
 int g_opt_rw_ng = 0;            // 16-row groups per cluster of the H = 256 rw kernels: 0 = automatic, 1 or 2 forced
 int g_opt_rw_exp = 0;
 int g_opt_rw_priv = 1;
-int g_opt_rw_sw = 1;
+int g_opt_rw_sw = 5;             // bit 0: forward sweeps, bit 1: BPTT sweeps with 16 rows per cluster (measured neutral), bit 2: BPTT sweeps with 2 x 16 rows
 unsigned long long* g_dbg_buffer = nullptr;
 }
 

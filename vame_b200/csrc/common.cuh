@@ -193,6 +193,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// the same signal delivered to the mbarrier at the same shared-memory offset in every CTA of the cluster whose rank bit is set in
+// cta_mask: the tensor pipe itself tells the peers "my MMAs up to here are complete" - no thread has to observe the completion first
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // TMEM -> registers: warp reads its own 32 lanes, 16 consecutive 32-bit columns per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];

@@ -703,6 +703,21 @@ __device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t pari
   rw_timeout(site, parity);
 }
 
+// Warp-specialised register allocation (setmaxnreg, per warpgroup of 4 warps): the kernel is launched with the register count
+// that its thread count allows; the MMA / store warpgroups then give registers back and the gate-math warpgroups take them.
+// Why it matters beyond speed: tcgen05.ld writes its destination registers asynchronously; the variants that ptxas could only
+// fit with spills (13 warps = 128 registers per thread) raised illegal-address faults on the B200 that vanished under
+// compute-sanitizer - no spills, no faults (profiles/r2_ng2_sw_fault.md).
+// a value the compiler cannot see through (blocks loop-invariant hoisting of everything derived from it)
+__device__ __forceinline__ uint64_t opaque64(uint64_t v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // TMEM <-> registers, 8 consecutive 32-bit columns of this thread's lane (staging of the store warps, see SW below)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
@@ -727,39 +742,48 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // through TENSOR MEMORY (tcgen05.st into spare columns, double-buffered, mbarrier handshake; warp 5 + i owns the TMEM lane
 // quarter (5 + i) % 4) and go straight back to the recurrence; the store warps do the bf16 splits / transposes and all global
 // stores of step t while step t + 1 is being computed.
-// NG: 16-row groups per cluster.  NG = 2 puts 32 batch rows on the N side of every MMA (N = 64 instead of 32: the MMA costs the same
-// 46 cycles), so a 512-window batch runs in ONE wave of 32 clusters.  Every group has its own four gate-math warps (and store
-// warps), TMEM accumulator columns and operand rows; the operand buffer is single (2 x 32 KB do not fit beside the 192 KB of
-// weights), so a CTA pushes h_t to a peer only after that peer has signalled that its MMAs of step t are complete (ofree).
+// NG: 16-row groups per cluster.  With NG = 2 a cluster serves two INDEPENDENT groups of 16 batch rows that are interleaved in
+// time: while the gate-math warps of group A drain the accumulators, do the gate math and exchange h_t (per group and step:
+// ~0.4 us of tensor-memory reads at 32 B/cycle per lane quarter, ~0.5 us for 12 KB of incoming DSMEM at ~15 B/cycle per SM -
+// tools/bench_mma/tmem_dsmem_bench.cu), the MMA lane issues the 48 MMAs of group B (1.1 us at the 46-cycle floor).  A 512-window
+// batch then runs in ONE wave of 32 clusters.  (Batching both groups into N = 64 MMAs was measured first: 5.6 us per step,
+// because everything after the MMAs scales with the rows - profiles/r2_probe_ng2_batched.log.)  Every group has its own
+// gate-math warps, accumulator columns, operand buffer and barriers; with NG = 2 the operand buffers are single (2 x 2 x 16 KB
+// do not fit beside the 192 KB of weights), so a CTA pushes h_t to a peer only after that peer has signalled that its MMAs of
+// step t are complete (ofree).
+__host__ __device__ constexpr int rw2_fwd_threads(bool sw, int ng) { return ng == 2 ? (sw ? 512 : 384) : (sw ? 288 : 160); }
 template <bool PRIV, bool SW, int NG>
-__global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
+__global__ void __launch_bounds__(rw2_fwd_threads(SW, NG), 1) gru_rw2_fwd_kernel(const GruSeqFwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
   static_assert(NG == 1 || NG == 2, "one or two 16-row groups per cluster");
   constexpr bool RW_MN = RW_MN_FWD != 0;
   constexpr int NKC = 4, H = 256, UC = 64;
-  constexpr int NGW = 4 * NG, NGT = 128 * NG;                      // gate-math warps / threads
-  constexpr int BT = RW_BTILE * NG;                                // one k chunk of the operand: [per group: 16 hi rows ; 16 lo rows] x 64 k
-  constexpr int NBUF = NG == 1 ? 2 : 1;                            // operand buffers
+  constexpr int NGW = 4 * NG;                                      // gate-math warps
+  constexpr int NBUF = NG == 1 ? 2 : 1;                            // operand buffers per group
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;                                             // [3 gates][NKC][RW_ATILE]
-  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [NBUF][NKC][BT]
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + NBUF * NKC * BT);
-  uint64_t* done = wbar + 1;                                      // [3]: accumulator of gate g complete
-  uint64_t* lfull = done + 3;                                     // [2]: own chunk of operand buffer b written (NGT arrivals)
-  uint64_t* hfull = lfull + 2;                                    // [2]: the three peers' chunks of buffer b have landed (tx bytes)
-  uint64_t* sfull = hfull + 2;                                    // [2] SW: staging buffer b written by the NGT gate-math threads
-  uint64_t* sempty = sfull + 2;                                   // [2] SW: staging buffer b read back by the NGT store threads
-  uint64_t* gfull = sempty + 2;                                   // [3] SW: gi of step s (TMEM buffer s % 3) written by the store threads
-  uint64_t* gempty = gfull + 3;                                   // [3] SW: ... consumed by the gate-math threads
-  uint64_t* ofree = gempty + 3;                                   // NBUF == 1: the 3 peers' MMAs of step s are complete (phase s)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofree + 1);
+  uint8_t* sH = smem + 3 * NKC * RW_ATILE;                        // [NG][NBUF][NKC][RW_BTILE]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sH + NG * NBUF * NKC * RW_BTILE);
+  uint64_t* done = wbar + 1;                                      // [NG][3]: accumulator of gate g complete
+  uint64_t* lfull = done + 3 * NG;                                // [NG][2]: own chunk of operand buffer b written (128 arrivals)
+  uint64_t* hfull = lfull + 2 * NG;                               // [NG][2]: the three peers' chunks of buffer b have landed (tx bytes)
+  uint64_t* sfull = hfull + 2 * NG;                               // [NG][2] SW: staging buffer b written by the 128 gate-math threads
+  uint64_t* sempty = sfull + 2 * NG;                              // [NG][2] SW: staging buffer b read back by the 128 store threads
+  uint64_t* gfull = sempty + 2 * NG;                              // [NG][3] SW: gi of step s (TMEM buffer s % 3) written by the store threads
+  uint64_t* gempty = gfull + 3 * NG;                              // [NG][3] SW: ... consumed by the gate-math threads
+  uint64_t* ofree = gempty + 3 * NG;                              // [NG] NBUF == 1: the 3 peers' MMAs of step s are complete (phase s)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofree + NG);
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirFwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int q = warp & 3, half = lane >> 4, oct = (lane >> 3) & 1;  // q: TMEM lane quarter of this warp = its 16 units of the slice
   const bool epi = warp < NGW;                                     // gate-math warp of group warp >> 2
-  const bool stw = SW && warp > NGW;                               // store warp of lane quarter q (serves every group in turn)
+  // NG = 2: warp-specialised register allocation, whole warpgroups per role: warps 0-7 gate math, 8 MMA issue (9-11 idle),
+  // SW: 12-15 store warps
+  constexpr bool WS = NG == 2;
+  constexpr int STW0 = WS ? 12 : NGW + 1;
+  const bool stw = SW && warp >= STW0;                             // store warp of lane quarter q (serves every group in turn)
   const int grp = epi ? (warp >> 2) : 0;
   const long gidx = (long)blockIdx.y * NG + grp;                   // 16-row group of the batch (gate-math warps)
   const long Bp = (long)a.tiles * 128;
@@ -767,25 +791,26 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
 
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int g = 0; g < 3; ++g) mbar_init(&done[g], 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&lfull[b], NGT);
-      mbar_init(&hfull[b], 1);
-      mbar_init(&sfull[b], NGT);
-      mbar_init(&sempty[b], NGT);
+    for (int p = 0; p < NG; ++p) {
+      for (int g = 0; g < 3; ++g) mbar_init(&done[3 * p + g], 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&lfull[2 * p + b], 128);
+        mbar_init(&hfull[2 * p + b], 1);
+        mbar_init(&sfull[2 * p + b], 128);
+        mbar_init(&sempty[2 * p + b], 128);
+      }
+      for (int b = 0; b < 3; ++b) {
+        mbar_init(&gfull[3 * p + b], 128);
+        mbar_init(&gempty[3 * p + b], 128);
+      }
+      mbar_init(&ofree[p], 3);
     }
-    for (int b = 0; b < 3; ++b) {
-      mbar_init(&gfull[b], NGT);
-      mbar_init(&gempty[b], NGT);
-    }
-    mbar_init(ofree, 3);
     mbar_fence_init();
   }
-  // tensor-memory columns: accumulator of gate g, group p at 32 (NG g + p); SW staging (h, r, z, n, gh_n: 40 columns) of group p,
-  // buffer b at SBASE + 40 (2 p + b); SW input projections (24 columns) of group p, buffer b at GBASE + 24 (3 p + b)
-  constexpr uint32_t SBASE = 96 * NG, GBASE = SBASE + 80 * NG;
+  // tensor-memory columns of group p at 248 p: accumulators of gate g at 32 g; SW staging (h, r, z, n, gh_n: 40 columns), buffer b
+  // at 96 + 40 b; SW input projections (24 columns), buffer b at 176 + 24 b
+  constexpr uint32_t GCOLS = 248, SBASE = 96, GBASE = 176;
   constexpr uint32_t TCOLS = SW ? 256 * NG : 128 * NG;
-  static_assert(GBASE + 72 * NG <= 256 * NG, "tensor-memory budget");
   if (warp == NGW) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -805,13 +830,9 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
   const int u = (int)c * UC + j;
   const long b0 = gidx * 16 + 8 * half;
   const int nrow = 8 * half + (lane & 7);                         // row inside the group after the transpose
-  const int orow = 32 * grp;                                      // first operand row of the group ([16 hi ; 16 lo] per group)
   const int kloc = 16 * q + 8 * oct;                              // k inside the CTA's own chunk after the transpose
-  // byte offset of (operand row n, k) inside an operand buffer of BT-sized 64-k chunks (K-major) / of rows n0 .. n0 + 7 (MN-major)
-  auto b_off = [&](int n, int k) -> uint32_t { return (uint32_t)(k >> 6) * BT + 2u * (uint32_t)p16_in_tile(n, k & 63); };
-  auto mn_off = [&](int n0, int k) -> uint32_t {
-    return (uint32_t)(k >> 6) * BT + (uint32_t)((n0 >> 3) * 1024 + ((k & 63) >> 3) * 128 + (k & 7) * 16);
-  };
+  uint8_t* sHg = sH + (size_t)grp * NBUF * NKC * RW_BTILE;         // this group's operand buffers
+  const uint32_t tcol = (SW ? GCOLS : 96u) * (uint32_t)grp;        // this group's tensor-memory columns
   float hprev[8], bhn = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
@@ -828,12 +849,12 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
       uint4 hi, lo;
       if constexpr (RW_MN) {
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(sH + mn_off(orow + 8 * half, cc * UC + j)) = hi;
-        *reinterpret_cast<uint4*>(sH + mn_off(orow + 16 + 8 * half, cc * UC + j)) = lo;
+        *reinterpret_cast<uint4*>(sHg + rw_mn_off(8 * half, cc * UC + j)) = hi;
+        *reinterpret_cast<uint4*>(sHg + rw_mn_off(16 + 8 * half, cc * UC + j)) = lo;
       } else {
         rw_transpose_pack(v, lane, hi, lo);
-        *reinterpret_cast<uint4*>(sH + b_off(orow + nrow, cc * UC + kloc)) = hi;
-        *reinterpret_cast<uint4*>(sH + b_off(orow + 16 + nrow, cc * UC + kloc)) = lo;
+        *reinterpret_cast<uint4*>(sHg + rw_b_off(nrow, cc * UC + kloc)) = hi;
+        *reinterpret_cast<uint4*>(sHg + rw_b_off(16 + nrow, cc * UC + kloc)) = lo;
       }
     }
     fence_proxy_async_smem();
@@ -841,27 +862,29 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
   // arm the receive barriers of the first exchanges (two buffers: buffer 1 is filled for step 1, buffer 0 for step 2; one buffer:
   // for step 1); later phases are armed right after the previous phase has been waited for, so a peer's complete_tx never
   // precedes the expect_tx
-  const uint32_t hx = (a.exp & 8) ? 3 * BT / 2 : 3 * BT;           // (experiment 8: only the hi plane is pushed)
+  const uint32_t hx = (a.exp & 8) ? 3 * RW_BTILE / 2 : 3 * RW_BTILE;   // (experiment 8: only the hi plane is pushed)
   if (tid == 0) {
-    if constexpr (NBUF == 2) {
-      if (steps > 1) mbar_expect_tx(&hfull[1], hx);
-      if (steps > 2) mbar_expect_tx(&hfull[0], hx);
-    } else {
-      if (steps > 1) mbar_expect_tx(&hfull[0], hx);
+    for (int p = 0; p < NG; ++p) {
+      if constexpr (NBUF == 2) {
+        if (steps > 1) mbar_expect_tx(&hfull[2 * p + 1], hx);
+        if (steps > 2) mbar_expect_tx(&hfull[2 * p + 0], hx);
+      } else {
+        if (steps > 1) mbar_expect_tx(&hfull[2 * p], hx);
+      }
     }
   }
   // all mbarriers of the cluster are initialised (and the h0 operands written) before any remote signal is sent
   cluster_arrive_release();
   cluster_wait_acquire();
 
-  constexpr uint32_t idesc = make_idesc_bf16(128, 32 * NG) | (RW_MN ? (1u << 16) : 0u);
-  const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t idesc = rw_idesc(RW_MN);
+  const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);        // this warp's lane quarter, column 0
+  const uint32_t taddr = tlane + tcol;                             // ... at this group's columns (gate-math warps)
   const long groups = Bp / 16;
   const bool gi_const = d.gi_ts == 0;                              // decoders: the input projection does not depend on t
   // input projections are prefetched TWO steps ahead (registers): under the write bursts of the sweep's own stores a load
   // issued one step ahead came back too late for the next gate math (measured: 3.25 -> 2.5 us per step)
   float gir[8], giz[8], gin[8], gir2[8], giz2[8], gin2[8];
-  float gsr[NG > 1 ? 8 : 1], gsz[NG > 1 ? 8 : 1], gsn[NG > 1 ? 8 : 1];   // store warps, NG = 2: fetched input projections of group 1
   auto load_gi = [&](int g_, int s_, float* r_, float* z_, float* n_) {
     const int t_ = d.reverse ? steps - 1 - s_ : s_;
     const float* gi_row = d.gi + ((((long)blockIdx.y * NG + g_) * 16 + 8 * half) * d.gi_bs + (long)t_ * d.gi_ts);
@@ -871,8 +894,8 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
   };
   // SW && !gi_const: the store warps fetch gi(s + 2) during step s and pass it on through tensor memory, so that the gate-math
   // warps issue no global memory instruction at all
-  const bool gi_tmem = SW && !gi_const && !(a.exp & 2);
-  auto gi_col = [&](int g_, int s_) -> uint32_t { return taddr + GBASE + 24u * (uint32_t)(3 * g_ + s_ % 3); };
+  const bool gi_tmem = SW && !gi_const;
+  auto gi_col = [&](int g_, int s_) -> uint32_t { return tlane + GCOLS * (uint32_t)g_ + GBASE + 24u * (uint32_t)(s_ % 3); };
   auto gi_publish = [&](int g_, int s_, const float* r_, const float* z_, const float* n_) {   // store warps
     const uint32_t gc = gi_col(g_, s_);
     __syncwarp();
@@ -881,11 +904,13 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
     tmem_st8(gc + 16, n_);
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(&gfull[s_ % 3]);
+    mbar_arrive(&gfull[3 * g_ + s_ % 3]);
   };
   if (epi && !gi_tmem) {
     load_gi(grp, 0, gir, giz, gin);
-    if (steps > 1 && !gi_const) load_gi(grp, 1, gir2, giz2, gin2);
+    if constexpr (!SW) {
+      if (steps > 1 && !gi_const) load_gi(grp, 1, gir2, giz2, gin2);
+    }
   }
   if (stw && gi_tmem) {
 #pragma unroll
@@ -897,74 +922,98 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
     }
   }
 
-  for (int s = 0; s < steps; ++s) {
-    const int t = d.reverse ? steps - 1 - s : s;
-    const int so = (d.out_slots == steps) ? t : (s & 1);
-    const int sp = (d.out_p_slots == steps) ? t : (s & 1);
-    const uint32_t ph = s & 1;
-    const uint32_t b = NBUF == 2 ? (uint32_t)(s & 1) : 0u;         // operand buffer of this step
-    const uint32_t nb = NBUF == 2 ? (b ^ 1u) : 0u;                 // ... of the next step
-    // phase parity of the barriers of buffer b: two buffers - used every other step; one buffer - every step
-    const uint32_t bpar = NBUF == 2 ? (uint32_t)(((s - 1) >> 1) & 1) : (uint32_t)((s - 1) & 1);
-    RW_STAMP(0);
-    if (warp == NGW) {
+  // one loop per warp role: the register budget of a role is set by setmaxnreg before its loop (warp-specialised allocation)
+  if (warp >= NGW && !stw) {
+    if constexpr (WS) reg_dec<72>();
+    if (warp == NGW)
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? steps - 1 - s : s;
+      const int so = (d.out_slots == steps) ? t : (s & 1);
+      const int sp = (d.out_p_slots == steps) ? t : (s & 1);
+      const uint32_t ph = s & 1;
+      const uint32_t b = NBUF == 2 ? (uint32_t)(s & 1) : 0u;         // operand buffer of this step
+      const uint32_t nb = NBUF == 2 ? (b ^ 1u) : 0u;                 // ... of the next step
+      // phase parity of the barriers of buffer b: two buffers - used every other step; one buffer - every step
+      const uint32_t bpar = NBUF == 2 ? (uint32_t)(((s - 1) >> 1) & 1) : (uint32_t)((s - 1) & 1);
+      RW_STAMP(0);
       if (elect_one()) {
-        const uint32_t hb = smem_u32(sH) + b * NKC * BT;
-        if (s == 0) {
-          mbar_wait_b(wbar, 0, 10);
-        } else {
-          mbar_wait_b(&lfull[b], bpar, 11);                         // own chunk of h_{t-1} written (and TMEM drained) by the gate warps
-          RW_STAMP_MMA(8);
-        }
-        fence_proxy_async_smem();
-        tc_fence_after();
-        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(hb);
-        // own chunk first (all three gates), then the peers' chunks gate by gate
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t ao = (g * NKC + c) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = c * BT + ks * 2 * ATOM_BYTES;
-            if (ks == 0) umma_bf16_c<0>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
-            else umma_bf16_c<1>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+        for (int p = 0; p < NG; ++p) {                              // the groups take turns on the tensor pipe
+          const uint32_t hb = smem_u32(sH) + ((uint32_t)p * NBUF + b) * NKC * RW_BTILE;
+          const uint32_t dcol = tmem + (SW ? GCOLS : 96u) * (uint32_t)p;
+          if (s == 0) {
+            if (p == 0) mbar_wait_b(wbar, 0, 10);
+          } else {
+            mbar_wait_b(&lfull[2 * p + b], bpar, 11);               // own chunk of h_{t-1} written (and TMEM drained) by the gate warps
+            if (p == 0) RW_STAMP_MMA(8);
           }
-        }
-        if (s > 0) {
-          mbar_wait_b(&hfull[b], bpar, 12);
-          if (s + NBUF < steps) mbar_expect_tx(&hfull[b], hx);     // arm the next use of this buffer (step s + NBUF)
-          fence_proxy_async_smem();                                 // the peers' chunks were written through the generic proxy
-        }
-        RW_STAMP_MMA(9);
-        RW_STAMP_CTA(0);
+          fence_proxy_async_smem();
+          tc_fence_after();
+          // (opaque copies: without them the compiler hoists all 64 operand descriptors of a step out of the time loop - 128 registers)
+          const uint64_t dA = opaque64(make_desc(smem_u32(sW))), dB = opaque64(make_desc(hb));
+          // own chunk first (all three gates), then the peers' chunks gate by gate
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-#pragma unroll
-          for (uint32_t r = 1; r < 4; ++r) {
-            const uint32_t kc = (c + r) & 3;
+          for (int g = 0; g < 3; ++g) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * BT + ks * 2 * ATOM_BYTES;
-              umma_bf16_c<1>(tmem + g * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              const uint32_t ao = (g * NKC + c) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = c * RW_BTILE + ks * 2 * ATOM_BYTES;
+              if (ks == 0) umma_bf16_c<0>(dcol + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              else umma_bf16_c<1>(dcol + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
             }
           }
-          umma_commit(&done[g]);
+          if (s > 0) {
+            mbar_wait_b(&hfull[2 * p + b], bpar, 12);
+            if (s + NBUF < steps) mbar_expect_tx(&hfull[2 * p + b], hx);   // arm the next use of this buffer (step s + NBUF)
+            fence_proxy_async_smem();                               // the peers' chunks were written through the generic proxy
+          }
+          if (p == 0) {
+            RW_STAMP_MMA(9);
+            RW_STAMP_CTA(0);
+          }
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+#pragma unroll
+            for (uint32_t r = 1; r < 4; ++r) {
+              const uint32_t kc = (c + r) & 3;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t ao = (g * NKC + kc) * RW_ATILE + ks * 2 * ATOM_BYTES, bo = kc * RW_BTILE + ks * 2 * ATOM_BYTES;
+                umma_bf16_c<1>(dcol + g * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              }
+            }
+            umma_commit(&done[3 * p + g]);
+          }
+          if constexpr (NBUF == 1) {
+            // every MMA of this group's step has finished reading the operand buffer once this commit fires: the tensor pipe tells
+            // the three peers that they may push h_t into it (no gate-math thread has to notice the completion first)
+            if (s + 1 < steps) umma_commit_multicast(&ofree[p], (uint16_t)(0xFu & ~(1u << c)));
+          }
+          if (p == 0) RW_STAMP_MMA(2);
         }
-        RW_STAMP_MMA(2);
       }
       __syncwarp();
-    } else if (stw) {                                               // ---- store warp of TMEM lane quarter q ----
+    }
+  } else if (stw) {
+    if constexpr (WS) reg_dec<104>();
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? steps - 1 - s : s;
+      const int so = (d.out_slots == steps) ? t : (s & 1);
+      const int sp = (d.out_p_slots == steps) ? t : (s & 1);
+      const uint32_t ph = s & 1;
+      const uint32_t b = NBUF == 2 ? (uint32_t)(s & 1) : 0u;         // operand buffer of this step
+      const uint32_t nb = NBUF == 2 ? (b ^ 1u) : 0u;                 // ... of the next step
+      // phase parity of the barriers of buffer b: two buffers - used every other step; one buffer - every step
+      const uint32_t bpar = NBUF == 2 ? (uint32_t)(((s - 1) >> 1) & 1) : (uint32_t)((s - 1) & 1);
+      RW_STAMP(0);
       const uint32_t sb = s & 1;
       const bool fetch = gi_tmem && s + 2 < steps;
-      if (fetch) {                                                  // loads first: they are in flight while the warp waits below
-        load_gi(0, s + 2, gir, giz, gin);
-        if constexpr (NG > 1) load_gi(1, s + 2, gsr, gsz, gsn);
-      }
-      mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 17);
-      tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int g_ = 0; g_ < NG; ++g_) {
         float hn[8], sr[8], sz[8], sn[8], sg[8];
-        const uint32_t stg = taddr + SBASE + 40u * (uint32_t)(2 * g_ + (int)sb);
+        const uint32_t stg = tlane + GCOLS * (uint32_t)g_ + SBASE + 40u * sb;
+        if (fetch) load_gi(g_, s + 2, gir, giz, gin);              // loads first: they are in flight while the warp waits below
+        mbar_wait_warp(&sfull[2 * g_ + sb], (s >> 1) & 1, 17);
+        tc_fence_after();
         tmem_ld8(stg, hn);
         tmem_ld8(stg + 8, sr);
         tmem_ld8(stg + 16, sz);
@@ -972,38 +1021,50 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
         tmem_ld8(stg + 32, sg);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&sempty[sb]);
-        if (a.exp & 16) continue;
-        // (pacing these stores - one per warp every 256-384 cycles - changed nothing: 3.04 us per step either way)
-        uint4 phi, plo;
-        rw_transpose_pack(hn, lane, phi, plo);
-        const long gi_ = (long)blockIdx.y * NG + g_, bb = gi_ * 16 + 8 * half, row = gi_ * 16 + nrow;
-        const int k0 = (int)c * UC + kloc;
-        __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
-                            ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
-        const int off = p16_in_tile((int)(row & 127), k0 & 63);
-        const long blk = pv_block(t, groups, gi_, c, q);
-        st8p(d.out + blk, lane, hn);
-        st8p(d.sv[0] + blk, lane, sr);
-        st8p(d.sv[1] + blk, lane, sz);
-        st8p(d.sv[2] + blk, lane, sn);
-        st8p(d.sv[3] + blk, lane, sg);
-        st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + bb, hn);
-        if (s + 1 == steps) st8(d.hfin + (long)u * Bp + bb, hn);
-        *reinterpret_cast<uint4*>(tl + off) = phi;
-        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
+        mbar_arrive(&sempty[2 * g_ + sb]);
+        if (!(a.exp & 16)) {
+          // (pacing these stores - one per warp every 256-384 cycles - changed nothing: 3.04 us per step either way)
+          uint4 phi, plo;
+          rw_transpose_pack(hn, lane, phi, plo);
+          const long gi_ = (long)blockIdx.y * NG + g_, bb = gi_ * 16 + 8 * half, row = gi_ * 16 + nrow;
+          const int k0 = (int)c * UC + kloc;
+          __nv_bfloat16* tl = reinterpret_cast<__nv_bfloat16*>(d.out_p) + (size_t)sp * d.out_p_slot_elems +
+                              ((size_t)(row >> 7) * NKC + (k0 >> 6)) * p16_tile_elems(128);
+          const int off = p16_in_tile((int)(row & 127), k0 & 63);
+          const long blk = pv_block(t, groups, gi_, c, q);
+          st8p(d.out + blk, lane, hn);
+          st8p(d.sv[0] + blk, lane, sr);
+          st8p(d.sv[1] + blk, lane, sz);
+          st8p(d.sv[2] + blk, lane, sn);
+          st8p(d.sv[3] + blk, lane, sg);
+          st8_T_p16(d.outT_p, d.outT_nk, u, (long)t * Bp + bb, hn);
+          if (s + 1 == steps) st8(d.hfin + (long)u * Bp + bb, hn);
+          *reinterpret_cast<uint4*>(tl + off) = phi;
+          *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = plo;
+        }
+        if (fetch) {                                                // buffer (s + 2) % 3 was last read in step s - 1
+          if (s >= 1) mbar_wait_warp(&gempty[3 * g_ + (s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
+          tc_fence_after();
+          gi_publish(g_, s + 2, gir, giz, gin);
+        }
       }
-      if (fetch) {                                                  // buffer (s + 2) % 3 was last read in step s - 1
-        if (s >= 1) mbar_wait_warp(&gempty[(s + 2) % 3], (((s + 2) / 3) - 1) & 1, 18);
-        tc_fence_after();
-        gi_publish(0, s + 2, gir, giz, gin);
-        if constexpr (NG > 1) gi_publish(1, s + 2, gsr, gsz, gsn);
-      }
-    } else if (epi) {
+    }
+  } else if (epi) {
+    if constexpr (WS) reg_inc<SW ? 168 : 216>();
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? steps - 1 - s : s;
+      const int so = (d.out_slots == steps) ? t : (s & 1);
+      const int sp = (d.out_p_slots == steps) ? t : (s & 1);
+      const uint32_t ph = s & 1;
+      const uint32_t b = NBUF == 2 ? (uint32_t)(s & 1) : 0u;         // operand buffer of this step
+      const uint32_t nb = NBUF == 2 ? (b ^ 1u) : 0u;                 // ... of the next step
+      // phase parity of the barriers of buffer b: two buffers - used every other step; one buffer - every step
+      const uint32_t bpar = NBUF == 2 ? (uint32_t)(((s - 1) >> 1) & 1) : (uint32_t)((s - 1) & 1);
+      RW_STAMP(0);
       float hn[8], sr[8], sz[8], sn[8], sg[8], ar[8], az[8], an[8];
       uint4 phi = make_uint4(0, 0, 0, 0), plo = make_uint4(0, 0, 0, 0);
       if (gi_tmem) {                                                // this step's input projections (published >= 1 step ago)
-        mbar_wait_warp(&gfull[s % 3], (s / 3) & 1, 19);
+        mbar_wait_warp(&gfull[3 * grp + s % 3], (s / 3) & 1, 19);
         tc_fence_after();
         const uint32_t gc = gi_col(grp, s);
         tmem_ld8(gc, gir);
@@ -1011,32 +1072,23 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
         tmem_ld8(gc + 16, gin);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&gempty[s % 3]);
+        mbar_arrive(&gempty[3 * grp + s % 3]);
       }
-      const uint32_t acc = taddr + 32u * (uint32_t)grp;             // this group's 32 columns inside every gate accumulator
-      mbar_wait_warp(&done[0], ph, 13);
+      mbar_wait_warp(&done[3 * grp + 0], ph, 13);
       tc_fence_after();
-      rw_reduce32(acc, half, ar);
+      rw_reduce32(taddr, half, ar);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sr[i] = rw_sigmoid(gir[i] + ar[i]);
-      mbar_wait_warp(&done[1], ph, 14);
+      mbar_wait_warp(&done[3 * grp + 1], ph, 14);
       tc_fence_after();
-      rw_reduce32(acc + 32 * NG, half, az);
+      rw_reduce32(taddr + 32, half, az);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sz[i] = rw_sigmoid(giz[i] + az[i]);
-      mbar_wait_warp(&done[2], ph, 15);
+      mbar_wait_warp(&done[3 * grp + 2], ph, 15);
       tc_fence_after();
-      if constexpr (NBUF == 1) {
-        // every MMA of this step has finished reading the operand buffer (commits complete in order): tell the three peers that
-        // they may push h_t into it.  A pure "done reading" signal that publishes no data -> relaxed (see the BPTT kernel).
-        if (tid == 0 && s + 1 < steps) {
-#pragma unroll
-          for (uint32_t r = 1; r < 4; ++r) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(ofree), (c + r) & 3));
-        }
-      }
       RW_STAMP(3);
       if (tid == 0) RW_STAMP_CTA(1);
-      rw_reduce32(acc + 64 * NG, half, an);
+      rw_reduce32(taddr + 64, half, an);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         sg[i] = an[i] + bhn;
@@ -1053,13 +1105,13 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
       }
       tc_fence_before();
       if (s + 1 < steps) {                                        // own chunk of the next operand buffer, then tell the MMA lane
-        uint8_t* own = sH + nb * NKC * BT + c * BT;
-        const uint32_t o_hi = RW_MN ? mn_off(orow + 8 * half, j) : 2u * p16_in_tile(orow + nrow, kloc);
-        const uint32_t o_lo = RW_MN ? mn_off(orow + 16 + 8 * half, j) : 2u * p16_in_tile(orow + 16 + nrow, kloc);
+        uint8_t* own = sHg + nb * NKC * RW_BTILE + c * RW_BTILE;
+        const uint32_t o_hi = RW_MN ? rw_mn_off(8 * half, j) : 2u * p16_in_tile(nrow, kloc);
+        const uint32_t o_lo = RW_MN ? rw_mn_off(16 + 8 * half, j) : 2u * p16_in_tile(16 + nrow, kloc);
         const uint32_t ohi = smem_u32(own) + o_hi, olo = smem_u32(own) + o_lo;
-        const uint32_t hbar = smem_u32(&hfull[nb]);
+        const uint32_t hbar = smem_u32(&hfull[2 * grp + nb]);
         if constexpr (NBUF == 1) {                                  // the peers' MMAs of this step are complete
-          mbar_wait_cluster_b(ofree, ph, 30);
+          mbar_wait_cluster_b(&ofree[grp], ph, 30);
           __syncwarp();
         }
 #pragma unroll
@@ -1071,21 +1123,23 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
         *reinterpret_cast<uint4*>(own + o_hi) = ohv;
         *reinterpret_cast<uint4*>(own + o_lo) = olv;
         fence_proxy_async_smem();
-        mbar_arrive(&lfull[nb]);
+        mbar_arrive(&lfull[2 * grp + nb]);
       }
       if constexpr (RW_MN && !SW) rw_transpose_pack(hn, lane, phi, plo);   // K-major P16 copy for the GEMMs (off the recurrence)
       RW_STAMP(5);
       if (tid == 0) RW_STAMP_CTA(2);
       if (tid == 96) RW_STAMP_CTA(3);
       // ---- off the recurrence (overlaps the exchange and the next step's MMAs); loads first: the LSU works in order ----
-      if (s + 1 < steps && !gi_const && !gi_tmem && !(a.exp & 2)) {
+      if constexpr (!SW) {                                          // (SW: the store warps deliver gi through tensor memory)
+        if (s + 1 < steps && !gi_const && !(a.exp & 2)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { gir[i] = gir2[i]; giz[i] = giz2[i]; gin[i] = gin2[i]; }
-        if (s + 2 < steps) load_gi(grp, s + 2, gir2, giz2, gin2);
+          for (int i = 0; i < 8; ++i) { gir[i] = gir2[i]; giz[i] = giz2[i]; gin[i] = gin2[i]; }
+          if (s + 2 < steps) load_gi(grp, s + 2, gir2, giz2, gin2);
+        }
       }
       if constexpr (SW) {                                           // hand h_t and the saved gates to the store warps
-        const uint32_t sb = s & 1, stg = taddr + SBASE + 40u * (uint32_t)(2 * grp + (int)sb);
-        if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 16);
+        const uint32_t sb = s & 1, stg = taddr + SBASE + 40u * sb;
+        if (s >= 2) mbar_wait_warp(&sempty[2 * grp + sb], ((s - 2) >> 1) & 1, 16);
         __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
         tmem_st8(stg, hn);
@@ -1095,7 +1149,7 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
         tmem_st8(stg + 32, sg);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&sfull[sb]);
+        mbar_arrive(&sfull[2 * grp + sb]);
         continue;
       }
       if constexpr (PRIV) {
@@ -1141,42 +1195,44 @@ __global__ void __launch_bounds__((4 * NG + (SW ? 5 : 1)) * 32, 1) gru_rw2_fwd_k
 // SW: as in the forward kernel, four extra warps take over everything that is not on the recurrence - here the gate gradients
 // of step t travel through tensor memory (32 columns, double-buffered) and the store warps write the transposed P16 operands of
 // the weight-gradient GEMMs, the P16 copy for dx, and keep the bias-gradient / time sums.
-// NG = 2 (see the forward kernel): 32 batch rows per cluster, N = 64 MMAs.  Two 24 KB receive slots no longer fit beside 192 KB
-// of weights, so the accumulator tile that is issued last (the CTA's own input units) takes its A operand from TENSOR MEMORY:
-// its 48 KB of W_hh^T (hi + lo rows x 192 k) are copied global -> registers -> tcgen05.st once before the sweep (96 columns,
-// column 8 ks + i of lane r = k elements 16 ks + 2 i, + 1 of tile row r) and only three tiles stay in shared memory.
+// NG = 2 (see the forward kernel): two independent 16-row groups per cluster, interleaved in time - group B's 48 MMAs run while
+// group A waits for its partial sums, does the gate-gradient math and builds its operand.  Four 12 KB receive slots no longer
+// fit beside 192 KB of weights, so the accumulator tile that is issued last (the CTA's own input units) takes its A operand
+// from TENSOR MEMORY: its 48 KB of W_hh^T (hi + lo rows x 192 k) are copied global -> registers -> tcgen05.st once before the
+// sweep (96 columns, column 8 ks + i of lane r = k elements 16 ks + 2 i, + 1 of tile row r) and only three tiles stay in
+// shared memory.
+__host__ __device__ constexpr int rw2_bwd_threads(bool sw, int ng) { return ng == 2 ? (sw ? 512 : 384) : (sw ? 288 : 160); }
 template <bool SUM, bool PRIV, bool SW, int NG>
-__global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
+__global__ void __launch_bounds__(rw2_bwd_threads(SW, NG), 1) gru_rw2_bwd_kernel(const GruSeqBwdArgs a) {
   static_assert(PRIV || !SW, "store warps serve the private layouts only");
   static_assert(NG == 1 || NG == 2, "one or two 16-row groups per cluster");
-  static_assert(!(SW && NG == 2), "the store-warp variant of the BPTT sweep (measured neutral) exists for 16-row clusters only");
+  static_assert(!(SW && NG == 2 && SUM), "two-group store warps do not keep the time sums (decoders use the variant without store warps)");
   constexpr bool RW_MN = RW_MN_BWD != 0;
   constexpr int H = 256, UC = 64, MT = 4, KS = 12, NKB = 3;
-  constexpr int NGW = 4 * NG, NGT = 128 * NG;                      // gate-math warps / threads
-  constexpr int RG = 16 * NG;                                      // batch rows of the cluster
-  constexpr int BT = RW_BTILE * NG;                                // one k chunk of the operand
-  constexpr int RSLOT = 3 * UC * RG * 4;                           // 3 source slots = the 3 k chunks of the operand
-  static_assert(RSLOT == NKB * BT, "receive slot and operand must have the same size");
+  constexpr int NGW = 4 * NG;                                      // gate-math warps
+  constexpr int RSLOT = 3 * UC * 16 * 4;                           // 12288 B: 3 source slots = the 3 k chunks of the operand
+  static_assert(RSLOT == NKB * RW_BTILE, "receive slot and operand must have the same size");
   constexpr bool WT = NG == 2;                                     // the own tile's A operand lives in tensor memory
   constexpr int MS = WT ? 3 : 4;                                   // A tiles in shared memory
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;                                             // [MS][NKB][RW_ATILE]; WT: tile i = input units of CTA (c + 1 + i) & 3
-  uint8_t* sR = smem + MS * NKB * RW_ATILE;                       // [2][RSLOT]
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sR + 2 * RSLOT);
-  uint64_t* done = wbar + 1;                                      // [4] accumulator tiles, in issue order
-  uint64_t* ofull = done + 4;                                     // operand of this step written (NGT arrivals)
-  uint64_t* pfull = ofull + 1;                                    // [2]: partial sums of 3 peers x NGW warps have landed in slot b
-  uint64_t* mfree = pfull + 2;                                    // [2]: all MMAs of the 3 peers' step s are complete (3 x NGW warps), slot s & 1
-  uint64_t* sfull = mfree + 2;                                    // [2] SW: staging buffer b written by the NGT gate-math threads
-  uint64_t* sempty = sfull + 2;                                   // [2] SW: ... read back by the NGT store threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);  // (mfree: a peer may signal step s + 1 before this CTA has looked at step s)
+  uint8_t* sR = smem + MS * NKB * RW_ATILE;                       // [NG][2][RSLOT]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sR + NG * 2 * RSLOT);
+  uint64_t* done = wbar + 1;                                      // [NG][4] accumulator tiles, in issue order
+  uint64_t* ofull = done + 4 * NG;                                // [NG] operand of this step written (128 arrivals)
+  uint64_t* pfull = ofull + NG;                                   // [NG][2]: partial sums of 3 peers x 4 warps have landed in slot b
+  uint64_t* mfree = pfull + 2 * NG;                               // [NG][2]: all MMAs of the 3 peers' step s are complete (3 x 4 warps), slot s & 1
+  uint64_t* sfull = mfree + 2 * NG;                               // [NG][2] SW: staging buffer b written by the 128 gate-math threads
+  uint64_t* sempty = sfull + 2 * NG;                              // [NG][2] SW: ... read back by the 128 store threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2 * NG);   // (mfree: a peer may signal step s + 1 before this CTA has looked at step s)
 
   const uint32_t c = cluster_ctarank();
   const GruSeqDirBwd& d = a.d[blockIdx.z];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int q = warp & 3, half = lane >> 4, oct = (lane >> 3) & 1;
   const bool epi = warp < NGW;
-  const bool stw = SW && warp > NGW;
+  constexpr bool WS = NG == 2;                                     // warps 0-7 gate math, 8 MMA issue (9-11 idle), SW: 12-15 store warps
+  const bool stw = SW && warp >= (WS ? 12 : NGW + 1);               // (see the forward kernel)
   const int grp = epi ? (warp >> 2) : (stw ? ((warp - NGW - 1) >> 2) : 0);
   const long gidx = (long)blockIdx.y * NG + grp;
   const long bpad = (long)a.tiles * 128;
@@ -1184,19 +1240,21 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
 
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int m = 0; m < 4; ++m) mbar_init(&done[m], 1);
-    mbar_init(ofull, NGT);
-    mbar_init(&pfull[0], 1);
-    mbar_init(&pfull[1], 1);
-    mbar_init(&mfree[0], 3 * NGW);
-    mbar_init(&mfree[1], 3 * NGW);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&sfull[b], NGT);
-      mbar_init(&sempty[b], NGT);
+    for (int p = 0; p < NG; ++p) {
+      for (int m = 0; m < 4; ++m) mbar_init(&done[4 * p + m], 1);
+      mbar_init(&ofull[p], 128);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&pfull[2 * p + b], 1);
+        mbar_init(&mfree[2 * p + b], 12);
+      }
+    }
+    for (int b = 0; b < 2 * NG; ++b) {
+      mbar_init(&sfull[b], 128);
+      mbar_init(&sempty[b], 128);
     }
     mbar_fence_init();
   }
-  // tensor-memory columns: accumulator tile i, group p at 32 (NG i + p); WT: own A tile at WCOL + [0, 96); SW staging (32 columns)
+  // tensor-memory columns: accumulator tile i of group p at 128 p + 32 i; WT: own A tile at WCOL + [0, 96); SW staging (32 columns)
   // of group p, buffer b at SBASE + 32 (2 p + b)
   constexpr uint32_t WCOL = 128 * NG, SBASE = WT ? WCOL + 96 : 128;
   constexpr uint32_t TCOLS = WT ? 512 : (SW ? 256 : 128);
@@ -1240,11 +1298,14 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
       tc_fence_before();
     }
   }
-  // arm the receive barriers of the first two steps' pushes (3 peers x 64 units x RG rows x 4 B); later phases are armed by
-  // thread 0 right after it has consumed the previous phase of the same slot, i.e. before any peer can push into it again
+  // arm the receive barriers of the first two steps' pushes (3 peers x 64 units x 16 rows x 4 B); later phases are armed by
+  // the group's first thread right after it has consumed the previous phase of the same slot, i.e. before any peer can push
+  // into it again
   if (tid == 0) {
-    mbar_expect_tx(&pfull[0], RSLOT);
-    if (steps > 1) mbar_expect_tx(&pfull[1], RSLOT);
+    for (int p = 0; p < NG; ++p) {
+      mbar_expect_tx(&pfull[2 * p], RSLOT);
+      if (steps > 1) mbar_expect_tx(&pfull[2 * p + 1], RSLOT);
+    }
   }
   if constexpr (WT) __syncthreads();                              // the tensor-memory A tile is complete before the MMA lane starts
   cluster_arrive_release();
@@ -1254,15 +1315,15 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
   const int u = (int)c * UC + j;
   const long b0 = gidx * 16 + 8 * half;
   const int nrow = 8 * half + (lane & 7);
-  const int orow = 32 * grp;                                      // first operand row of the group
   const int kq = 16 * q + 8 * oct;
-  constexpr uint32_t idesc = make_idesc_bf16(128, 32 * NG) | (RW_MN ? (1u << 16) : 0u);
-  auto b_off = [&](int n, int k) -> uint32_t { return (uint32_t)(k >> 6) * BT + 2u * (uint32_t)p16_in_tile(n, k & 63); };
-  auto mn_off = [&](int n0, int k) -> uint32_t {
-    return (uint32_t)(k >> 6) * BT + (uint32_t)((n0 >> 3) * 1024 + ((k & 63) >> 3) * 128 + (k & 7) * 16);
-  };
-  // fp32 partial sums in a receive slot: [source slot: 3][unit: 64][row: RG]
-  auto part_off = [&](int slot, int unit) -> uint32_t { return (uint32_t)(((slot * UC + unit) * RG + 16 * grp + 8 * half) * 4); };
+  const uint32_t idesc = rw_idesc(RW_MN);
+  uint8_t* sRg = sR + (size_t)grp * 2 * RSLOT;                     // this group's two receive slots
+  uint64_t* doneg = done + 4 * grp;
+  uint64_t* pfullg = pfull + 2 * grp;
+  uint64_t* mfreeg = mfree + 2 * grp;
+  const uint32_t tacc = taddr + 128u * (uint32_t)grp;             // this group's accumulator tiles (gate-math warps)
+  // fp32 partial sums in a receive slot: [source slot: 3][unit: 64][row: 16]
+  auto part_off = [&](int slot, int unit) -> uint32_t { return (uint32_t)(((slot * UC + unit) * 16 + 8 * half) * 4); };
 
   float carry[8], own[8];
   float sum_r[SUM ? 8 : 1], sum_z[SUM ? 8 : 1], sum_n[SUM ? 8 : 1];
@@ -1304,80 +1365,123 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
       for (int i = 0; i < 8; ++i) dh[i] = 0.f;
     }
   };
-  if (epi) {
-    if (d.dh_last) ld8(d.dh_last + (long)u * d.dh_last_ld + b0, carry);
-    load_step(0);
-  }
-
-  for (int s = 0; s < steps; ++s) {
-    const int t = d.reverse ? s : steps - 1 - s;
-    const uint32_t ph = s & 1;
-    uint8_t* rprev = sR + (ph ^ 1u) * RSLOT;                      // partial sums of step s - 1; then this step's operand
-    RW_STAMP(0);
-    if (warp == NGW) {
+  // one loop per warp role: the register budget of a role is set by setmaxnreg before its loop (warp-specialised allocation)
+  // (everything a role does after the common set-up lives inside its branch: ptxas applies a setmaxnreg budget only to code
+  //  that the instruction dominates)
+  if (warp >= NGW && !stw) {
+    // the pool that setmaxnreg.inc draws from holds only RELEASED registers: 4 x (168 - this) must cover 8 x (gate - 168)
+    if constexpr (WS) reg_dec<SW ? 56 : (SUM ? 56 : 72)>();        // (SW: 512 threads start with 128; + 104 for the store warps -> gate 176)
+    if (warp == NGW)
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? s : steps - 1 - s;
+      const uint32_t ph = s & 1;
+      uint8_t* rprev = sRg + (ph ^ 1u) * RSLOT;                     // partial sums of step s - 1; then this step's operand
+      RW_STAMP(0);
       if (elect_one()) {
-        if (s == 0) mbar_wait_b(wbar, 0, 20);
-        mbar_wait_b(ofull, ph, 21);
-        fence_proxy_async_smem();
-        tc_fence_after();
-        const uint64_t dA = make_desc(smem_u32(sW)), dB = make_desc(smem_u32(rprev));
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {                        // peers' tiles first, the own tile last
-          const uint32_t m = WT ? i : ((c + 1 + i) & 3);          // WT: shared memory holds the tiles in issue order
+        for (int p = 0; p < NG; ++p) {                            // the groups take turns on the tensor pipe
+          if (s == 0 && p == 0) mbar_wait_b(wbar, 0, 20);
+          mbar_wait_b(&ofull[p], ph, 21);
+          fence_proxy_async_smem();
+          tc_fence_after();
+          const uint64_t dA = opaque64(make_desc(smem_u32(sW))), dB = opaque64(make_desc(smem_u32(sR) + ((uint32_t)p * 2 + (ph ^ 1u)) * RSLOT));
+          const uint32_t dcol = tmem + 128u * (uint32_t)p;
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint32_t bo = (ks >> 2) * BT + (ks & 3) * 2 * ATOM_BYTES;
-            if (WT && i == 3) {
-              if (ks == 0) umma_bf16_ta<0>(tmem + i * 32 * NG, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
-              else umma_bf16_ta<1>(tmem + i * 32 * NG, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
-            } else {
-              const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
-              if (ks == 0) umma_bf16_c<0>(tmem + i * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
-              else umma_bf16_c<1>(tmem + i * 32 * NG, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+          for (uint32_t i = 0; i < 4; ++i) {                      // peers' tiles first, the own tile last
+            const uint32_t m = WT ? i : ((c + 1 + i) & 3);        // WT: shared memory holds the tiles in issue order
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint32_t bo = (ks >> 2) * RW_BTILE + (ks & 3) * 2 * ATOM_BYTES;
+              if (WT && i == 3) {
+                if (ks == 0) umma_bf16_ta<0>(dcol + i * 32, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
+                else umma_bf16_ta<1>(dcol + i * 32, tmem + WCOL + ks * 8, desc_advance(dB, bo), idesc);
+              } else {
+                const uint32_t ao = (m * NKB + (ks >> 2)) * RW_ATILE + (ks & 3) * 2 * ATOM_BYTES;
+                if (ks == 0) umma_bf16_c<0>(dcol + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+                else umma_bf16_c<1>(dcol + i * 32, desc_advance(dA, ao), desc_advance(dB, bo), idesc);
+              }
             }
+            umma_commit(&done[4 * p + i]);
           }
-          umma_commit(&done[i]);
+          if (p == 0) RW_STAMP_MMA(3);
         }
-        RW_STAMP_MMA(3);
       }
       __syncwarp();
-    } else if (stw) {                                               // ---- store warp of TMEM lane quarter q, group grp ----
-      float dar[8], daz[8], dan[8], dgn[8];
-      const uint32_t sb = s & 1, stg = taddr + SBASE + 32u * (uint32_t)(2 * grp + (int)sb);
-      mbar_wait_warp(&sfull[sb], (s >> 1) & 1, 26);
-      tc_fence_after();
-      tmem_ld8(stg, dar);
-      tmem_ld8(stg + 8, daz);
-      tmem_ld8(stg + 16, dan);
-      tmem_ld8(stg + 24, dgn);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sempty[sb]);
+    }
+  } else if (stw) {
+    if constexpr (WS) reg_dec<104>();
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? s : steps - 1 - s;
+      const uint32_t sb = s & 1;
+#pragma unroll 1
+      for (int g_ = 0; g_ < NG; ++g_) {                             // the store warps serve the groups in turn
+        float dar[8], daz[8], dan[8], dgn[8];
+        const uint32_t stg = taddr + SBASE + 32u * (uint32_t)(2 * g_ + (int)sb);
+        mbar_wait_warp(&sfull[2 * g_ + sb], (s >> 1) & 1, 26);
+        tc_fence_after();
+        tmem_ld8(stg, dar);
+        tmem_ld8(stg + 8, daz);
+        tmem_ld8(stg + 16, dan);
+        tmem_ld8(stg + 24, dgn);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sempty[2 * g_ + sb]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
-        bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i];
+        for (int i = 0; i < 8; ++i) {
+          if constexpr (SUM) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
+          bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i];
+        }
+        if (a.exp & 16) continue;
+        const long gi_ = (long)blockIdx.y * NG + g_;
+        const long o = (long)t * bpad + gi_ * 16 + 8 * half;
+        st8_T_p16(d.dghT_p, d.gT_nk, u, o, dar);
+        st8_T_p16(d.dghT_p, d.gT_nk, H + u, o, daz);
+        st8_T_p16(d.dghT_p, d.gT_nk, 2 * H + u, o, dgn);
+        if (d.dgiT_p) {
+          st8_T_p16(d.dgiT_p, d.gT_nk, u, o, dar);
+          st8_T_p16(d.dgiT_p, d.gT_nk, H + u, o, daz);
+          st8_T_p16(d.dgiT_p, d.gT_nk, 2 * H + u, o, dan);
+        }
+        if (d.dgi_p) {
+          constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+          const long row = gi_ * 16 + nrow;
+          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
+                                (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+          const int rr = (int)(row & 127);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint4 hi, lo;
+            rw_transpose_pack(g == 0 ? dar : (g == 1 ? daz : dan), lane, hi, lo);
+            const int k = g * H + (int)c * UC + kq;
+            __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+            const int off = p16_in_tile(rr, k & 63);
+            *reinterpret_cast<uint4*>(tl + off) = hi;
+            *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+          }
+        }
       }
-      if (a.exp & 16) continue;
-      const long o = (long)t * bpad + b0;
-      st8_T_p16(d.dghT_p, d.gT_nk, u, o, dar);
-      st8_T_p16(d.dghT_p, d.gT_nk, H + u, o, daz);
-      st8_T_p16(d.dghT_p, d.gT_nk, 2 * H + u, o, dgn);
-      if (d.dgiT_p) {
-        st8_T_p16(d.dgiT_p, d.gT_nk, u, o, dar);
-        st8_T_p16(d.dgiT_p, d.gT_nk, H + u, o, daz);
-        st8_T_p16(d.dgiT_p, d.gT_nk, 2 * H + u, o, dan);
+    }
+    if constexpr (SW) {
+      if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
+        if (half == 0) {
+          atomicAdd(d.db_ih + u, bsum[0]); atomicAdd(d.db_ih + H + u, bsum[1]); atomicAdd(d.db_ih + 2 * H + u, bsum[2]);
+          atomicAdd(d.db_hh + u, bsum[0]); atomicAdd(d.db_hh + H + u, bsum[1]); atomicAdd(d.db_hh + 2 * H + u, bsum[3]);
+        }
       }
-      if (d.dgi_p) {
+      if constexpr (SUM) {                                          // (NG = 1 only: b0 / gidx are those of group 0)
+        st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
+        st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
+        st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
         constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
         const long row = gidx * 16 + nrow;
-        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_p) + (size_t)t * d.dgi_p_slot_elems +
-                              (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
         const int rr = (int)(row & 127);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
           uint4 hi, lo;
-          rw_transpose_pack(g == 0 ? dar : (g == 1 ? daz : dan), lane, hi, lo);
+          rw_transpose_pack(g == 0 ? sum_r : (g == 1 ? sum_z : sum_n), lane, hi, lo);
           const int k = g * H + (int)c * UC + kq;
           __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
           const int off = p16_in_tile(rr, k & 63);
@@ -1385,13 +1489,22 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
           *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
         }
       }
-    } else if (epi) {
+    }
+  } else if (epi) {
+    if constexpr (WS) reg_inc<SW ? 176 : (SUM ? 224 : 216)>();
+    if (d.dh_last) ld8(d.dh_last + (long)u * d.dh_last_ld + b0, carry);
+    load_step(0);
+    for (int s = 0; s < steps; ++s) {
+      const int t = d.reverse ? s : steps - 1 - s;
+      const uint32_t ph = s & 1;
+      uint8_t* rprev = sRg + (ph ^ 1u) * RSLOT;                     // partial sums of step s - 1; then this step's operand
+      RW_STAMP(0);
       float dar[8], daz[8], dan[8], dgn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] += carry[i] + own[i];
       if (s > 0) {
-        mbar_wait_cluster_b(&pfull[ph ^ 1u], ((s - 1) >> 1) & 1, 22);   // the peers' partial sums of step s - 1 have landed
-        if (tid == 0 && s + 1 < steps) mbar_expect_tx(&pfull[ph ^ 1u], RSLOT);   // arm it for the pushes of step s + 1
+        mbar_wait_cluster_b(&pfullg[ph ^ 1u], ((s - 1) >> 1) & 1, 22);   // the peers' partial sums of step s - 1 have landed
+        if (q == 0 && lane == 0 && s + 1 < steps) mbar_expect_tx(&pfullg[ph ^ 1u], RSLOT);   // arm it for the pushes of step s + 1
         __syncwarp();
         RW_STAMP(1);
         if (tid == 0) RW_STAMP_CTA8(0);
@@ -1416,57 +1529,56 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
         if constexpr (SUM && !SW) { sum_r[i] += dar[i]; sum_z[i] += daz[i]; sum_n[i] += dan[i]; }
         if constexpr (PRIV && !SW) { bsum[0] += dar[i]; bsum[1] += daz[i]; bsum[2] += dan[i]; bsum[3] += dgn[i]; }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(NGT) : "memory");        // everyone has consumed rprev before it becomes the operand
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // the group has consumed rprev before it becomes the operand
       uint4 rhi, rlo, zhi, zlo, ghi, glo;
       if constexpr (RW_MN) {
         split8(dar, rhi, rlo);
         split8(daz, zhi, zlo);
         split8(dgn, ghi, glo);
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, j)) = rhi;
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, j)) = rlo;
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, UC + j)) = zhi;
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, UC + j)) = zlo;
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 8 * half, 2 * UC + j)) = ghi;
-        *reinterpret_cast<uint4*>(rprev + mn_off(orow + 16 + 8 * half, 2 * UC + j)) = glo;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, j)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, j)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, UC + j)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, UC + j)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(8 * half, 2 * UC + j)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + rw_mn_off(16 + 8 * half, 2 * UC + j)) = glo;
       } else {
         rw_transpose_pack(dar, lane, rhi, rlo);
         rw_transpose_pack(daz, lane, zhi, zlo);
         rw_transpose_pack(dgn, lane, ghi, glo);
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, kq)) = rhi;
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, kq)) = rlo;
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, UC + kq)) = zhi;
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, UC + kq)) = zlo;
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + nrow, 2 * UC + kq)) = ghi;
-        *reinterpret_cast<uint4*>(rprev + b_off(orow + 16 + nrow, 2 * UC + kq)) = glo;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, kq)) = rhi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, kq)) = rlo;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, UC + kq)) = zhi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, UC + kq)) = zlo;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(nrow, 2 * UC + kq)) = ghi;
+        *reinterpret_cast<uint4*>(rprev + rw_b_off(16 + nrow, 2 * UC + kq)) = glo;
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(ofull);
+      mbar_arrive(&ofull[grp]);
       RW_STAMP(2);
       if (tid == 0) RW_STAMP_CTA8(2);
       if (tid == 96) RW_STAMP_CTA8(3);
       // ---- while the MMAs run: next step's inputs ----
       if (s + 1 < steps && !(a.exp & 64)) load_step(s + 1);          // (experiment 64: no global loads)
       // ---- partial sums of dh_{t-1}: accumulator i holds the input units owned by CTA (c + 1 + i) & 3 ----
-      const uint32_t acc = taddr + 32u * (uint32_t)grp;             // this group's 32 columns inside every accumulator tile
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {
-        mbar_wait_warp(&done[i], ph, 24);
+        mbar_wait_warp(&doneg[i], ph, 24);
         tc_fence_after();
         RW_STAMP(6 + i);
         float part[8];
-        rw_reduce32(acc + i * 32 * NG, half, part);
+        rw_reduce32(tacc + i * 32, half, part);
         if (i == 0 && s > 0) {
           // the receive slot written below is the peers' operand of step s - 1: their MMAs of that step must be complete
           // (signalled long ago - this wait only makes the ordering a guarantee instead of a timing margin)
-          mbar_wait_cluster_b(&mfree[ph ^ 1u], ((s - 1) >> 1) & 1, 23);
+          mbar_wait_cluster_b(&mfreeg[ph ^ 1u], ((s - 1) >> 1) & 1, 23);
           __syncwarp();
         }
         if (i < 3) {
           const uint32_t owner = (c + 1 + i) & 3;
           const uint32_t slot = (c - owner - 1) & 3;             // = 2 - i: position of this CTA among the owner's three peers
-          const uint32_t off = smem_u32(sR) + ph * RSLOT + part_off((int)slot, j);
-          const uint32_t ra = mapa_u32(off, owner), pbar = mapa_u32(smem_u32(&pfull[ph]), owner);
+          const uint32_t off = smem_u32(sRg) + ph * RSLOT + part_off((int)slot, j);
+          const uint32_t ra = mapa_u32(off, owner), pbar = mapa_u32(smem_u32(&pfullg[ph]), owner);
           st_async_f4(ra, part[0], part[1], part[2], part[3], pbar);
           st_async_f4(ra + 16, part[4], part[5], part[6], part[7], pbar);
           if (i == 2 && tid == 0) RW_STAMP_CTA8(4);
@@ -1478,8 +1590,8 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
           if (lane == 0 && s + 1 < steps) {
 #pragma unroll
             for (uint32_t r = 1; r < 4; ++r) {
-              if (a.exp & 128) mbar_arrive_remote(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
-              else mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&mfree[ph]), (c + r) & 3));
+              if (a.exp & 128) mbar_arrive_remote(mapa_u32(smem_u32(&mfreeg[ph]), (c + r) & 3));
+              else mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&mfreeg[ph]), (c + r) & 3));
             }
           }
         }
@@ -1492,7 +1604,7 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
       //      cluster scope waits for every earlier store of the thread ----
       if constexpr (SW) {                                           // hand the gate gradients to the store warps
         const uint32_t sb = s & 1, stg = taddr + SBASE + 32u * (uint32_t)(2 * grp + (int)sb);
-        if (s >= 2) mbar_wait_warp(&sempty[sb], ((s - 2) >> 1) & 1, 27);
+        if (s >= 2) mbar_wait_warp(&sempty[2 * grp + sb], ((s - 2) >> 1) & 1, 27);
         __syncwarp();                                               // tcgen05.st is .sync.aligned: the warp must be converged
         tc_fence_after();
         tmem_st8(stg, dar);
@@ -1501,7 +1613,7 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
         tmem_st8(stg + 24, dgn);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&sfull[sb]);
+        mbar_arrive(&sfull[2 * grp + sb]);
         continue;
       }
       if (!(a.exp & 16)) {                                         // (experiment 16: no global stores)
@@ -1547,50 +1659,48 @@ __global__ void __launch_bounds__((SW ? 8 * NG + 1 : 4 * NG + 1) * 32, 1) gru_rw
       }
       RW_STAMP(5);
     }
-  }
   // gradient of the initial state: carry + own tile + the peers' partial sums of the last step
-  if (epi) {
-    mbar_wait_cluster_b(&pfull[(steps - 1) & 1], ((steps - 1) >> 1) & 1, 25);
-    __syncwarp();
-    const uint8_t* rl = sR + ((steps - 1) & 1) * RSLOT;
-    float g0[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g0[i] = carry[i] + own[i];
-#pragma unroll
-    for (int src = 0; src < 3; ++src) {
-      float v[8];
-      ld8s(reinterpret_cast<const float*>(rl + part_off(src, j)), v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g0[i] += v[i];
-    }
-    st8(d.dh0_out + (long)u * bpad + b0, g0);
-  }
-  if (SW ? stw : epi) {
-    if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
-#pragma unroll
-      for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
-      if (half == 0) {
-        atomicAdd(d.db_ih + u, bsum[0]); atomicAdd(d.db_ih + H + u, bsum[1]); atomicAdd(d.db_ih + 2 * H + u, bsum[2]);
-        atomicAdd(d.db_hh + u, bsum[0]); atomicAdd(d.db_hh + H + u, bsum[1]); atomicAdd(d.db_hh + 2 * H + u, bsum[3]);
+      mbar_wait_cluster_b(&pfullg[(steps - 1) & 1], ((steps - 1) >> 1) & 1, 25);
+      __syncwarp();
+      const uint8_t* rl = sRg + ((steps - 1) & 1) * RSLOT;
+      float g0[8];
+  #pragma unroll
+      for (int i = 0; i < 8; ++i) g0[i] = carry[i] + own[i];
+  #pragma unroll
+      for (int src = 0; src < 3; ++src) {
+        float v[8];
+        ld8s(reinterpret_cast<const float*>(rl + part_off(src, j)), v);
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) g0[i] += v[i];
       }
-    }
-    if constexpr (SUM) {
-      st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
-      st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
-      st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
-      constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
-      const long row = gidx * 16 + nrow;
-      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
-      const int rr = (int)(row & 127);
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        uint4 hi, lo;
-        rw_transpose_pack(g == 0 ? sum_r : (g == 1 ? sum_z : sum_n), lane, hi, lo);
-        const int k = g * H + (int)c * UC + kq;
-        __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
-        const int off = p16_in_tile(rr, k & 63);
-        *reinterpret_cast<uint4*>(tl + off) = hi;
-        *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+      st8(d.dh0_out + (long)u * bpad + b0, g0);
+    if constexpr (!SW) {
+      if constexpr (PRIV) {                                         // lanes l and l + 16 own the same unit
+  #pragma unroll
+        for (int k = 0; k < 4; ++k) bsum[k] += __shfl_xor_sync(0xffffffffu, bsum[k], 16);
+        if (half == 0) {
+          atomicAdd(d.db_ih + u, bsum[0]); atomicAdd(d.db_ih + H + u, bsum[1]); atomicAdd(d.db_ih + 2 * H + u, bsum[2]);
+          atomicAdd(d.db_hh + u, bsum[0]); atomicAdd(d.db_hh + H + u, bsum[1]); atomicAdd(d.db_hh + 2 * H + u, bsum[3]);
+        }
+      }
+      if constexpr (SUM) {
+        st8(d.dgi_sum + (long)u * bpad + b0, sum_r);
+        st8(d.dgi_sum + (long)(H + u) * bpad + b0, sum_z);
+        st8(d.dgi_sum + (long)(2 * H + u) * bpad + b0, sum_n);
+        constexpr int nkc3 = (3 * H + KCHUNK - 1) / KCHUNK;
+        const long row = gidx * 16 + nrow;
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(d.dgi_sum_p) + (size_t)(row >> 7) * nkc3 * p16_tile_elems(128);
+        const int rr = (int)(row & 127);
+  #pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          uint4 hi, lo;
+          rw_transpose_pack(g == 0 ? sum_r : (g == 1 ? sum_z : sum_n), lane, hi, lo);
+          const int k = g * H + (int)c * UC + kq;
+          __nv_bfloat16* tl = base + (size_t)(k >> 6) * p16_tile_elems(128);
+          const int off = p16_in_tile(rr, k & 63);
+          *reinterpret_cast<uint4*>(tl + off) = hi;
+          *reinterpret_cast<uint4*>(tl + 128 * KCHUNK + off) = lo;
+        }
       }
     }
   }
@@ -1644,10 +1754,10 @@ static void rw_launch(K kernel, const A& a, size_t smem, int groups, int ndir, c
 template <int NG>
 static void rw2_launch_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
   const int groups = a.tiles * 8 / NG;
-  const size_t smem = (size_t)12 * RW_ATILE + (size_t)(NG == 1 ? 2 : 1) * 4 * RW_BTILE * NG + 256;
-  if (a.d[0].priv && (g_opt_rw_sw & 1)) rw_launch(gru_rw2_fwd_kernel<true, true, NG>, a, smem, groups, a.ndir, st, (4 * NG + 5) * 32);
-  else if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true, false, NG>, a, smem, groups, a.ndir, st, (4 * NG + 1) * 32);
-  else rw_launch(gru_rw2_fwd_kernel<false, false, NG>, a, smem, groups, a.ndir, st, (4 * NG + 1) * 32);
+  const size_t smem = (size_t)12 * RW_ATILE + (size_t)(NG == 1 ? 2 : 1) * 4 * RW_BTILE * NG + 512;
+  if (a.d[0].priv && (g_opt_rw_sw & 1)) rw_launch(gru_rw2_fwd_kernel<true, true, NG>, a, smem, groups, a.ndir, st, rw2_fwd_threads(true, NG));
+  else if (a.d[0].priv) rw_launch(gru_rw2_fwd_kernel<true, false, NG>, a, smem, groups, a.ndir, st, rw2_fwd_threads(false, NG));
+  else rw_launch(gru_rw2_fwd_kernel<false, false, NG>, a, smem, groups, a.ndir, st, rw2_fwd_threads(false, NG));
 }
 
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
@@ -1673,15 +1783,15 @@ void launch_gru_rw_fwd(const GruSeqFwdArgs& a_in, cudaStream_t st) {
 template <bool SUM, int NG>
 static void rw2_launch_bwd(const GruSeqBwdArgs& a, cudaStream_t st) {
   const int groups = a.tiles * 8 / NG;
-  const size_t sm2 = (size_t)(NG == 2 ? 9 : 12) * RW_ATILE + (size_t)2 * 12288 * NG + 256;
-  if constexpr (NG == 1) {
-    if (a.d[0].priv && (g_opt_rw_sw & 2)) {
-      rw_launch(gru_rw2_bwd_kernel<SUM, true, true, 1>, a, sm2, groups, a.ndir, st, 9 * 32);
+  const size_t sm2 = (size_t)(NG == 2 ? 9 : 12) * RW_ATILE + (size_t)2 * 12288 * NG + 512;
+  if constexpr (NG == 1 || !SUM) {
+    if (a.d[0].priv && (g_opt_rw_sw & (NG == 1 ? 2 : 4))) {         // rw_sw bit 1: store warps at 16 rows per cluster, bit 2: at 2 x 16
+      rw_launch(gru_rw2_bwd_kernel<SUM, true, true, NG>, a, sm2, groups, a.ndir, st, rw2_bwd_threads(true, NG));
       return;
     }
   }
-  if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true, false, NG>, a, sm2, groups, a.ndir, st, (4 * NG + 1) * 32);
-  else rw_launch(gru_rw2_bwd_kernel<SUM, false, false, NG>, a, sm2, groups, a.ndir, st, (4 * NG + 1) * 32);
+  if (a.d[0].priv) rw_launch(gru_rw2_bwd_kernel<SUM, true, false, NG>, a, sm2, groups, a.ndir, st, rw2_bwd_threads(false, NG));
+  else rw_launch(gru_rw2_bwd_kernel<SUM, false, false, NG>, a, sm2, groups, a.ndir, st, rw2_bwd_threads(false, NG));
 }
 
 template <bool SUM>
