@@ -63,6 +63,12 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append((time.time(), ln.strip()))
 
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a moment to come up: block until its first sample so that short timed regions are covered."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self, t0=None, t1=None):
         """t0/t1 (time.time()): keep the samples that arrived inside the timed region; the sampler is started before the warm-up
         steps (nvidia-smi needs ~0.1 s to come up, longer than a short timed region), so if none fell inside, the samples taken
@@ -138,6 +144,80 @@ def cpu_port_step_time(F, T, Z, H, fut, S, B, steps, warmup, threads=None, budge
     return dt, torch.get_num_threads()
 
 
+def train_epoch_throughput(F, T, Z, H, fut, S, B, dev, n_batches=200):
+    """windows/s of the drop-in vame_b200.rnn_vae.train() (the function vame.train_model calls once per epoch) over n_batches
+    batches, fed (a) by host float64 batches like the reference's DataLoader yields and (b) by the device sampler."""
+    import tempfile
+    import numpy as np
+    import torch
+    from vame_b200 import rnn_vae as rv
+    from vame_b200.dataloader import SEQUENCE_DATASET, Data
+    from vame_b200.rnn_model import RNN_VAE
+    torch.manual_seed(19)
+    model = RNN_VAE(2 * T, Z, F, fut, S, H, H, H, H, 0, 0, 0, False).cuda(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, amsgrad=True)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=1)
+    rng = np.random.default_rng(19)
+    N = n_batches * B
+    series = np.cumsum(rng.standard_normal((F, N)), axis=1) * 0.05 + rng.standard_normal((F, N))
+    out = {"batches": n_batches, "unit": "windows/s"}
+    with tempfile.TemporaryDirectory() as tmp:
+        d = tmp + os.sep
+        import contextlib
+        import io
+        np.save(d + "train_seq.npy", series)
+        with contextlib.redirect_stdout(io.StringIO()):          # (the dataset prints like the reference's)
+            ds = SEQUENCE_DATASET(d, data="train_seq.npy", train=True, temporal_window=2 * T)
+        loader = Data.DataLoader(ds, batch_size=B, shuffle=True, drop_last=True)            # -> DeviceWindowSampler
+        g = torch.Generator().manual_seed(3)
+        host = [torch.randn(B, F, 2 * T, generator=g, dtype=torch.float64) for _ in range(8)]
+        host_loader = [host[i % 8] for i in range(n_batches)]
+        for name, ld in (("device_sampler", loader), ("host_f64_loader", host_loader)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                rv.train(ld if name == "device_sampler" else host_loader[:8], 1, model, opt, "linear", 1, 0, 4, 2 * T, fut, S, sched,
+                         "sum", "sum", Z, 0.1, B, False)                                # warm-up: graph capture
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rv.train(ld, 2, model, opt, "linear", 1, 0, 4, 2 * T, fut, S, sched, "sum", "sum", Z, 0.1, B, False)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            out[name] = len(ld) * B / dt
+            out[name + "_ms_per_batch"] = dt / len(ld) * 1e3
+    return out
+
+
+def cudnn_reference_step(F, T, Z, H, fut, S, B, dev, steps=10, warmup=3):
+    """The comparator BASELINE.md section 3 names: the reference's own modules (oracle port = the same nn.GRU / nn.Linear /
+    torch.svd calls) moved to the B200 with .cuda(), i.e. PyTorch's cuDNN RNN path - the only other sm_100 kernel for this op."""
+    import torch
+    from oracle import vame_oracle as vo
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)
+    device = torch.device("cuda", dev)
+    for m in port.mods.values():
+        m.to(device)
+    opt = vo.make_optimizer(port)
+    x, xf, eps = (t.to(device) for t in vo.synthetic_batch(B, T, F, max(S, 1), Z))
+    xf = xf[:, :S] if fut else xf
+    hp = dict(beta=1.0, kl_weight=1.0, kmeans_loss=Z, kmeans_lambda=0.1, bsize=B)
+    try:
+        for _ in range(warmup):
+            vo.train_step(port, x, xf, eps, hp, optimizer=opt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            vo.train_step(port, x, xf, eps, hp, optimizer=opt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": B / (ms * 1e-3), "unit": "windows/s", "ms_per_step": ms, "steps": steps,
+                "what": "reference modules on the GPU (torch %s: cuDNN GRU, cuBLAS linears, cuSOLVER B x B SVD of cluster_loss, "
+                        "torch.optim.Adam(amsgrad)), eager, fp32, .item() of 4-5 loss terms per step as in train()" % torch.__version__}
+    except Exception as ex:      # a comparator must never take the benchmark down
+        return {"value": None, "error": repr(ex)[:200]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,6 +236,8 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-epoch", action="store_true", help="skip the train()-epoch measurement (e2e_train_epoch)")
+    ap.add_argument("--no-cudnn", action="store_true", help="skip the cuDNN comparator (the reference's modules moved to the GPU)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for experiments (vame_set_option), recorded in config.options")
     args = ap.parse_args()
@@ -171,7 +253,8 @@ def main():
                             "bwd + %sAMSGrad" % (args.workload, F, T, Z, H, B, "future decoder S=%d" % S if fut else "no future decoder",
                                                  "/future" if fut else "", "NCCL grad allreduce + " if world > 1 else ""),
                 "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
-                "l2": "per-step working set (activations + P16 operand copies, > 1 GB) exceeds the 126 MB L2; no explicit flush"}
+                "l2": "per-step working set (activations + P16 operand copies, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+                "batches": "8 distinct synthetic batches in rotation (device-resident for `value`, pinned host memory for `e2e`)"}
     step_flops = 3 * fwd_flops_per_window(F, T, Z, H, fut, S) * B            # train = 3 x forward
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -211,8 +294,15 @@ def main():
     port = vo.RefPort(2 * T, Z, F, fut, S, hidden=H)                  # reference default init under seed 19 (rnn_vae.py:292)
     eng = Engine(F, T, Z, H, H, H, fut, S, False, device="cuda:%d" % local_rank)
     eng.load_state_dict(port.state_dict())
-    x, xf, eps = vo.synthetic_batch(B, T, F, max(S, 1), Z, seed=19 + rank)
-    xf = xf[:, :S] if fut else None
+    # NB distinct synthetic batches in rotation (a fresh batch every step, like training): with ONE repeated batch the latent
+    # Gram matrix barely moves between steps and the warm-started eigen-solver of the k-means prior would look better than in use
+    NB = 8
+    batches = []
+    for i in range(NB):
+        bx, bf, be = vo.synthetic_batch(B, T, F, max(S, 1), Z, seed=19 + rank + 1000 * i)
+        batches.append((bx, bf[:, :S] if fut else None, be))
+    x, xf, eps = batches[0]
+    dev_batches = [(a.cuda(), b.cuda() if fut else None, c.cuda()) for a, b, c in batches]
     cfg = eng.loss_cfg(kmeans_loss=Z, kmeans_lambda=0.1, bsize=B, beta=1.0, kl_weight=1.0)
     eng.set_hyper(lr=5e-4, kl_weight=1.0, beta=1.0, kmeans_lambda=0.1)
     ts = TrainStep(eng, B, cfg, world=world, use_graph=not args.no_graph)
@@ -227,16 +317,30 @@ def main():
 
     # ---- device-resident throughput
     sampler = ClockSampler(local_rank)
-    sampler.start()                                        # (comes up during the warm-up steps)
-    for _ in range(W):
-        ts.run()
+    sampler.start()
+    sampler.wait_first()                                   # the first sample is in before the warm-up starts
+    def step(i):
+        ts.load(*dev_batches[i % NB])                      # device -> static buffers (three small copies on the stream)
+        return ts.run()
+
+    for i in range(W):
+        step(i)
+    barrier()
+    # keep the GPU under the same load until the sampler has delivered a few samples of it (25 ms period), so that the clocks
+    # line always holds samples taken under load even when the timed region itself is shorter than one sampling period
+    n_lines = len(sampler.lines)
+    t_lim = time.time() + 1.0
+    while len(sampler.lines) < n_lines + 4 and time.time() < t_lim:
+        for i in range(10):
+            step(i)
+        torch.cuda.synchronize()
     barrier()
     launches0 = lib.vame_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    for _ in range(K):
-        ts.run()
+    for i in range(K):
+        step(i)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -250,21 +354,21 @@ def main():
     loss_after = float(ts.losses[4].item())
 
     # ---- end to end through host buffers: pinned H2D of the batch + D2H of the loss every step
-    xh, eh = x.pin_memory(), eps.pin_memory()
-    fh = xf.pin_memory() if fut else None
+    host_batches = [(a.pin_memory(), b.pin_memory() if fut else None, c.pin_memory()) for a, b, c in batches]
+    xh, fh, eh = host_batches[0]
     loss_h = torch.zeros(8).pin_memory()
     # the host batch of step i+1 is handed to TrainStep.load() right after step i has been enqueued: it is uploaded on a copy
     # stream while step i computes; every timed step still contains one H2D of a full batch and one D2H of the loss vector
-    for _ in range(3):
-        ts.load(xh, fh, eh)
+    for i in range(3):
+        ts.load(*host_batches[i % NB])
         ts.run()
     barrier()
     e0.record()
-    ts.load(xh, fh, eh)
+    ts.load(*host_batches[0])
     for i in range(K):
         out = ts.run()
         if i + 1 < K:
-            ts.load(xh, fh, eh)
+            ts.load(*host_batches[(i + 1) % NB])
         loss_h.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the caller consumes the loss every step
     e1.record()
@@ -335,6 +439,16 @@ def main():
                 "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
                 "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
 
+    # ---- the plugin call itself: windows/s of vame_b200.rnn_vae.train() over one epoch of >= 200 batches (rank 0, N = 1):
+    #      (a) fed by a reference-style loader of HOST float64 (B, F, 2T) batches (rnn_vae.py:106-112: cast + H2D per batch),
+    #      (b) fed by the on-device window sampler that install() binds into vame.model.rnn_vae (one graph replay per batch)
+    epoch = None
+    if rank == 0 and world == 1 and not args.no_train_epoch:
+        epoch = train_epoch_throughput(F, T, Z, H, fut, S, B, local_rank)
+    cudnn = None
+    if rank == 0 and world == 1 and not args.no_cudnn:
+        cudnn = cudnn_reference_step(F, T, Z, H, fut, S, B, local_rank)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -350,7 +464,8 @@ def main():
                 "config": dict(cfg_desc, cuda_graph=bool(graphed)), "clocks": clocks,
                 "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 32},
-                "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu, "loss_after": loss_after}
+                "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu, "loss_after": loss_after,
+                "e2e_train_epoch": epoch, "cudnn_reference": cudnn, "nccl_in_graph": bool(getattr(ts, "nccl_in_graph", False))}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -175,6 +175,21 @@ int vame_trainset_row_std(const double* x_fn, long n_frames, int num_features, d
 int vame_trainset_savgol(const double* x_fn, long n_frames, int num_features, int window, const double* coeffs, const double* head,
                          const double* tail, double* out_fn, void* stream);
 
+/* ---- on-device window sampler ------------------------------------------------------------------------------
+ * Replaces SEQUENCE_DATASET.__getitem__ (vame/model/dataloader.py:45-56) + torch DataLoader collation + the permute / split /
+ * float32 cast at the top of train() (vame/model/rnn_vae.py:107-112) for one batch.  series_fn: the reference's (num_features,
+ * n_frames) float64 array (train_seq.npy / test_seq.npy), resident on the device; mean / std: the scalars of seq_mean.npy /
+ * seq_std.npy.  Window b covers frames start_b .. start_b + window - 1 with start_b uniform in [0, n_frames - window)
+ * (np.random.choice(nf - temp_window), dataloader.py:49) drawn from a Philox4x32-10 stream keyed by (seed, *counter, b), or
+ * taken from `starts` (device int64[batch]) when given.  Outputs: x [batch, t_data, F] = frames 0 .. t_data-1 of the z-scored
+ * window as float32, fut [batch, t_future, F] = frames t_data .. t_data+t_future-1 (may be NULL), eps [batch, zdims] standard
+ * normal (may be NULL; the reference's randn_like, rnn_model.py:73), starts_out int64[batch] (may be NULL).
+ * counter: device uint64 draw counter (may be NULL = draw 0); incremented on the stream after the batch, so CUDA-graph replays
+ * of the call produce fresh batches. */
+int vame_sample_windows(const double* series_fn, long n_frames, int num_features, int window, double mean, double std,
+                        int batch, int t_data, int t_future, int zdims, const long long* starts, unsigned long long seed,
+                        unsigned long long* counter, float* x, float* fut, float* eps, long long* starts_out, void* stream);
+
 /* ---- k-means on the latent vectors ---------------------------------------------------------------------
  * Replaces sklearn.cluster.KMeans(init='k-means++', n_clusters, random_state, n_init).fit / .predict as called at
  * vame/analysis/pose_segmentation.py:141-143 and :183-185.  x is [n, dim] fp32 row-major on the device (dim <= 64,

@@ -116,6 +116,39 @@ def gen_step_case(name, rm, rv):
     print("wrote step_%s" % name, "total", total.item())
 
 
+def gen_step_opts(rm, rv):
+    """The option branches the default configuration never takes, through the reference's own objects: Lambda softplus
+    (rnn_model.py:59-61,67), MSE reduction 'mean' for both reconstruction terms (rnn_vae.py:35-43), kmeans_loss < zdims
+    (rnn_vae.py:48: only the leading singular values) and three different hidden sizes (rnn_model.py:158-161)."""
+    B, T, F, Z, S = 20, 6, 7, 6, 3
+    H1, HR, HP, K = 64, 32, 96, 3
+    torch.manual_seed(19)
+    model = rm.RNN_VAE(2 * T, Z, F, True, S, H1, H1, HR, HP, 0, 0, 0, True)
+    x, xf, eps = _inputs(B, T, F, S, Z)
+    klw, lam = 0.7, 0.1
+    model.train()
+    pred, future, z, mu, logvar = _with_eps(eps, lambda: model(x))
+    rec = rv.reconstruction_loss(x, pred, "mean")
+    fl = rv.future_reconstruction_loss(xf, future, "mean")
+    kl = rv.kullback_leibler_loss(mu, logvar)
+    km = rv.cluster_loss(z.T, K, lam, B)
+    total = rec + fl + 1.0 * klw * kl + klw * km
+    model.zero_grad()
+    total.backward()
+    d = dict(x=x.numpy(), fut=xf.numpy(), eps=eps.numpy(), pred=pred.detach().numpy(), future=future.detach().numpy(),
+             z=z.detach().numpy(), mu=mu.detach().numpy(), logvar=logvar.detach().numpy(), loss_rec=rec.item(), loss_fut=fl.item(),
+             loss_kl=kl.item(), loss_kmeans=km.item(), loss_total=total.item(),
+             cfg=np.array([B, T, F, Z, S, H1, HR, HP, K]), hp_kl_weight=klw, hp_lambda=lam)
+    model.eval()
+    with torch.no_grad():
+        d["pred_eval"] = model(x)[0].numpy()
+    for k, p in model.named_parameters():
+        d["grad/" + k] = p.grad.detach().numpy().copy()
+        d["w/" + k] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "step_opts.npz"), **d)
+    print("wrote step_opts total", total.item())
+
+
 def gen_train_fn(rm, rv):
     """Reference train()/test() (rnn_vae.py:94-210) on a fixed 5-batch loader; pins the 6-tuple / 3-tuple
     return values including the division by idx = n_batches-1."""
@@ -192,6 +225,59 @@ def gen_video1(rm, ps):
     np.savez_compressed(os.path.join(OUT, "video1.npz"), clean=clean.astype(np.float32),
                         latent_first=lat[::40].copy(), n_ref_windows=lat.shape[0], cfg=np.array([T, F, Z, H]))
     print("wrote video1", clean.shape, lat.shape)
+
+
+def gen_video1_trained(rm, rv, ps, epochs=10, batch=128):
+    """A TRAINED checkpoint for the video-1 embedding check (the error of split-precision products grows with |W_hh|,
+    which the seed-19 initial weights do not exercise): the reference's own train() (vame/model/rnn_vae.py:94-164) on the
+    reference's SEQUENCE_DATASET + DataLoader over video-1's train_seq.npy for `epochs` epochs (KL annealing as in the default
+    config: kl_start 2, annealtime 4), then the reference's embedd_latent_vectors loop with the trained weights on the first 6000
+    frames.  Committed: the state_dict (fp32) and every 40th latent vector; the cleaned series is the one of video1.npz."""
+    import shutil
+    import torch.utils.data as Data
+    import vame
+    from vame.util import auxiliary
+    T, F, Z, H = 30, 12, 30, 256
+    dl = sys.modules["vame.model.dataloader"]
+    with tempfile.TemporaryDirectory() as tmp:
+        proj = os.path.join(tmp, "proj")
+        for sub in ("videos/pose_estimation", "data/video-1", "data/train", "results/video-1", "model"):
+            os.makedirs(os.path.join(proj, sub))
+        shutil.copy("/root/reference/examples/video-1.csv", os.path.join(proj, "videos", "pose_estimation", "video-1.csv"))
+        cfg_file, _ = auxiliary.create_config_template()
+        cfg_file["Project"] = "proj"
+        cfg_file["project_path"] = proj
+        cfg_file["video_sets"] = ["video-1"]
+        cfg_file.update(dict(egocentric_data=True, num_features=F, time_window=T, zdims=Z, test_fraction=0.1,
+                             pose_confidence=0.99, iqr_factor=4, savgol_filter=True, savgol_length=5,
+                             savgol_order=2, robust=True, all_data="yes", batch_size=batch,
+                             prediction_decoder=0, prediction_steps=15))
+        cfgp = os.path.join(proj, "config.yaml")
+        auxiliary.write_config(cfgp, cfg_file)
+        vame.csv_to_numpy(cfgp)
+        vame.create_trainset(cfgp, check_parameter=False)
+        clean = np.load(os.path.join(proj, "data", "video-1", "video-1-PE-seq-clean.npy"))
+        model = _ref_model(rm, T, Z, F, False, 0, H)
+        np.random.seed(19)                                   # the reference dataset draws window starts from numpy's global stream
+        torch.manual_seed(19)
+        trainset = dl.SEQUENCE_DATASET(os.path.join(proj, "data", "train", ""), data="train_seq.npy", train=True, temporal_window=2 * T)
+        loader = Data.DataLoader(trainset, batch_size=batch, shuffle=True, drop_last=True)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4, amsgrad=True)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=100, gamma=1)
+        hist = []
+        for epoch in range(1, epochs + 1):
+            ret = rv.train(loader, epoch, model, opt, "linear", 1, 2, 4, 2 * T, False, 15, sched, "sum", "sum", Z, 0.1, batch, False)
+            hist.append([float(v) for v in ret])
+            print("epoch", epoch, hist[-1], flush=True)
+        model.eval()
+        cfg = dict(project_path=proj, time_window=T, num_features=F)
+        np.save(os.path.join(proj, "data", "video-1", "video-1-PE-seq-clean.npy"), clean[:, :6000])
+        lat = ps.embedd_latent_vectors(cfg, ["video-1"], model, True)[0]
+    sd = {"w/" + k: v.detach().numpy() for k, v in model.state_dict().items()}
+    whh = max(float(np.abs(v).max()) for k, v in sd.items() if "weight_hh" in k)
+    np.savez_compressed(os.path.join(OUT, "video1_trained.npz"), latent_first=lat[::40].copy(), n_ref_windows=lat.shape[0],
+                        cfg=np.array([T, F, Z, H]), history=np.array(hist), epochs=np.array([epochs]), batch=np.array([batch]), **sd)
+    print("wrote video1_trained", lat.shape, "max |W_hh| %.3f (init bound %.4f)" % (whh, 1 / np.sqrt(H)))
 
 
 def gen_kmeans(ps):
@@ -312,11 +398,19 @@ def main():
     if "--only-trainset" in sys.argv:
         gen_trainset()
         return
+    if "--only-step-opts" in sys.argv:
+        gen_step_opts(rm, rv)
+        return
+    if "--only-video1-trained" in sys.argv:
+        gen_video1_trained(rm, rv, ps)
+        return
     for name in CASES:
         gen_step_case(name, rm, rv)
+    gen_step_opts(rm, rv)
     gen_train_fn(rm, rv)
     gen_embed_synth(rm, ps)
     gen_video1(rm, ps)
+    gen_video1_trained(rm, rv, ps)
     gen_kmeans(ps)
     gen_trainset()
 

@@ -23,10 +23,22 @@ def _free_port():
 
 
 class _FakeEngine:
-    """Stands in for vame_b200.engine.Engine on a CPU box: only the flat gradient buffer matters to the exchange."""
+    """Stands in for vame_b200.engine.Engine on a CPU box: only the flat buffers matter to the exchange / the safeguards."""
 
-    def __init__(self, grad):
+    def __init__(self, grad, flat=None):
         self.grad = grad
+        self.flat = flat
+        self.opt_state = None
+        self.dirty = False
+
+    def init_optimizer(self):
+        if self.opt_state is None:
+            z = lambda: torch.zeros_like(self.flat)  # noqa: E731
+            self.opt_state = dict(exp_avg=z(), exp_avg_sq=z(), max_exp_avg_sq=z(), step=torch.zeros(1, dtype=torch.int32))
+        return self.opt_state
+
+    def mark_dirty(self):
+        self.dirty = True
 
 
 def _worker(rank, world, port, q):
@@ -50,7 +62,21 @@ def _worker(rank, world, port, q):
     g = eng.grad.numpy().astype(np.float64) / world
     m, v, vm = np.zeros_like(w), np.zeros_like(w), np.zeros_like(w)
     gnp.amsgrad_step(w, g, m, v, vm, 1, 5e-4)
-    q.put((rank, flat.numpy(), eng.grad.numpy(), w))
+    # replica-consistency safeguards: ranks that start from different weights / optimizer state are detected, and
+    # made identical by the broadcast that precedes the first data-parallel train step
+    from vame_b200.rnn_vae import _broadcast_replicas, assert_replicas_consistent
+    from vame_b200._lib import VameB200Error
+    e2 = _FakeEngine(None, flat=torch.full((1000,), float(rank + 1)))
+    e2.init_optimizer()["exp_avg"].fill_(float(rank))
+    try:
+        assert_replicas_consistent(e2)
+        diverged_detected = False
+    except VameB200Error:
+        diverged_detected = True
+    _broadcast_replicas(e2)
+    assert_replicas_consistent(e2)                                    # passes after the broadcast
+    ok = diverged_detected and bool((e2.flat == 1.0).all()) and bool((e2.opt_state["exp_avg"] == 0.0).all()) and e2.dirty
+    q.put((rank, flat.numpy(), eng.grad.numpy(), w, ok))
     dist.destroy_process_group()
 
 
@@ -71,6 +97,7 @@ def test_dp_allreduce_equals_shard_average():
     for r in res:
         np.testing.assert_allclose(r[2], summed, rtol=1e-6, atol=1e-7)       # every rank holds the global sum
     np.testing.assert_array_equal(res[0][3], res[1][3])                      # replicas stay bit-identical after the step
+    assert res[0][4] and res[1][4], "replica-consistency safeguards (broadcast / checksum) failed"
     # single-process emulation: reference on each shard, average, one step
     B, T, F, Z, H, S = 8, 6, 5, 4, 32, 3
     torch.manual_seed(19)

@@ -122,3 +122,40 @@ def test_trainstep_product_path_vs_oracle_and_repack_for_other_batch_sizes():
         mu_ref = twin.lmbda(twin.encode(xb), None)[1]
     e = float((out["mu"].double().cpu() - mu_ref.double()).abs().max() / mu_ref.double().abs().max())
     assert e <= 1e-4, e
+
+
+def test_load_model_and_embedd_latent_vectors_trained_checkpoint(tmp_path, golden_dir):
+    """The two inference drop-ins on a real project layout (vame/analysis/pose_segmentation.py:27-64, 67-101): a `.pkl` written
+    in the reference's format (torch.save of the state_dict, rnn_vae.py:367) holding the weights the REFERENCE's own train()
+    produced in 10 epochs on video-1 (oracle/gen_golden.py:gen_video1_trained; split-precision error grows with |W_hh|, which
+    initial weights do not exercise), `<file>-PE-seq-clean.npy` as create_trainset leaves it; the latent vectors must match the
+    reference's literal batch-1 loop (every 40th of the first 5970 windows) within 1e-4 and the oracle on all 29 967."""
+    from collections import OrderedDict
+    from oracle import vame_oracle as vo
+    from vame_b200 import pose_segmentation as ps
+    g = np.load(os.path.join(golden_dir, "video1_trained.npz"))
+    clean = np.load(os.path.join(golden_dir, "video1.npz"))["clean"].astype(np.float64)      # (F, N)
+    T, F, Z, H = (int(v) for v in g["cfg"])
+    proj = tmp_path / "proj"
+    (proj / "model" / "best_model").mkdir(parents=True)
+    (proj / "data" / "video-1").mkdir(parents=True)
+    np.save(proj / "data" / "video-1" / "video-1-PE-seq-clean.npy", clean)
+    sd = OrderedDict((k[2:], torch.from_numpy(g[k])) for k in g.files if k.startswith("w/"))
+    torch.save(sd, proj / "model" / "best_model" / "VAME_proj.pkl")
+    cfg = dict(project_path=str(proj), Project="proj", time_window=T, num_features=F, zdims=Z, prediction_decoder=0,
+               prediction_steps=15, hidden_size_layer_1=H, hidden_size_layer_2=H, hidden_size_rec=H, hidden_size_pred=H,
+               dropout_encoder=0, dropout_rec=0, dropout_pred=0, softplus=False)
+    model = ps.load_model(cfg, "VAME", True)
+    assert not model.training and list(model.state_dict().keys()) == list(sd.keys())
+    whh = max(float(v.abs().max()) for k, v in sd.items() if "weight_hh" in k)
+    assert whh > 1.5 / np.sqrt(H), "the fixture is supposed to hold TRAINED recurrent weights"
+    lat = ps.embedd_latent_vectors(cfg, ["video-1"], model, True)
+    assert len(lat) == 1 and lat[0].shape == (clean.shape[1] - T, Z) and lat[0].dtype == np.float32
+    n = int(g["n_ref_windows"])
+    ref = g["latent_first"]
+    err = np.abs(lat[0][:n][::40] - ref).max() / np.abs(ref).max()
+    assert err <= 1e-4, err
+    port = vo.RefPort(2 * T, Z, F, False, 0, hidden=H).load_state_dict(sd)
+    full = vo.embed_batched(port, clean, T)
+    err_full = np.abs(lat[0] - full).max() / np.abs(full).max()
+    assert err_full <= 1e-4, err_full

@@ -64,6 +64,10 @@ def test_install_rebinds_hot_path_names():
         assert sys.modules["vame.model.rnn_vae"].RNN_VAE is rnn_model.RNN_VAE
         assert sys.modules["vame.model.rnn_vae"].train is rnn_vae.train
         assert sys.modules["vame.model.rnn_vae"].cluster_loss is rnn_vae.cluster_loss
+        from vame_b200 import dataloader
+        assert sys.modules["vame.model.rnn_vae"].SEQUENCE_DATASET is dataloader.SEQUENCE_DATASET      # the loader seam
+        assert sys.modules["vame.model.rnn_vae"].Data.DataLoader is dataloader.Data.DataLoader
+        assert sys.modules["vame.model.rnn_vae"].Data.Dataset is torch.utils.data.Dataset               # everything else forwards
         assert sys.modules["vame.analysis.pose_segmentation"].RNN_VAE is rnn_model.RNN_VAE
         assert sys.modules["vame.analysis.pose_segmentation"].load_model is pose_segmentation.load_model
         assert sys.modules["vame.model.evaluate"].RNN_VAE is rnn_model.RNN_VAE
@@ -74,3 +78,33 @@ def test_install_rebinds_hot_path_names():
         for m in mods:
             sys.modules[m].__dict__.clear()
             sys.modules[m].__dict__.update(saved[m])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not reference_available(), reason="reference not mounted")
+def test_sequence_dataset_mirror_matches_reference_class(tmp_path):
+    """vame_b200.dataloader.SEQUENCE_DATASET vs the reference class on the same files: statistics files, length, item
+    arithmetic (same numpy RNG state -> same window), and the plain-DataLoader fallback of the Data shim on a CPU box."""
+    import os
+    from oracle.ref_shim import load_reference
+    load_reference()
+    ref_dl = sys.modules["vame.model.dataloader"]
+    from vame_b200 import dataloader as dl
+    rng = np.random.default_rng(3)
+    X = np.cumsum(rng.standard_normal((5000, 8)), axis=0)            # (N, F): both classes transpose it (dataloader.py:22-23)
+    da, db = str(tmp_path / "a") + os.sep, str(tmp_path / "b") + os.sep
+    os.makedirs(da), os.makedirs(db)
+    for d in (da, db):
+        np.save(d + "train_seq.npy", X)
+    ref = ref_dl.SEQUENCE_DATASET(da, data="train_seq.npy", train=True, temporal_window=40)
+    ours = dl.SEQUENCE_DATASET(db, data="train_seq.npy", train=True, temporal_window=40)
+    assert len(ref) == len(ours) == 5000
+    assert np.load(da + "seq_mean.npy") == np.load(db + "seq_mean.npy") and np.load(da + "seq_std.npy") == np.load(db + "seq_std.npy")
+    np.random.seed(11)
+    a = ref[0]
+    np.random.seed(11)
+    b = ours[0]
+    assert a.dtype == b.dtype == torch.float64 and torch.equal(a, b)
+    if not torch.cuda.is_available():
+        loader = dl.Data.DataLoader(ours, batch_size=16, shuffle=True, drop_last=True)
+        assert isinstance(loader, torch.utils.data.DataLoader) and tuple(next(iter(loader)).shape) == (16, 8, 40)

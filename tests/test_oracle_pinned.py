@@ -139,6 +139,29 @@ def test_embed_video1_subsample(golden_dir):
     assert np.abs(lat[::40] - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+def test_port_option_branches_match_reference(golden_dir):
+    """softplus, 'mean' MSE reductions, kmeans_loss < zdims and three different hidden sizes: the oracle port vs the step the
+    reference's own objects computed (oracle/gen_golden.py:gen_step_opts)."""
+    g = _load(golden_dir, "step_opts.npz")
+    B, T, F, Z, S, H1, HR, HP, K = (int(v) for v in g["cfg"])
+    torch.manual_seed(19)
+    port = vo.RefPort(2 * T, Z, F, True, S, hidden=H1, softplus=True, hidden_rec=HR, hidden_pred=HP)
+    for k, p in port.named_parameters():                         # same seed, same construction order -> same init
+        np.testing.assert_array_equal(p.detach().numpy(), g["w/" + k])
+    x, xf, eps = (torch.from_numpy(g[k]) for k in ("x", "fut", "eps"))
+    hp = dict(beta=1.0, kl_weight=float(g["hp_kl_weight"]), kmeans_loss=K, kmeans_lambda=float(g["hp_lambda"]), bsize=B,
+              mse_red="mean", mse_pred="mean")
+    terms, grads, aux = vo.train_step(port, x, xf, eps, hp)
+    for k in ("rec", "fut", "kl", "kmeans", "total"):
+        assert abs(terms[k] - float(g["loss_" + k])) <= 2e-6 * max(1.0, abs(float(g["loss_" + k]))), k
+    for k in ("pred", "future", "z", "mu", "logvar"):
+        np.testing.assert_allclose(aux[k].numpy(), g[k], rtol=1e-5, atol=1e-6)
+    assert float(aux["logvar"].min()) >= 0.0                     # softplus
+    for k, gr in grads.items():
+        ref = g["grad/" + k]
+        assert np.abs(gr.numpy() - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
+
+
 @pytest.mark.reference
 @pytest.mark.skipif(not reference_available(), reason="reference not mounted")
 def test_port_vs_live_reference_forward():

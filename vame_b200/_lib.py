@@ -52,6 +52,8 @@ SIGNATURES = {
                                     c_size_t, c_void_p]),
     "vame_decoder_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vame_cluster_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "vame_sample_windows": (c_int, [c_void_p, c_long, c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_int, c_void_p,
+                                    ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vame_kmeans_workspace_bytes": (c_size_t, [c_long, c_int, c_int]),
     "vame_kmeans_lloyd": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
@@ -80,7 +82,7 @@ def lib():
             fn.argtypes = args
         _lib = L
         # runtime switches (debugging / A-B measurements): VAME_B200_PDL, VAME_B200_STREAMS, VAME_B200_PERSISTENT = 0 | 1
-        for opt in ("pdl", "streams", "persistent", "flags", "warps16", "slice16", "m64", "rw", "rw2", "rw_priv", "rw_sw", "rw_waves", "rw_exp"):
+        for opt in ("pdl", "streams", "persistent", "flags", "warps16", "slice16", "m64", "rw", "rw2", "rw_priv", "rw_sw", "rw_waves", "rw_exp", "rw_ng"):
             v = os.environ.get("VAME_B200_" + opt.upper())
             if v is not None:
                 L.vame_set_option(opt.encode(), int(v))

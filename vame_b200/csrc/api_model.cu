@@ -63,6 +63,7 @@ struct Ws {
   float* dhidden;    // feature-major [4H][B_pad]
   float* dx1;        // feature-major [2H][T*B_pad]
   double* acc;       // [8]
+  double* prior_state;   // [CP_STATE_DOUBLES] eigenvector basis of the previous k-means-prior call (training workspaces only)
   size_t bytes;
 };
 
@@ -171,6 +172,7 @@ static Ws carve_ws(const vame_dims& d, int B, bool training, void* base) {
     w.dx1 = A.f32((size_t)rows * 2 * H);
   }
   w.acc = (double*)A.raw(8 * sizeof(double));
+  w.prior_state = training ? (double*)A.raw((size_t)CP_STATE_DOUBLES * sizeof(double)) : nullptr;
   w.bytes = (A.off + 1023) & ~(size_t)1023;
   return w;
 }
@@ -849,7 +851,7 @@ int vame_forward(const vame_dims* d, int batch, const float* params, const void*
       cudaStream_t sp = side().s[2];
       edge(st, sp);
       launch_cluster_prior(w.z, batch, Z, A.cfg.kmeans_loss, A.cfg.kmeans_lambda, A.cfg.bsize > 0 ? A.cfg.bsize : (float)batch,
-                           A.cfg.kl_weight, A.hyper, w.dz_km, w.acc, sp);
+                           A.cfg.kl_weight, A.hyper, w.dz_km, w.acc, sp, w.prior_state);
       A.inflight = true;
     }
   }
@@ -890,7 +892,7 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
   if (AP.inflight && training && g_opt_streams) AP.inflight = false;       // already running since the forward pass (vame_arm_prior)
   else
     launch_cluster_prior(w.z, batch, Z, cfg->kmeans_loss, cfg->kmeans_lambda, cfg->bsize, cfg->kl_weight, hyper,
-                         training ? w.dz_km : nullptr, w.acc, sA);
+                         training ? w.dz_km : nullptr, w.acc, sA, training ? w.prior_state : nullptr);
   const float* rec_target = w.x_tb;
   if (target) {                              // clean target of a noisy forward input
     launch_bt_to_tb(target, batch, T, F, t_bs, t_ts, Bp, w.dec[0].target_tb, st);

@@ -227,10 +227,18 @@ __global__ void mse_p16_kernel(const float* __restrict__ pred, long ldp, const f
   }
 }
 
+// state (optional, CP_STATE_DOUBLES doubles that persist between calls, e.g. in the training workspace): the eigenvector basis of
+// the previous call.  Consecutive training batches are samples of the same latent distribution, so their Gram matrices are
+// close and V_prev^T G V_prev is already almost diagonal: the Jacobi iteration then needs 2-3 sweeps instead of 8-9 (~35 us
+// each at Z = 30).  The result does not depend on the starting basis (same off-diagonal stopping criterion); the basis is
+// re-started from the identity every 256 calls so that rounding drift of V's orthonormality cannot accumulate, and whenever
+// the state does not carry this kernel's tag for the same Z (first call, other model).
+constexpr unsigned long long CP_STATE_TAG = 0x5641'4D45'5052'494FULL;     // "VAMEPRIO"
 __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __restrict__ z, int B, int Z, int kloss,
                                                                 double lmbda, double bsize, double gcoef,
                                                                 const float* __restrict__ hyper,
-                                                                float* __restrict__ dz, double* __restrict__ acc) {
+                                                                float* __restrict__ dz, double* __restrict__ acc,
+                                                                double* __restrict__ state) {
   if (hyper) {
     lmbda = (double)hyper[HY_KMLAMBDA];
     gcoef = (double)hyper[HY_KLW];
@@ -282,6 +290,35 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
     if (e < Z * Z) A[e / Z][e % Z] = g[s] / bsize;
   }
   __syncthreads();
+  // ---- warm start: A <- V0^T A V0, V <- V0 with the previous call's eigenvector basis
+  unsigned long long calls = 0;
+  if (state) {
+    const unsigned long long* su = reinterpret_cast<const unsigned long long*>(state);
+    const bool valid = su[0] == CP_STATE_TAG && su[1] == (unsigned long long)Z;
+    calls = valid ? su[2] : 0;
+    if (valid && (calls & 255ull) != 0) {                      // (block-uniform: every thread reads the same words)
+      const double* v0 = state + 4;
+      for (int e = tid; e < Z * Z; e += nt) V[e / Z][e % Z] = v0[e];
+      __syncthreads();
+      for (int e = tid; e < Z * Z; e += nt) {                   // A2 = A V0
+        const int i = e / Z, j = e % Z;
+        double t = 0;
+        for (int m = 0; m < Z; ++m) t += A[i][m] * V[m][j];
+        A2[i][j] = t;
+      }
+      __syncthreads();
+      for (int e = tid; e < Z * Z; e += nt) {                   // A = V0^T A2 (symmetrised: the two triangles differ by rounding)
+        const int i = e / Z, j = e % Z;
+        if (i <= j) {
+          double t = 0;
+          for (int m = 0; m < Z; ++m) t += V[m][i] * A2[m][j];
+          A[i][j] = t;
+          A[j][i] = t;
+        }
+      }
+      __syncthreads();
+    }
+  }
 
   // ---- parallel cyclic Jacobi (round-robin tournament ordering: n-1 rounds of n/2 disjoint rotations).
   // Each round is two phases: (A) the n/2 rotations are computed from the current matrix, (B) every element of
@@ -344,6 +381,13 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
     }
   }
   A = Acur; V = Vcur;
+  if (state) {                                                   // this call's basis is the next call's starting point
+    for (int e = tid; e < Z * Z; e += nt) state[4 + e] = V[e / Z][e % Z];
+    if (tid == 0) {
+      unsigned long long* su = reinterpret_cast<unsigned long long*>(state);
+      su[0] = CP_STATE_TAG; su[1] = (unsigned long long)Z; su[2] = calls + 1;
+    }
+  }
   // ---- eigenvalues, top-k selection (rank bound min(k, B, Z)), loss
   if (tid < n) {
     const double e = (tid < Z) ? A[tid][tid] : -1e300;
@@ -618,14 +662,14 @@ void launch_mse(const float* pred, long ldp, const float* target, int rows, int 
   mse_kernel<<<grid_for((long)rows * F, 256, 296), 256, 0, st>>>(pred, ldp, target, rows, B, B_pad, F, gscale, dpred, acc, slot);   // grid-stride
 }
 void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
-                          float* dz, double* acc, cudaStream_t st) {
+                          float* dz, double* acc, cudaStream_t st, double* state) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(cluster_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
     attr = true;
   }
   count_launch();
-  cluster_prior_kernel<<<1, 1024, CP_SMEM, st>>>(z, B, Z, kloss, lmbda, bsize, gcoef, hyper, dz, acc);
+  cluster_prior_kernel<<<1, 1024, CP_SMEM, st>>>(z, B, Z, kloss, lmbda, bsize, gcoef, hyper, dz, acc, state);
 }
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st) {
   int ysplit = (int)min((long)256, (rows + 31) / 32);

@@ -34,8 +34,10 @@ void launch_mse_p16(const float* pred, long ldp, const float* target, int rows, 
 void launch_mse(const float* pred, long ldp, const float* target, int rows, int B, int B_pad, int F, float gscale, float* dpred,
                 double* acc, int slot, cudaStream_t st);
 // hyper != nullptr: lambda = hyper[HY_KMLAMBDA], gradient coefficient = hyper[HY_KLW]; else the scalar arguments
+// state: optional CP_STATE_DOUBLES doubles that persist between calls (warm start of the eigen-solver, see simt.cu)
+constexpr int CP_STATE_DOUBLES = 4 + 64 * 64;
 void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
-                          float* dz, double* acc, cudaStream_t st);
+                          float* dz, double* acc, cudaStream_t st, double* state = nullptr);
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st);
 void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out, cudaStream_t st);
 void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st);

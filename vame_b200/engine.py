@@ -166,7 +166,9 @@ class Engine:
             nb = self.lib.vame_workspace_bytes(ctypes.byref(self.dims), int(batch), int(training))
             if nb == 0:
                 raise L.VameB200Error("vame_workspace_bytes failed: %s" % self.lib.vame_last_error().decode())
-            ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+            # zero-filled: the library keeps small pieces of state in a training workspace between calls (the eigenvector basis
+            # that warm-starts the k-means-prior solver) and recognises "no state yet" deterministically
+            ws = torch.zeros(nb, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
 
@@ -364,16 +366,21 @@ class TrainStep:
     The two compute phases are captured once as CUDA graphs and replayed (the launch-bound recurrence is ~200 dependent
     kernels); hyper-parameters that change between steps (lr, kl_weight, ...) live in device memory (Engine.hyper)."""
 
-    def __init__(self, eng, batch, cfg, world=1, use_graph=True, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, eng, batch, cfg, world=1, use_graph=True, betas=(0.9, 0.999), eps=1e-8, sampler=None):
         self.eng, self.B, self.cfg, self.world = eng, int(batch), cfg, int(world)
+        # optional vame_b200.dataloader.DeviceWindowSampler: its vame_sample_windows launch becomes the first node of the step
+        # (window starts, z-score, data / future split and the reparameterisation noise are produced on the device)
+        self.sampler = sampler
         d = eng.dims
         dev = eng.device
         self.x = torch.zeros(batch, d.time_window, d.num_features, device=dev)
         self.fut = torch.zeros(batch, max(d.future_steps, 1), d.num_features, device=dev) if d.future_decoder else None
         self.eps = torch.zeros(batch, d.zdims, device=dev)
         self.losses = torch.zeros(8, device=dev)
+        self.acc = torch.zeros(8, dtype=torch.float64, device=dev)   # epoch sums of the loss terms (accumulated inside the step)
         self.betas, self.adam_eps = betas, eps
         self.graphs = None
+        self.nccl_in_graph = False
         self.use_graph = use_graph
         self._stage, self._staged, self._k_load = None, [], 0
         self.defer_repack = os.environ.get("VAME_B200_DEFER_REPACK", "0") != "0"
@@ -384,6 +391,8 @@ class TrainStep:
 
     def _phase1(self):
         e = self.eng
+        if self.sampler is not None:
+            self.sampler.fill(self.x, self.fut if self.cfg.with_future else None, self.eps)
         if self.defer_repack:
             # weights updated by the previous step's optimizer kernel: re-pack what the first sweep needs now, the rest beside it
             L.check(e.lib.vame_pack_weights_deferred(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), L.cur_stream()),
@@ -412,6 +421,7 @@ class TrainStep:
             # only the weight formats a step of THIS batch size reads; any other consumer re-packs everything (mark_dirty in run())
             L.check(e.lib.vame_pack_weights_train(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), self.B, L.cur_stream()),
                     "vame_pack_weights_train")
+        self.acc.add_(self.losses)           # device-side epoch accumulation: no host work per batch
 
     def capture(self):
         """Warm up eagerly (also refreshes the packed weights), then capture both phases."""
@@ -427,6 +437,9 @@ class TrainStep:
             with torch.cuda.stream(s):
                 for _ in range(2):
                     self._phase1()
+                    if self.world > 1:               # warms up the communicator on this stream before any capture
+                        import torch.distributed as dist
+                        dist.all_reduce(e.grad, op=dist.ReduceOp.SUM)
                     self._phase2()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
@@ -438,18 +451,39 @@ class TrainStep:
                     self._phase2()
                 self.graphs = (g1, None)
             else:
-                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    self._phase1()
-                with torch.cuda.graph(g2):
-                    self._phase2()
-                self.graphs = (g1, g2)
+                # N > 1: the NCCL allreduce is captured INSIDE the graph (one launch per step, no host round trip between
+                # backward, allreduce and optimizer); if this NCCL / torch build cannot capture collectives, fall back to two
+                # graphs around an eager allreduce
+                import torch.distributed as dist
+                self.graphs = None
+                if os.environ.get("VAME_B200_NCCL_IN_GRAPH", "1") != "0":
+                    try:
+                        g1 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g1):
+                            self._phase1()
+                            dist.all_reduce(e.grad, op=dist.ReduceOp.SUM)
+                            self._phase2()
+                        self.graphs = (g1, None)
+                        self.nccl_in_graph = True
+                    except Exception as ex:
+                        self.capture_error = "nccl-in-graph: " + repr(ex)
+                        torch.cuda.synchronize()
+                if self.graphs is None:
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        self._phase1()
+                    with torch.cuda.graph(g2):
+                        self._phase2()
+                    self.graphs = (g1, g2)
         except Exception as ex:      # capture is an optimisation; eager launches are the same kernels
             self.graphs = None
             self.capture_error = repr(ex)
             torch.cuda.synchronize()
         # undo the warm-up updates
         e.flat.copy_(flat)
+        self.acc.zero_()
+        if self.sampler is not None:
+            self.sampler.counter.zero_()
         for k, v in state.items():
             e.opt_state[k].copy_(v)
         e.pack_weights()
@@ -509,7 +543,7 @@ class TrainStep:
             self.graphs[0].replay()
         else:
             self._phase1()
-        if self.world > 1:
+        if self.world > 1 and not self.nccl_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.eng.grad, op=dist.ReduceOp.SUM)
         if self.graphs is not None:

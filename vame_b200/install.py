@@ -1,7 +1,8 @@
 """Drop the B200 hot path in behind an UNMODIFIED VAME installation.
 
 ``install()`` rebinds, in the already-imported reference modules, exactly the names on the hot path
-(SURVEY.md §8b): the five model classes, the four loss functions, ``train`` / ``test`` and
+(SURVEY.md §8b): the five model classes, the four loss functions, ``train`` / ``test``, the dataset / loader pair that
+``train_model`` builds (``SEQUENCE_DATASET``, ``Data.DataLoader`` -> on-device window sampler) and
 ``load_model`` / ``embedd_latent_vectors``, the k-means parameterization and the arithmetic of ``create_trainset``
 (``traindata_fixed`` / ``traindata_aligned``).  Everything else (config handling, csv / alignment preprocessing, train_model's epoch
 loop, checkpoint files, clustering, plotting) keeps running the reference's own code, so existing projects and
@@ -44,6 +45,12 @@ def install(verbose=False):
             setattr(rv, n, getattr(_rv, n))
             done.append((rv.__name__, n))
         rv.use_gpu = True
+        # the loader seam (rnn_vae.py:23,326-330): train_model builds SEQUENCE_DATASET(...) and Data.DataLoader(...) from these
+        # module globals; ours keep the series in HBM and sample every batch with one kernel inside the captured step
+        from . import dataloader as _dl
+        rv.SEQUENCE_DATASET = _dl.SEQUENCE_DATASET
+        rv.Data = _dl.Data
+        done += [(rv.__name__, "SEQUENCE_DATASET"), (rv.__name__, "Data.DataLoader")]
     ps = sys.modules.get("vame.analysis.pose_segmentation")
     if ps is not None:
         for n in ("load_model", "embedd_latent_vectors", "individual_parameterization"):

@@ -96,20 +96,53 @@ def _engine_of(model):
     return model.engine
 
 
-def _train_step(model, eng, batch, cfg, world, betas, adam_eps):
-    """Cached engine.TrainStep (captured CUDA graphs) for this batch size / loss configuration; hyper-parameters that change
-    between epochs (lr, kl_weight, beta, lambda) are read from device memory, so the graphs stay valid."""
+def _train_step(model, eng, batch, cfg, world, betas, adam_eps, sampler=None):
+    """Cached engine.TrainStep (captured CUDA graphs) for this batch size / loss configuration [/ device sampler];
+    hyper-parameters that change between epochs (lr, kl_weight, beta, lambda) are read from device memory, so the graphs stay
+    valid."""
     from .engine import TrainStep
     key = (int(batch), cfg.mse_red_mean, cfg.mse_pred_mean, cfg.kmeans_loss, float(cfg.bsize), cfg.with_future, int(world),
-           tuple(betas), float(adam_eps))
+           tuple(betas), float(adam_eps), id(sampler) if sampler is not None else None)
     cache = model.__dict__.setdefault("_b200_steps", {})
     ts = cache.get(key)
     if ts is None:
         import copy
-        ts = TrainStep(eng, batch, copy.copy(cfg), world=world, betas=betas, eps=adam_eps)
+        if world > 1:
+            _broadcast_replicas(eng)
+        ts = TrainStep(eng, batch, copy.copy(cfg), world=world, betas=betas, eps=adam_eps, sampler=sampler)
         ts.capture()
         cache[key] = ts
     return ts
+
+
+def _broadcast_replicas(eng):
+    """Data-parallel replicas must start identical: rank 0's parameters and optimizer state are broadcast once, when the first
+    train step of a world > 1 job is built (different seeds or a pretrained_model loaded on one rank only would otherwise
+    diverge silently - only gradients are summed)."""
+    eng.init_optimizer()
+    dist.broadcast(eng.flat, src=0)
+    for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq", "step"):
+        dist.broadcast(eng.opt_state[k], src=0)
+    eng.mark_dirty()
+
+
+def replica_checksum(eng):
+    """(sum, sum of squares) of the flat parameters in float64: equal on every rank of a consistent data-parallel job."""
+    f = eng.flat.double()
+    return torch.stack([f.sum(), (f * f).sum()])
+
+
+def assert_replicas_consistent(eng, tol=0.0):
+    """Raises if the ranks' parameters differ (cheap: two scalars per rank)."""
+    if _world() <= 1:
+        return
+    c = replica_checksum(eng)
+    lo, hi = c.clone(), c.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if bool(((hi - lo).abs() > tol * hi.abs().clamp_min(1e-30)).any()):
+        raise VameB200Error("data-parallel replicas have diverged: parameter checksums differ across ranks (%s vs %s)"
+                            % (lo.tolist(), hi.tolist()))
 
 
 def _to_device(data_item, seq_len_half, future_steps, device):
@@ -137,7 +170,17 @@ def train(train_loader, epoch, model, optimizer, anneal_function, BETA, kl_start
     idx = -1
     loss_last = None
     eng.set_hyper(lr=lr, kl_weight=kl_weight, beta=BETA, kmeans_lambda=klmbda)
-    for idx, data_item in enumerate(train_loader):
+    from .dataloader import DeviceWindowSampler
+    fused_sampler = isinstance(train_loader, DeviceWindowSampler) and not (noise == True)   # noqa: E712
+    if fused_sampler:
+        # the sampler's launch is the first node of the captured step: one CUDA-graph replay per batch, no host work per window
+        ts = _train_step(model, eng, train_loader.batch_size, cfg, world, betas, adam_eps, sampler=train_loader)
+        ts.acc.zero_()
+        n_batches = len(train_loader)
+        for idx in range(n_batches):
+            loss_last = ts.run()
+        acc = ts.acc
+    for idx, data_item in (enumerate(train_loader) if not fused_sampler else ()):
         data, fut = _to_device(data_item, seq_len_half, future_steps, eng.device)
         eps = torch.randn(data.shape[0], eng.dims.zdims, device=eng.device)
         if noise == True:   # noqa: E712
@@ -159,7 +202,15 @@ def train(train_loader, epoch, model, optimizer, anneal_function, BETA, kl_start
     model.bind_flat_grads()
     a = acc.cpu().tolist()                       # the only device->host sync of the epoch
     rec, fl, kl, km, total = a[0], a[1], a[2], a[3], a[4]
-    scheduler.step(loss_last[4])                 # rnn_vae.py:155: the scheduler sees the LAST batch's loss
+    sched_loss = loss_last[4]                    # rnn_vae.py:155: the scheduler sees the LAST batch's loss
+    if world > 1:
+        # every rank must take the same lr decision (ReduceLROnPlateau): feed the rank-mean of the last-batch loss, and make sure
+        # the replicas still agree (a silent divergence would otherwise only show up as a bad model)
+        sched_loss = sched_loss.clone()
+        dist.all_reduce(sched_loss, op=dist.ReduceOp.SUM)
+        sched_loss /= world
+        assert_replicas_consistent(eng)
+    scheduler.step(sched_loss)
     div = idx if idx > 0 else float("nan")       # rnn_vae.py:157-164 divide by the last batch index (reference quirk)
     if future_decoder:
         print('Train loss: {:.3f}, MSE-Loss: {:.3f}, MSE-Future-Loss {:.3f}, KL-Loss: {:.3f}, Kmeans-Loss: {:.3f}, weight: {:.2f}'.format(
