@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -83,8 +83,9 @@ class ClockSampler:
         window = "all"
         lines = [ln for _, ln in self.lines]
         if t0 is not None and t1 is not None:
-            inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.05]
-            window = "timed region" if inside else "warm-up + timed region (same load)"
+            # the timed region plus the 0.15 s of identical load right before it (see main(): 150 extra warm-up steps)
+            inside = [ln for ts, ln in self.lines if t0 - 0.15 <= ts <= t1 + 0.05]
+            window = "timed region + the 0.15 s of identical load before it" if inside else "warm-up + timed region (same load)"
             lines = inside or lines
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -326,14 +327,11 @@ def main():
     for i in range(W):
         step(i)
     barrier()
-    # keep the GPU under the same load until the sampler has delivered a few samples of it (25 ms period), so that the clocks
-    # line always holds samples taken under load even when the timed region itself is shorter than one sampling period
-    n_lines = len(sampler.lines)
-    t_lim = time.time() + 1.0
-    while len(sampler.lines) < n_lines + 4 and time.time() < t_lim:
-        for i in range(10):
-            step(i)
-        torch.cuda.synchronize()
+    # keep the GPU under the same load for a few sampling periods (10 ms each) before the timed region, so that the clocks line
+    # always holds samples taken under load even when the timed region itself is shorter than one period.  A FIXED number of
+    # steps: with N > 1 every step contains collectives, so all ranks must run the same count.
+    for i in range(150):
+        step(i)
     barrier()
     launches0 = lib.vame_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -121,6 +121,16 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
                   const float* dz, const float* dmu, const float* dlogvar, float* grads, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* Data-parallel overlap of the gradient allreduce with the tail of the backward pass (no counterpart in the reference, which is
+ * single-device).  Every gradient except encoder layer 0's - the flat range [vame_grad_bucket_split(d), total) - is final ~200 us
+ * before vame_backward ends.  With vame_grad_overlap(1), vame_backward records an external CUDA event at that point (an
+ * event-record node when the call is captured into a CUDA graph); vame_wait_grads_ready(stream) makes `stream` wait for the
+ * event of the most recently enqueued vame_backward, so the caller can all-reduce that range on a communication stream while
+ * the last BPTT sweep still runs, and only the small encoder-layer-0 range [0, split) after the call. */
+int vame_grad_overlap(int enable);
+long vame_grad_bucket_split(const vame_dims* d);
+int vame_wait_grads_ready(void* stream);
+
 /* torch.optim.Adam(amsgrad=True) (rnn_vae.py:332,143) over the flat buffers.  lr is read from hyper[0] when hyper is
  * not NULL.  step_dev: device int32 step counter (incremented here).  scratch: device float[2].
  * grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). */

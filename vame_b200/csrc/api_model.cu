@@ -931,6 +931,42 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
   return check_launch("vame_loss");
 }
 
+// ---- gradient-bucket hand-over for the data-parallel step -------------------------------------------------------------------
+// Every gradient except encoder layer 0's is final well before vame_backward ends (the layer-0 BPTT sweep and its weight-gradient
+// GEMMs are the last ~200 us).  With the overlap enabled, vame_backward records an EXTERNAL event (an event-record node when the
+// call is captured into a CUDA graph) at that point; the host makes its communication stream wait for it and all-reduces the
+// first bucket while the last sweep runs.
+struct GradOverlap {
+  bool on = false;
+  cudaEvent_t ev = nullptr;
+};
+static GradOverlap& grad_overlap() {
+  static GradOverlap G;
+  return G;
+}
+int vame_grad_overlap(int enable) {
+  GradOverlap& G = grad_overlap();
+  if (enable && !G.ev) {
+    if (cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming) != cudaSuccess) return fail("vame_grad_overlap: cudaEventCreate failed");
+  }
+  G.on = enable != 0;
+  return 0;
+}
+long vame_grad_bucket_split(const vame_dims* d) {
+  if (!d || check_dims(d)) return -1;
+  return param_layout(*d).e1.wih[0];     // [0, split): encoder layer 0 (final last); [split, total): everything else
+}
+int vame_wait_grads_ready(void* stream) {
+  GradOverlap& G = grad_overlap();
+  VB_REQUIRE(G.ev, "vame_wait_grads_ready: no vame_backward has run with vame_grad_overlap(1) yet");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing((cudaStream_t)stream, &cap);
+  if (cudaStreamWaitEvent((cudaStream_t)stream, G.ev, cap == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault) !=
+      cudaSuccess)
+    return fail("vame_wait_grads_ready: cudaStreamWaitEvent failed");
+  return 0;
+}
+
 int vame_backward(const vame_dims* d, int batch, const float* params, const void* packed, int use_loss_grads, const vame_loss_cfg* cfg,
                   const float* hyper, const float* dpred, const float* dfuture, const float* dz_ext, const float* dmu_ext,
                   const float* dlv_ext, float* grads, void* ws, size_t ws_bytes, void* stream) {
@@ -1104,6 +1140,16 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
           .run(3 * H, H, G + L.e1.wih[dd] + (long)e * H, 2 * H, nullptr, 1, splits_for(3 * H, H, nk), sdir[dd]);
   }
   mark(sB, "side:L1 weight grads done");
+  if (grad_overlap().on) {
+    // every gradient outside encoder layer 0 has been enqueued: decoder(s), Lambda and layer-1 weight gradients live on sB / sC /
+    // sA; once they are complete the first bucket [vame_grad_bucket_split, total) may be all-reduced
+    edge(sC, sB);
+    if (used_sA) edge(sA, sB);
+    // (the external flag - an event-record NODE that code outside the graph can wait for - is only legal during stream capture)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(sB, &cap);
+    cudaEventRecordWithFlags(grad_overlap().ev, sB, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+  }
   // ---- encoder layer 0
   mark(st, "bwd:dx1 gemm");
   gru_sweep_bwd(W.e0, w.e0, w.tiles, w.dx1, w.dx1 + (size_t)H * rows, rows, w.dhidden, w.dhidden + (size_t)H * Bp, Bp, true, st,

@@ -381,6 +381,16 @@ class TrainStep:
         self.betas, self.adam_eps = betas, eps
         self.graphs = None
         self.nccl_in_graph = False
+        # N > 1: the allreduce of everything but encoder layer 0's gradients runs on a communication stream under the last BPTT
+        # sweep (vame_grad_overlap); VAME_B200_GRAD_OVERLAP=0 falls back to one allreduce of the whole buffer after the backward
+        # Measured at N = 2 (profiles/r2_dp_n2.md): +3.2 % at 512 windows per GPU, neutral to slightly negative at 256 (the NCCL
+        # CTAs compete with the 128-SM sweep for the 20 SMs the weight-gradient GEMMs run on) -> on by default from 384 up
+        ov = os.environ.get("VAME_B200_GRAD_OVERLAP")
+        self.overlap = self.world > 1 and (ov != "0" if ov is not None else self.B >= 384)
+        self._comm_stream = None
+        if self.overlap:
+            self.split = int(eng.lib.vame_grad_bucket_split(ctypes.byref(eng.dims)))
+            self._comm_stream = torch.cuda.Stream(device=dev)
         self.use_graph = use_graph
         self._stage, self._staged, self._k_load = None, [], 0
         self.defer_repack = os.environ.get("VAME_B200_DEFER_REPACK", "0") != "0"
@@ -410,8 +420,30 @@ class TrainStep:
             if self.early_prior:
                 e.lib.vame_arm_prior(None, None)
         e.loss(self.cfg, self.fut if self.cfg.with_future else None, want_grads=True, use_hyper=True, out=self.losses)
-        e.backward(self.cfg, use_hyper=True)
+        if self.overlap:
+            L.check(e.lib.vame_grad_overlap(1), "vame_grad_overlap")
+        try:
+            e.backward(self.cfg, use_hyper=True)
+        finally:
+            if self.overlap:
+                e.lib.vame_grad_overlap(0)
         self.cfg.defer_prior_join = 0
+
+    def _allreduce(self):
+        """Gradient exchange between the two phases (world > 1)."""
+        import torch.distributed as dist
+        g = self.eng.grad
+        if not self.overlap:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            return
+        cur = torch.cuda.current_stream()
+        cs = self._comm_stream
+        with torch.cuda.stream(cs):
+            # bucket A = everything but encoder layer 0: final when the event inside the (already enqueued) backward fires
+            L.check(self.eng.lib.vame_wait_grads_ready(ctypes.c_void_p(cs.cuda_stream)), "vame_wait_grads_ready")
+            dist.all_reduce(g[self.split:], op=dist.ReduceOp.SUM)
+        dist.all_reduce(g[:self.split], op=dist.ReduceOp.SUM)      # bucket B: after the backward (stream order)
+        cur.wait_stream(cs)
 
     def _phase2(self):
         # with defer_repack the packed copies are refreshed at the start of the next step (and by _ensure_packed for any other caller)
@@ -437,9 +469,8 @@ class TrainStep:
             with torch.cuda.stream(s):
                 for _ in range(2):
                     self._phase1()
-                    if self.world > 1:               # warms up the communicator on this stream before any capture
-                        import torch.distributed as dist
-                        dist.all_reduce(e.grad, op=dist.ReduceOp.SUM)
+                    if self.world > 1:               # warms up the communicator before any capture
+                        self._allreduce()
                     self._phase2()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
@@ -456,7 +487,9 @@ class TrainStep:
                 # graphs around an eager allreduce
                 import torch.distributed as dist
                 self.graphs = None
-                if os.environ.get("VAME_B200_NCCL_IN_GRAPH", "1") != "0":
+                # (opt-in: measured no faster than two graphs at N = 2, and torch's destroy_process_group() then hangs at exit
+                #  waiting for the captured collectives - profiles/r2_dp_n2.md)
+                if os.environ.get("VAME_B200_NCCL_IN_GRAPH", "0") != "0":
                     try:
                         g1 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g1):
@@ -544,8 +577,7 @@ class TrainStep:
         else:
             self._phase1()
         if self.world > 1 and not self.nccl_in_graph:
-            import torch.distributed as dist
-            dist.all_reduce(self.eng.grad, op=dist.ReduceOp.SUM)
+            self._allreduce()
         if self.graphs is not None:
             if self.graphs[1] is not None:
                 self.graphs[1].replay()
