@@ -85,7 +85,7 @@ def lib():
             fn.argtypes = args
         _lib = L
         # runtime switches (debugging / A-B measurements): VAME_B200_PDL, VAME_B200_STREAMS, VAME_B200_PERSISTENT = 0 | 1
-        for opt in ("pdl", "streams", "persistent", "flags", "warps16", "slice16", "m64", "rw", "rw2", "rw_priv", "rw_sw", "rw_waves", "rw_exp", "rw_ng"):
+        for opt in ("pdl", "streams", "persistent", "flags", "warps16", "slice16", "m64", "rw", "rw2", "rw_priv", "rw_sw", "rw_waves", "rw_exp", "rw_ng", "rows"):
             v = os.environ.get("VAME_B200_" + opt.upper())
             if v is not None:
                 L.vame_set_option(opt.encode(), int(v))

@@ -297,6 +297,10 @@ struct JobQ {
     PackJob j{}; j.src = w; j.out = out; j.kind = 4 + mode; j.R = H;
     push(j);
   }
+  void whh_rows(const float* w, int H, void* out) {
+    PackJob j{}; j.src = w; j.out = out; j.kind = 6; j.R = H;
+    push(j);
+  }
   void bias(const float* b_ih, const float* b_hh, int H, float* out) {
     PackJob j{}; j.src = b_ih; j.src2 = b_hh; j.out = out; j.kind = 3; j.R = H;
     push(j);
@@ -312,6 +316,7 @@ static void pack_gru_fwd(const float* P, const GruOff& o, const GruPacked& W, Jo
   for (int d = 0; d < 2; ++d) {
     if (slices || !W.whh_rw[d]) q.whh(P + o.whh[d], H, 0, W.whh_p[d]);
     if (W.whh_rw[d]) q.whh_rw(P + o.whh[d], H, 0, W.whh_rw[d]);
+    if (slices && W.whh_rows[d]) q.whh_rows(P + o.whh[d], H, W.whh_rows[d]);     // large-batch inference only: not in the train-loop re-pack
     q.bias(P + o.bih[d], P + o.bhh[d], H, W.bias_gi + (size_t)d * 3 * H);
   }
   // both directions' W_ih are adjacent in the flat buffer -> one [6H, In] matrix; K split in wih_nseg column blocks
@@ -431,7 +436,9 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
   zero_p16_padding(L, tiles, true, st);
   // resident-weight cluster kernel (gru_rw.cu): needs 8 consecutive batch rows of gi per vector load
   const bool rw = (g_opt_rw & 1) && W.whh_rw[0] && rw_applicable(H, tiles) && L.gi_bs == 1 && (L.gi_ts % 4) == 0;
-  if (rw || (g_opt_persistent & 1)) {           // one cluster kernel for the whole sweep
+  // large inference batches (embedding): row-resident kernel, 128 rows per persistent CTA (gru_rows.cu)
+  const bool rows = !rw && !save && W.whh_rows[0] && rows_fwd_applicable(H, tiles);
+  if (rw || rows || (g_opt_persistent & 1)) {   // one kernel for the whole sweep
     GruSeqFwdArgs a{};
     a.ndir = 2; a.H = H; a.tiles = tiles; a.steps = L.steps;
     const long Bp = (long)tiles * 128;
@@ -439,6 +446,7 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
       GruSeqDirFwd& D = a.d[d];
       D.w_p = W.whh_p[d]; D.b_hn = d == 0 ? b_hn0 : b_hn1;
       D.w_rw = W.whh_rw[d];
+      D.w_rows = W.whh_rows[d];
       D.gi = L.gi + (size_t)d * 3 * H * L.gi_ld; D.gi_ld = L.gi_ld; D.gi_bs = L.gi_bs; D.gi_ts = L.gi_ts;
       D.h0 = L.h0[d]; D.h0_ld = Bp; D.h0_p = L.h0_p[d];
       D.out = L.out[d]; D.out_ld = (long)L.out_slots * Bp; D.out_slots = L.out_slots;
@@ -452,6 +460,7 @@ static void gru_sweep_fwd(const GruPacked& W, const float* b_hn0, const float* b
       D.hfin = L.hfin[d];
     }
     if (rw) launch_gru_rw_fwd(a, st);
+    else if (rows) launch_gru_rows_fwd(a, st);
     else launch_gru_seq_fwd(a, st);
     return;
   }

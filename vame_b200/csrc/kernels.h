@@ -34,7 +34,8 @@ void launch_pack_p16(const float* src, long ld, int transposed, int R, int K, in
 void launch_pack_p16_rowsum(const float* src, long ld, int R, int K, int R_src, void* out, float* rowsum, cudaStream_t st);
 
 // batched pack jobs (one launch): kind 0 = generic pack_p16, 1 / 2 = W_hh forward / backward slices (R = H), 3 = fused bias (R = H),
-// 4 / 5 = W_hh in the resident-weight forward / backward format of gru_rw.cu (R = H, H % 64 == 0)
+// 4 / 5 = W_hh in the resident-weight forward / backward format of gru_rw.cu (R = H, H % 64 == 0),
+// 6 = W_hh in the row-resident inference format of gru_rows.cu (R = H, H % 64 == 0)
 struct PackJob {
   const float* src; const float* src2; void* out;
   long ld;
@@ -117,6 +118,7 @@ void launch_gru_step_fwd(const GruFwdArgs& a, cudaStream_t st);
 struct GruSeqDirFwd {
   const void* w_p; const float* b_hn;
   const void* w_rw;                                     // resident-weight format (pack kind 4), used by launch_gru_rw_fwd
+  const void* w_rows;                                   // row-resident inference format (pack kind 6), used by launch_gru_rows_fwd
   const float* gi; long gi_ld, gi_bs, gi_ts;
   const float* h0; long h0_ld; const void* h0_p;       // initial state: fp32 feature-major + P16
   float* out; long out_ld; int out_slots;               // fp32 h sequence, slot offset = slot*B_pad (slots = steps or 2)
@@ -183,6 +185,10 @@ size_t rw_whh_bytes(int H);       // packed W_hh of one direction, forward forma
 size_t rw_whhT_bytes(int H);      // ... backward format
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 void launch_gru_rw_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
+// ---- gru_rows.cu: row-resident forward sweep for large inference batches (128 rows per persistent CTA, W_hh streamed from L2) ----
+extern int g_opt_rows;             // 1: inference sweeps of H = 256 layers that do not fit the rw kernels use gru_rows_fwd_kernel
+bool rows_fwd_applicable(int H, int tiles);
+void launch_gru_rows_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 unsigned int rw_timeouts();
 int rw_timeout_info(int i);        // first time-out: 0 site id, 1 parity, 2-4 blockIdx, 5 threadIdx.x
 void rw_timeouts_reset();       // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)

@@ -82,6 +82,7 @@ struct GruPacked {
   void* whhT_p[2];     // backward-step slices
   void* whh_rw[2];     // resident-weight forward / backward formats of gru_rw.cu (nullptr when H % 64 != 0)
   void* whhT_rw[2];
+  void* whh_rows[2];   // row-resident inference format of gru_rows.cu: [H/32 slices][KC][hi 96x64 | lo 96x64] (nullptr unless H == 256)
   void* wih_p[2];      // input projection B operand, K segments (encoder layer 1 has two: fwd / bwd halves of its input)
   int wih_nseg;
   void* wihT_p[2];     // per direction: [In rows, K = 3H] (for dx / dz)
@@ -109,6 +110,7 @@ inline void carve_gru_packed(Arena& A, GruPacked& g, int In, int H, int nseg) {
     } else {
       g.whh_rw[d] = g.whhT_rw[d] = nullptr;
     }
+    g.whh_rows[d] = H == 256 ? A.raw((size_t)(H / 32) * (H / KCHUNK) * p16_tile_bytes(96)) : nullptr;
   }
   g.wih_nseg = nseg;
   for (int s = 0; s < nseg; ++s) g.wih_p[s] = A.raw(p16_bytes(6 * H, In / nseg, 128));

@@ -245,6 +245,27 @@ __device__ __forceinline__ void pack_whh_rw_body(const float* __restrict__ w, in
     *reinterpret_cast<uint4*>(out + (size_t)tile * (128 * KCHUNK) + p16_in_tile(L, k8 * 8)) = plane ? lo : hi;
   }
 }
+// Row-resident inference format (gru_rows.cu): 32-unit slices, one P16 tile (RB = 96: hi plane, lo plane) per (slice c, 64-k chunk);
+// tile row p = 32 g + j <-> W_hh[g*H + 32 c + j, :] (r, z, n gate rows of the slice's units).  H % 64 == 0.
+__device__ __forceinline__ void pack_whh_rows_body(const float* __restrict__ w, int H, __nv_bfloat16* __restrict__ out, long bid, long nb) {
+  const int nkc = H / KCHUNK;
+  const long total = (long)(H / 32) * 96 * nkc * 8;
+  for (long idx = bid * (long)blockDim.x + threadIdx.x; idx < total; idx += nb * blockDim.x) {
+    const int k8g = (int)(idx % (nkc * 8));
+    const int p = (int)(idx / (nkc * 8));              // packed row
+    const int c = p / 96, g = (p % 96) / 32, j = p % 32;
+    const int srow = g * H + 32 * c + j, kbase = k8g * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = w[(long)srow * H + kbase + i];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    __nv_bfloat16* tile = out + ((size_t)c * nkc + kbase / KCHUNK) * p16_tile_elems(96);
+    const int off = p16_in_tile(p % 96, kbase % KCHUNK);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + 96 * KCHUNK + off) = lo;
+  }
+}
 __global__ void pack_whh_kernel(const float* __restrict__ w, int H, int mode, __nv_bfloat16* __restrict__ out) {
   pack_whh_body(w, H, mode, out, blockIdx.x, gridDim.x);
 }
@@ -282,6 +303,8 @@ __global__ void pack_jobs_kernel(const PackJobs jobs) {
     pack_whh_body(J.src, J.R, J.kind - 1, (__nv_bfloat16*)J.out, bid, nb);
   } else if (J.kind == 4 || J.kind == 5) {
     pack_whh_rw_body(J.src, J.R, J.kind - 4, (__nv_bfloat16*)J.out, bid, nb);
+  } else if (J.kind == 6) {
+    pack_whh_rows_body(J.src, J.R, (__nv_bfloat16*)J.out, bid, nb);
   } else {                                         // fused projection bias: out[i] = b_ih[i] + (i < 2H ? b_hh[i] : 0), R = H
     const int H = J.R;
     for (long i = bid * blockDim.x + threadIdx.x; i < 3L * H; i += nb * blockDim.x)
@@ -295,6 +318,7 @@ void launch_pack_jobs(PackJobs& jobs, cudaStream_t st) {
     PackJob& J = jobs.j[i];
     long work;
     if (J.kind == 0) work = (long)((J.R + J.RB - 1) / J.RB) * J.RB * ((J.K + KCHUNK - 1) / KCHUNK) * 8;
+    else if (J.kind == 6) work = (long)(J.R / 32) * 96 * (J.R / KCHUNK) * 8;
     else if (J.kind == 1) work = (long)(J.R / 32) * 96 * ((J.R + KCHUNK - 1) / KCHUNK) * 8;
     else if (J.kind == 2) work = (long)(J.R / 32) * ((J.R + 127) / 128) * 128 * 16;
     else if (J.kind == 4 || J.kind == 5) work = 4L * 3 * (J.R / 64) * 128 * 8;
