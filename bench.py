@@ -576,16 +576,20 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom.split(" ")[0])
+            tj = json.load(open(tpath))
+            traffic = tj.get(dom.split(" ")[0] + ("@2groups" if ng == 2 else ""), tj.get(dom.split(" ")[0]))
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s", "frac": ach / peak_burst,
                 "traffic": traffic, "peak_source": how + ", burst figure (kernel timed alone)",
                 "algorithmic_flops_per_launch": flops_launch, "issued_mma_flops_per_launch": 4 * flops_launch,
+                "issued_frac": 4 * ach / peak_burst, "algorithmic_ceiling_frac": 0.25,
                 "us_per_launch": {k: v * 1e6 for k, v in res.items()}, "row_groups_per_cluster": ng,
-                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the kernels issue 4x that in "
-                        "bf16 MMAs (hi/lo split operands), so the algorithmic ceiling is <= 1/4 of the bf16 peak; the step is a serial "
-                        "chain of %d dependent time steps, latency-bound: per step ~1.2 us of tcgen05.mma (48 MMAs of M=128 N=32 K=16 per "
-                        "CTA at the ~45-cycle issue floor), ~0.7 us gate math and ~1 us cluster exchange of h / partial sums "
-                        "(DESIGN.md section 4)" % (6 * T),
+                "note": "algorithmic FLOPs = one fp32 recurrent projection per direction per time step; the sweep kernels issue 4x that "
+                        "in bf16 MMAs (hi/lo split of both operands in ONE MMA), so their algorithmic ceiling is 1/4 of the bf16 peak "
+                        "(frac <= 0.25; issued_frac = 4 x frac); the GEMMs and the embedding kernel issue 3x (ceiling 1/3).  The step is "
+                        "a serial chain of %d dependent time steps: per step and SM 48 MMAs at the 46-cycle issue floor (1.1 us), "
+                        "~0.5 us for 12 KB of incoming DSMEM (~15 B/cycle/SM measured), ~0.4 us of tensor-memory drain (32 B/cycle per "
+                        "lane quarter measured) and the gate math; with 512 windows per GPU two independent 16-row groups per cluster "
+                        "take turns on the tensor pipe (DESIGN.md section 4.1, profiles/r2_tmem_dsmem_microbench.log)" % (6 * T),
                 "step_tflops_algorithmic": step_flops / (ms * 1e-3) / 1e12,
                 "step_frac_of_sustained_peak": step_flops / (ms * 1e-3) / 1e12 / peak_sus}
 

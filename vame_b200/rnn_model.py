@@ -14,6 +14,10 @@ from ._lib import VameB200Error
 from .engine import Engine
 
 
+import os as _os
+_CHECK_DECODER_INPUT = _os.environ.get("VAME_B200_CHECK_DECODER_INPUT", "1") != "0"
+
+
 def _bigru(in_size, hidden, layers, dropout):
     """Parameter container with the reference's nn.GRU configuration (bias, batch_first, bidirectional)."""
     return nn.GRU(in_size, hidden, layers, bias=True, batch_first=True, dropout=dropout, bidirectional=True)
@@ -88,6 +92,10 @@ class Decoder(nn.Module):
         steps = self.sequence_length if self._which == 0 else self.future_steps
         if inputs.shape[0] != z.shape[0] or inputs.shape[1] < steps or inputs.shape[2] != z.shape[1]:
             raise ValueError("decoder inputs must be z repeated over >= %d time steps, got %s" % (steps, tuple(inputs.shape)))
+        if _CHECK_DECODER_INPUT and not torch.equal(inputs[:, :steps].float(), z.float().unsqueeze(1).expand(-1, steps, -1)):
+            # the library projects z ONCE per sample (the reference's input is z at every step, rnn_model.py:169-170); any other
+            # `inputs` would silently be ignored - VAME_B200_CHECK_DECODER_INPUT=1 (default) turns that into an error
+            raise ValueError("vame_b200 Decoder.forward: `inputs` is not z repeated over time; only that form is supported")
         return eng.decoder_forward(z.detach().float(), self._which)
 
 
