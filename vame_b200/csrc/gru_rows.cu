@@ -25,8 +25,10 @@ constexpr int GR_H = 256, GR_NKC = 4, GR_NSL = 8;              // hidden units, 
 constexpr int GR_WTILE = 96 * KCHUNK * 2 * 2;                   // 24576 B: one (slice, k chunk) W tile, hi + lo planes
 constexpr int GR_HTILE = 128 * KCHUNK * 2 * 2;                  // 32768 B: one k chunk of the h operand, hi + lo planes
 constexpr int GR_NST = 4;                                       // W pipeline stages (96 KB in flight per SM)
-constexpr int GR_THREADS = 384;                                 // warps 0-7: gate math, 8: TMA producer (+ TMEM alloc), 9: MMA issue, 10-11: idle
-                                                                // (whole warpgroups, so that setmaxnreg can move registers to the gate-math warps)
+// EW gate-math warps per tensor-memory lane quarter (2 or 4): warps 0 .. 4 EW - 1 gate math (32 / EW units of a slice per thread),
+// then one warpgroup: TMA producer (+ TMEM alloc), MMA issue, two idle warps (whole warpgroups, so that setmaxnreg can move
+// registers to the gate-math warps)
+__host__ __device__ constexpr int gr_threads(int ew) { return (4 * ew + 4) * 32; }
 constexpr uint32_t GR_HCOL = 192;                               // tensor memory: accumulators [0, 96), [96, 192); fp32 h [192, 448)
 constexpr size_t GR_SMEM = (size_t)GR_NKC * GR_HTILE + (size_t)GR_NST * GR_WTILE + 1024 + 256;
 
@@ -60,11 +62,40 @@ template <int N>
 __device__ __forceinline__ void gr_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void gr_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 gate-math warps
+template <int NT>
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }   // the gate-math warps
+__device__ __forceinline__ void tmem_ld8u(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tm_ld(uint32_t taddr, float* v) {
+  if constexpr (N == 16) tmem_ld16u(taddr, v);
+  else tmem_ld8u(taddr, v);
+}
+template <int N>
+__device__ __forceinline__ void tm_st(uint32_t taddr, const float* v) {
+  if constexpr (N == 16) tmem_st16(taddr, v);
+  else tmem_st8u(taddr, v);
+}
 }  // namespace
 
-// grid = (tiles, directions), 320 threads, 1 CTA per SM
-__global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSeqFwdArgs a) {
+// grid = (tiles, directions), 1 CTA per SM
+template <int EW>
+__global__ void __launch_bounds__(gr_threads(EW), 1) gru_rows_fwd_kernel(const GruSeqFwdArgs a) {
+  constexpr int NEW = 4 * EW, NET = 128 * EW, UPT = 32 / EW;      // gate-math warps / threads, units of a slice per thread
+  constexpr bool PF = EW == 2;                                   // input projections fetched one slice ahead (second register set)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sH = smem;                                            // [NKC][hi 128 x 64 | lo 128 x 64]  (P16 tiles, RB = 128)
   uint8_t* sW = smem + GR_NKC * GR_HTILE;                         // [NST][hi 96 x 64 | lo 96 x 64]     (P16 tiles, RB = 96)
@@ -83,23 +114,24 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
 
   if (tid == 0) {
     for (int i = 0; i < GR_NST; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 256); }
-    mbar_init(hready, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], NET); }
+    mbar_init(hready, NET);
     mbar_fence_init();
   }
-  for (int i = tid; i < GR_H; i += GR_THREADS) sBhn[i] = d.b_hn[i];
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < GR_H; i += gr_threads(EW)) sBhn[i] = d.b_hn[i];
+  if (warp == NEW) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // 384 threads start with 168 registers each; the producer / MMA warpgroup gives 4 x 96 back, the two gate-math warpgroups take
-  // 8 x 48 (no spills around the asynchronous tcgen05.ld - see gru_rw.cu / profiles/r2_ng2_sw_fault.md)
-  // (each role's code sits inside the branch of its setmaxnreg: ptxas applies a budget only to code the instruction dominates)
-  if (warp >= 8) {
-  gr_reg_dec<72>();
-  if (warp == 8) {
+  // EW = 2: 384 threads start with 168 registers each; the producer / MMA warpgroup gives 4 x 96 back, the two gate-math
+  // warpgroups take 8 x 48.  EW = 4: 640 threads start with 96; 4 x 56 given back, 16 x 8 taken.  (No spills around the
+  // asynchronous tcgen05.ld - see gru_rw.cu / profiles/r2_ng2_sw_fault.md; each role's code sits inside the branch of its
+  // setmaxnreg: ptxas applies a budget only to code the instruction dominates.)
+  if (warp >= NEW) {
+  gr_reg_dec<EW == 2 ? 72 : 40>();
+  if (warp == NEW) {
     // ---------------- TMA producer: the W tiles of (slice, k chunk), the same sequence every step ----------------
     if (elect_one()) {
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.w_rows);
@@ -114,7 +146,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == NEW + 1) {
     // ---------------- MMA issue ----------------
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, 96);
@@ -152,20 +184,20 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
     __syncwarp();
   }
   } else {
-    gr_reg_inc<216>();
-    // ---------------- gate math: warp w owns tensor-memory lane quarter w & 3 (32 rows) and units 16 (w >> 2) .. + 15 of a slice ----
+    gr_reg_inc<EW == 2 ? 216 : 104>();
+    // ---------------- gate math: warp w owns tensor-memory lane quarter w & 3 (32 rows) and units UPT (w >> 2) .. + UPT - 1 of a slice ----
     const int q = warp & 3, hh = warp >> 2;
     const int r = 32 * q + lane;                                  // row inside the tile = tensor-memory lane
     const long row = (long)tile * 128 + r;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const float* gi_row = d.gi + row * d.gi_bs;
 
-    // rebuild of the operand tiles from the fp32 state: this warp converts units [128 hh, 128 hh + 128) of its 32 rows
+    // rebuild of the operand tiles from the fp32 state: this warp converts units [256 / EW * hh, + 256 / EW) of its 32 rows
     auto rebuild = [&]() {
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j) {                               // 16 units per iteration
+      for (int j = 0; j < 16 / EW; ++j) {                         // 16 units per iteration
         float v[16];
-        const int k0 = 128 * hh + 16 * j;
+        const int k0 = (256 / EW) * hh + 16 * j;
         tmem_ld16u(tlane + GR_HCOL + k0, v);
         tmem_ld_wait();
         uint4 hi0, lo0, hi1, lo1;
@@ -179,17 +211,17 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
         *reinterpret_cast<uint4*>(t + GR_HTILE / 2 + o1) = lo1;
       }
     };
-    // initial state -> fp32 tensor-memory state (every warp: its 16-unit share of each slice), then the operand tiles
+    // initial state -> fp32 tensor-memory state (every warp: its share of each slice), then the operand tiles
 #pragma unroll 1
     for (int c = 0; c < GR_NSL; ++c) {
-      float v[16];
+      float v[UPT];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = d.h0[(long)(32 * c + 16 * hh + i) * d.h0_ld + row];
-      tmem_st16(tlane + GR_HCOL + 32 * c + 16 * hh, v);
+      for (int i = 0; i < UPT; ++i) v[i] = d.h0[(long)(32 * c + UPT * hh + i) * d.h0_ld + row];
+      tm_st<UPT>(tlane + GR_HCOL + 32 * c + UPT * hh, v);
     }
     tmem_st_wait_();
     tc_fence_before();
-    epi_sync();
+    epi_sync<NET>();
     tc_fence_after();
     rebuild();
     fence_proxy_async_smem();
@@ -198,39 +230,39 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
     uint32_t acc_use = 0;
     // input projections are fetched ONE SLICE AHEAD into a second register set: they stream from HBM (393 KB per CTA and step),
     // and a load issued at the top of its own slice left ~1.5 us of latency exposed 8 times per step (measured: 25.7 us per step)
-    float gA[48], gB[48];
+    float gA[3 * UPT], gB[PF ? 3 * UPT : 1];
     auto load_gi = [&](int s_, int c_, float* g_) {
       const int t_ = d.reverse ? steps - 1 - s_ : s_;
-      const float* p_ = gi_row + (long)t_ * d.gi_ts + (long)(32 * c_ + 16 * hh) * d.gi_ld;
+      const float* p_ = gi_row + (long)t_ * d.gi_ts + (long)(32 * c_ + UPT * hh) * d.gi_ld;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < UPT; ++i) {
         g_[i] = p_[(long)i * d.gi_ld];
-        g_[16 + i] = p_[(long)(GR_H + i) * d.gi_ld];
-        g_[32 + i] = p_[(long)(2 * GR_H + i) * d.gi_ld];
+        g_[UPT + i] = p_[(long)(GR_H + i) * d.gi_ld];
+        g_[2 * UPT + i] = p_[(long)(2 * GR_H + i) * d.gi_ld];
       }
     };
     auto slice = [&](int c, const float* g_) {
       const uint32_t ab = acc_use & 1;
-      const int u0 = 32 * c + 16 * hh;                            // first of this thread's 16 units
+      const int u0 = 32 * c + UPT * hh;                           // first of this thread's units
       mbar_wait(&accfull[ab], (acc_use >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      float ar[16], az[16], an[16], hp[16];
-      const uint32_t acol = tlane + ab * 96 + 16 * hh;
-      tmem_ld16u(acol, ar);
-      tmem_ld16u(acol + 32, az);
-      tmem_ld16u(acol + 64, an);
-      tmem_ld16u(tlane + GR_HCOL + u0, hp);
+      float ar[UPT], az[UPT], an[UPT], hp[UPT];
+      const uint32_t acol = tlane + ab * 96 + UPT * hh;
+      tm_ld<UPT>(acol, ar);
+      tm_ld<UPT>(acol + 32, az);
+      tm_ld<UPT>(acol + 64, an);
+      tm_ld<UPT>(tlane + GR_HCOL + u0, hp);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&accempty[ab]);                                 // the accumulator is in registers: the MMAs of slice c + 2 may start
-      float hn[16];
+      float hn[UPT];
 #ifdef VAME_ACCURATE_MATH
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < UPT; ++i) {
         const float rg = gr_sigmoid(g_[i] + ar[i]);
-        const float zg = gr_sigmoid(g_[16 + i] + az[i]);
-        const float ng = gr_tanh(g_[32 + i] + rg * (an[i] + sBhn[u0 + i]));
+        const float zg = gr_sigmoid(g_[UPT + i] + az[i]);
+        const float ng = gr_tanh(g_[2 * UPT + i] + rg * (an[i] + sBhn[u0 + i]));
         hn[i] = (1.0f - zg) * ng + zg * hp[i];
       }
 #else
@@ -239,17 +271,17 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
       // units from one rcp of their product - 3 ex2 + 1 rcp per unit.  Arguments are clamped to [-20, 20] (sigmoid / tanh are
       // saturated to 2e-9 there) so that the products stay far below the fp32 range.
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
+      for (int i = 0; i < UPT; i += 2) {
         float rg[2], zg[2], dn[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float xr = fminf(fmaxf(g_[i + k] + ar[i + k], -20.f), 20.f);
-          const float xz = fminf(fmaxf(g_[16 + i + k] + az[i + k], -20.f), 20.f);
+          const float xz = fminf(fmaxf(g_[UPT + i + k] + az[i + k], -20.f), 20.f);
           const float dr = 1.0f + __expf(-xr), dz = 1.0f + __expf(-xz);
           const float inv = __fdividef(1.0f, dr * dz);
           rg[k] = inv * dz;
           zg[k] = inv * dr;
-          const float y = fminf(fmaxf(g_[32 + i + k] + rg[k] * (an[i + k] + sBhn[u0 + i + k]), -10.f), 10.f);
+          const float y = fminf(fmaxf(g_[2 * UPT + i + k] + rg[k] * (an[i + k] + sBhn[u0 + i + k]), -10.f), 10.f);
           dn[k] = 1.0f + __expf(-2.0f * y);
         }
         const float invn = __fdividef(1.0f, dn[0] * dn[1]);
@@ -260,25 +292,33 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
         }
       }
 #endif
-      tmem_st16(tlane + GR_HCOL + u0, hn);
+      tm_st<UPT>(tlane + GR_HCOL + u0, hn);
       ++acc_use;
     };
-    load_gi(0, 0, gA);
+    if constexpr (PF) load_gi(0, 0, gA);
     for (int s = 0; s < steps; ++s) {
       const int t = d.reverse ? steps - 1 - s : s;
+      if constexpr (PF) {
 #pragma unroll 1
-      for (int c = 0; c < GR_NSL; c += 2) {
-        load_gi(s, c + 1, gB);
-        slice(c, gA);
-        if (c + 2 < GR_NSL) load_gi(s, c + 2, gA);
-        else if (s + 1 < steps) load_gi(s + 1, 0, gA);
-        slice(c + 1, gB);
+        for (int c = 0; c < GR_NSL; c += 2) {
+          load_gi(s, c + 1, gB);
+          slice(c, gA);
+          if (c + 2 < GR_NSL) load_gi(s, c + 2, gA);
+          else if (s + 1 < steps) load_gi(s + 1, 0, gA);
+          slice(c + 1, gB);
+        }
+      } else {                                                    // 16 gate-math warps hide the load latency among themselves
+#pragma unroll 1
+        for (int c = 0; c < GR_NSL; ++c) {
+          load_gi(s, c, gA);
+          slice(c, gA);
+        }
       }
       // ---- end of the step: every MMA has completed (accfull of the last slice), the new state is complete in tensor memory ----
       tmem_st_wait_();
       tc_fence_before();
       if (tid == 0) bulk_wait_read0();                            // the previous step's bulk store has finished reading sH
-      epi_sync();
+      epi_sync<NET>();
       tc_fence_after();
       rebuild();
       fence_proxy_async_smem();
@@ -286,7 +326,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
       if (!last) mbar_arrive(hready);
       const bool store = d.out_p && (d.out_p_slots == steps || last);
       if (store) {
-        epi_sync();                                               // all 8 warps have written their part of the tiles
+        epi_sync<NET>();                                          // all gate-math warps have written their part of the tiles
         if (tid == 0) {
           const int sp = (d.out_p_slots == steps) ? t : (s & 1);
           uint8_t* dst = reinterpret_cast<uint8_t*>(d.out_p) + ((size_t)sp * d.out_p_slot_elems + (size_t)tile * GR_NKC * (GR_HTILE / 2)) * 2;
@@ -299,11 +339,11 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
         const int so = (d.out_slots == steps) ? t : (s & 1);
 #pragma unroll 1
         for (int c = 0; c < GR_NSL; ++c) {
-          float v[16];
-          tmem_ld16u(tlane + GR_HCOL + 32 * c + 16 * hh, v);
+          float v[UPT];
+          tm_ld<UPT>(tlane + GR_HCOL + 32 * c + UPT * hh, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) d.out[(long)(32 * c + 16 * hh + i) * d.out_ld + (long)so * Bp + row] = v[i];
+          for (int i = 0; i < UPT; ++i) d.out[(long)(32 * c + UPT * hh + i) * d.out_ld + (long)so * Bp + row] = v[i];
         }
       }
     }
@@ -311,7 +351,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_rows_fwd_kernel(const GruSe
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == NEW) tmem_dealloc(tmem, 512);
 }
 
 bool rows_fwd_applicable(int H, int tiles) { return g_opt_rows && H == GR_H && tiles >= 1; }
@@ -319,11 +359,13 @@ bool rows_fwd_applicable(int H, int tiles) { return g_opt_rows && H == GR_H && t
 void launch_gru_rows_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gru_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+    cudaFuncSetAttribute(gru_rows_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+    cudaFuncSetAttribute(gru_rows_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
     attr = true;
   }
   count_launch();
-  gru_rows_fwd_kernel<<<dim3(a.tiles, a.ndir), GR_THREADS, GR_SMEM, st>>>(a);
+  if (g_opt_rows >= 4) gru_rows_fwd_kernel<4><<<dim3(a.tiles, a.ndir), gr_threads(4), GR_SMEM, st>>>(a);
+  else gru_rows_fwd_kernel<2><<<dim3(a.tiles, a.ndir), gr_threads(2), GR_SMEM, st>>>(a);
 }
 
 }  // namespace vb

@@ -324,8 +324,10 @@ class Engine:
                                                   L.ptr(ws), ws.numel(), L.cur_stream()), "vame_decoder_forward")
         return pred
 
-    def embed(self, series_nf, first_window=0, n_windows=None, chunk=8192, out=None):
-        """mu of every stride-1 window of a frame-major (N, F) float32 CUDA series -> (n_windows, Z)."""
+    def embed(self, series_nf, first_window=0, n_windows=None, chunk=9472, out=None):
+        """mu of every stride-1 window of a frame-major (N, F) float32 CUDA series -> (n_windows, Z).
+        chunk: windows per pass; the default 9472 = 74 tiles of 128 rows x 2 directions = 148 CTAs of the row-resident sweep
+        kernel, one per SM."""
         d = self.dims
         assert series_nf.is_cuda and series_nf.dtype == torch.float32 and series_nf.is_contiguous() and series_nf.shape[1] == d.num_features
         N = series_nf.shape[0]

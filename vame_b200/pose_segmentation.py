@@ -31,7 +31,7 @@ def load_model(cfg, model_name, fixed):
     return model
 
 
-def embed_series(model, data, temp_win, chunk=8192, shard=None):
+def embed_series(model, data, temp_win, chunk=9472, shard=None):
     """(F, N) array -> (N - temp_win, Z) float32 numpy array of latent means.
     shard = (rank, world): embed only this rank's contiguous slice of the window range (no collective on the data path)."""
     eng = model.engine
