@@ -127,7 +127,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
  * event-record node when the call is captured into a CUDA graph); vame_wait_grads_ready(stream) makes `stream` wait for the
  * event of the most recently enqueued vame_backward, so the caller can all-reduce that range on a communication stream while
  * the last BPTT sweep still runs, and only the small encoder-layer-0 range [0, split) after the call. */
-int vame_grad_overlap(int enable);
+int vame_grad_overlap(int enable);   /* 0 off, 1 = consumer outside the captured graph (external event), 2 = consumer captured into the same graph */
 long vame_grad_bucket_split(const vame_dims* d);
 int vame_wait_grads_ready(void* stream);
 
@@ -137,6 +137,16 @@ int vame_wait_grads_ready(void* stream);
 int vame_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
                    float lr, const float* hyper, int* step_dev, float* scratch, float beta1, float beta2, float eps,
                    float grad_scale, void* stream);
+
+/* The same optimizer step in two pieces, so that a train loop can update the parameters whose gradients are final early (everything
+ * but encoder layer 0, see vame_grad_bucket_split) on a side stream while the backward pass still runs: vame_adam_prepare
+ * increments the step counter and writes the bias-corrected step size into scratch (once per step), vame_adam_apply updates one
+ * range of the flat buffers (n a multiple of 4, pointers already offset).  vame_pack_weights_train_part re-packs the formats of
+ * encoder layer 0 (part 0) or of everything else (part 1). */
+int vame_adam_prepare(float lr, const float* hyper, int* step_dev, float* scratch, float beta1, float beta2, void* stream);
+int vame_adam_apply(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
+                    const float* scratch, float beta1, float beta2, float eps, float grad_scale, void* stream);
+int vame_pack_weights_train_part(const vame_dims* d, const float* params, void* packed, int batch, int part, void* stream);
 
 /* embedd_latent_vectors (vame/analysis/pose_segmentation.py:87-98): mu of every stride-1 window.
  * series: [n_frames, F] fp32 (frame-major, i.e. the transpose of the reference's (F, N) array);

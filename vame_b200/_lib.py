@@ -42,6 +42,10 @@ SIGNATURES = {
                           c_void_p, c_size_t, c_void_p]),
     "vame_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vame_adam_prepare": (c_int, [c_float, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
+    "vame_adam_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float, c_float,
+                                c_void_p]),
+    "vame_pack_weights_train_part": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vame_grad_overlap": (c_int, [c_int]),
     "vame_grad_bucket_split": (c_long, [c_void_p]),
     "vame_wait_grads_ready": (c_int, [c_void_p]),

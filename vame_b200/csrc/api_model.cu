@@ -338,7 +338,7 @@ static void pack_gru_weights(const float* P, const GruOff& o, const GruPacked& W
 
 // everything except the forward formats of encoder layer 0 (first = false), or only those (first = true), or all (both)
 static void pack_weights_part(const vame_dims& d, const float* P, const PackedWeights& W, bool first, bool rest, cudaStream_t st,
-                              int train_batch = 0) {
+                              int train_batch = 0, bool skip_e0_bwd = false) {
   const ParamLayout L = param_layout(d);
   const int H = d.hidden_enc, F = d.num_features, Z = d.zdims;
   // train_batch > 0: formats of the slice kernels are skipped for the layers whose sweeps run on the rw kernels at that batch
@@ -347,7 +347,7 @@ static void pack_weights_part(const vame_dims& d, const float* P, const PackedWe
   JobQ q(st);
   if (first) pack_gru_fwd(P, L.e0, W.e0, q, slices_of(H));
   if (rest) {
-    pack_gru_bwd(P, L.e0, W.e0, q, slices_of(H));
+    if (!skip_e0_bwd) pack_gru_bwd(P, L.e0, W.e0, q, slices_of(H));
     pack_gru_weights(P, L.e1, W.e1, q, slices_of(H));
     for (int i = 0; i < 4; ++i) q.rows(P + L.lam_w + (long)i * H, 4 * H, 2 * Z, H, 2 * Z, W.lam_p[i]);
     q.T(P + L.lam_w, 4 * H, 4 * H, 2 * Z, 2 * Z, W.lamT_p);
@@ -361,6 +361,21 @@ static void pack_weights_part(const vame_dims& d, const float* P, const PackedWe
     }
   }
   q.flush();
+}
+// split by LAYER (early optimizer step of the train loop): part 0 = every format of encoder layer 0, part 1 = everything else
+static void pack_weights_layers(const vame_dims& d, const float* P, const PackedWeights& W, int part, cudaStream_t st, int batch) {
+  const ParamLayout L = param_layout(d);
+  const int H = d.hidden_enc;
+  const int tiles = batch > 0 ? pad128(batch) / 128 : 0;
+  if (part == 0) {
+    const bool slices = !(tiles > 0 && g_opt_rw == 3 && rw_applicable(H, tiles));
+    JobQ q(st);
+    pack_gru_fwd(P, L.e0, W.e0, q, slices);
+    pack_gru_bwd(P, L.e0, W.e0, q, slices);
+    q.flush();
+  } else {
+    pack_weights_part(d, P, W, false, true, st, batch, /*skip_e0_bwd=*/true);
+  }
 }
 static void pack_all_weights(const vame_dims& d, const float* P, const PackedWeights& W, cudaStream_t st) {
   pack_weights_part(d, P, W, true, true, st);
@@ -796,6 +811,13 @@ int vame_pack_weights_train(const vame_dims* d, const float* params, void* packe
   return check_launch("vame_pack_weights_train");
 }
 
+int vame_pack_weights_train_part(const vame_dims* d, const float* params, void* packed, int batch, int part, void* stream) {
+  if (check_dims(d)) return -1;
+  VB_REQUIRE(params && packed && batch > 0 && (part == 0 || part == 1), "vame_pack_weights_train_part: bad arguments");
+  pack_weights_layers(*d, params, packed_layout(*d, packed), part, (cudaStream_t)stream, batch);
+  return check_launch("vame_pack_weights_train_part");
+}
+
 int vame_pack_weights_deferred(const vame_dims* d, const float* params, void* packed, void* stream) {
   if (check_dims(d)) return -1;
   VB_REQUIRE(params && packed, "vame_pack_weights_deferred: null pointer");
@@ -947,6 +969,7 @@ int vame_loss(const vame_dims* d, int batch, const vame_loss_cfg* cfg, const flo
 // first bucket while the last sweep runs.
 struct GradOverlap {
   bool on = false;
+  bool internal = false;     // mode 2: the consumer is captured into the SAME graph (plain event = dependency edge)
   cudaEvent_t ev = nullptr;
 };
 static GradOverlap& grad_overlap() {
@@ -959,6 +982,7 @@ int vame_grad_overlap(int enable) {
     if (cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming) != cudaSuccess) return fail("vame_grad_overlap: cudaEventCreate failed");
   }
   G.on = enable != 0;
+  G.internal = enable == 2;
   return 0;
 }
 long vame_grad_bucket_split(const vame_dims* d) {
@@ -970,8 +994,8 @@ int vame_wait_grads_ready(void* stream) {
   VB_REQUIRE(G.ev, "vame_wait_grads_ready: no vame_backward has run with vame_grad_overlap(1) yet");
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing((cudaStream_t)stream, &cap);
-  if (cudaStreamWaitEvent((cudaStream_t)stream, G.ev, cap == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault) !=
-      cudaSuccess)
+  if (cudaStreamWaitEvent((cudaStream_t)stream, G.ev,
+                          (cap == cudaStreamCaptureStatusActive && !G.internal) ? cudaEventWaitExternal : cudaEventWaitDefault) != cudaSuccess)
     return fail("vame_wait_grads_ready: cudaStreamWaitEvent failed");
   return 0;
 }
@@ -1154,10 +1178,13 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
     // sA; once they are complete the first bucket [vame_grad_bucket_split, total) may be all-reduced
     edge(sC, sB);
     if (used_sA) edge(sA, sB);
-    // (the external flag - an event-record NODE that code outside the graph can wait for - is only legal during stream capture)
+    edge(st, sB);          // ... and the dx1 GEMM (main stream) has read the layer-1 weights: the consumer may re-pack them
+    // (the external flag - an event-record NODE that code outside the graph can wait for - is only legal during stream capture;
+    //  mode 2: the consumer is captured into the same graph, a plain record is the dependency edge)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(sB, &cap);
-    cudaEventRecordWithFlags(grad_overlap().ev, sB, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+    cudaEventRecordWithFlags(grad_overlap().ev, sB,
+                             (cap == cudaStreamCaptureStatusActive && !grad_overlap().internal) ? cudaEventRecordExternal : cudaEventRecordDefault);
   }
   // ---- encoder layer 0
   mark(st, "bwd:dx1 gemm");
@@ -1192,6 +1219,20 @@ int vame_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 
 /* Re-run one recurrent sweep of encoder layer 1 on the buffers of the last vame_forward(save=1) [+ vame_backward]:
  * which = 0 forward steps, 1 backward steps.  Used by bench.py to time the dominant kernel with CUDA events. */
+int vame_adam_prepare(float lr, const float* hyper, int* step_dev, float* scratch, float beta1, float beta2, void* stream) {
+  VB_REQUIRE(step_dev && scratch, "vame_adam_prepare: null pointer");
+  launch_adam_prepare(lr, hyper, step_dev, scratch, beta1, beta2, (cudaStream_t)stream);
+  return check_launch("vame_adam_prepare");
+}
+
+int vame_adam_apply(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
+                    const float* scratch, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  VB_REQUIRE(params && grads && exp_avg && exp_avg_sq && max_exp_avg_sq && scratch, "vame_adam_apply: null pointer");
+  VB_REQUIRE(n > 0 && n % 4 == 0, "vame_adam_apply: the range must be a positive multiple of 4 floats");
+  launch_adam_apply(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, n, scratch, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+  return check_launch("vame_adam_apply");
+}
+
 int vame_debug_gru_sweep(const vame_dims* d, int batch, int which, const float* params, const void* packed, void* ws, size_t ws_bytes,
                          void* stream) {
   if (check_dims(d)) return -1;

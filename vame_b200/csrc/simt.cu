@@ -798,6 +798,15 @@ void launch_adam(float* p, const float* g, float* m, float* v, float* vmax, long
   count_launch();
   adam_amsgrad_kernel<<<grid_for(n / 4 + 1, 256, 148 * 4), 256, 0, st>>>(p, g, m, v, vmax, n, scratch2, b1, b2, eps, grad_scale);
 }
+void launch_adam_prepare(float lr, const float* hyper, int* step_dev, float* scratch2, float b1, float b2, cudaStream_t st) {
+  count_launch();
+  adam_prepare_kernel<<<1, 32, 0, st>>>(step_dev, scratch2, lr, hyper, b1, b2);
+}
+void launch_adam_apply(float* p, const float* g, float* m, float* v, float* vmax, long n, const float* scratch2, float b1, float b2,
+                       float eps, float grad_scale, cudaStream_t st) {
+  count_launch();
+  adam_amsgrad_kernel<<<grid_for(n / 4 + 1, 256, 148 * 4), 256, 0, st>>>(p, g, m, v, vmax, n, scratch2, b1, b2, eps, grad_scale);
+}
 void launch_finalize_losses(const double* acc, float* out, double rec_div, double fut_div, double kl_n, double beta, double klw,
                             const float* hyper, int future, cudaStream_t st) {
   count_launch();

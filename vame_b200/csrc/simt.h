@@ -38,6 +38,9 @@ void launch_mse(const float* pred, long ldp, const float* target, int rows, int 
 constexpr int CP_STATE_DOUBLES = 4 + 64 * 64;
 void launch_cluster_prior(const float* z, int B, int Z, int kloss, double lmbda, double bsize, double gcoef, const float* hyper,
                           float* dz, double* acc, cudaStream_t st, double* state = nullptr);
+void launch_adam_prepare(float lr, const float* hyper, int* step_dev, float* scratch2, float b1, float b2, cudaStream_t st);
+void launch_adam_apply(float* p, const float* g, float* m, float* v, float* vmax, long n, const float* scratch2, float b1, float b2,
+                       float eps, float grad_scale, cudaStream_t st);
 void launch_colsum(const float* X, long ld, long rows, int N, float* out, cudaStream_t st);
 void launch_timesum_fm(const float* X, long ld, int T, int Bp, int C, float* out, cudaStream_t st);
 void launch_rowsum_fm(const float* X, long ld, long ncols, int nfeat, float* out, cudaStream_t st);

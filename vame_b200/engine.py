@@ -368,7 +368,7 @@ class TrainStep:
     The two compute phases are captured once as CUDA graphs and replayed (the launch-bound recurrence is ~200 dependent
     kernels); hyper-parameters that change between steps (lr, kl_weight, ...) live in device memory (Engine.hyper)."""
 
-    def __init__(self, eng, batch, cfg, world=1, use_graph=True, betas=(0.9, 0.999), eps=1e-8, sampler=None):
+    def __init__(self, eng, batch, cfg, world=1, use_graph=True, betas=(0.9, 0.999), eps=1e-8, sampler=None, early_opt=None):
         self.eng, self.B, self.cfg, self.world = eng, int(batch), cfg, int(world)
         # optional vame_b200.dataloader.DeviceWindowSampler: its vame_sample_windows launch becomes the first node of the step
         # (window starts, z-score, data / future split and the reparameterisation noise are produced on the device)
@@ -389,6 +389,14 @@ class TrainStep:
         # CTAs compete with the 128-SM sweep for the 20 SMs the weight-gradient GEMMs run on) -> on by default from 384 up
         ov = os.environ.get("VAME_B200_GRAD_OVERLAP")
         self.overlap = self.world > 1 and (ov != "0" if ov is not None else self.B >= 384)
+        # N = 1, opt-in (VAME_B200_EARLY_OPT=1): the optimizer step + weight re-pack of everything but encoder layer 0 on a side stream
+        # under the last BPTT sweep (their gradients are final ~200 us before the backward pass ends).  Measured neutral (C2 292.7 k
+        # vs 295.7 k, C5 363.6 k vs 362.1 k windows/s): the end of the step is bound by the weight-gradient GEMMs, not by AMSGrad
+        self.early_opt = (self.world == 1 and os.environ.get("VAME_B200_EARLY_OPT", "0") != "0"
+                          and os.environ.get("VAME_B200_DEFER_REPACK", "0") == "0") if early_opt is None else bool(early_opt)
+        self._opt_stream = torch.cuda.Stream(device=dev) if self.early_opt else None
+        if self.early_opt:
+            self.split = int(eng.lib.vame_grad_bucket_split(ctypes.byref(eng.dims)))
         self._comm_stream = None
         if self.overlap:
             self.split = int(eng.lib.vame_grad_bucket_split(ctypes.byref(eng.dims)))
@@ -401,8 +409,23 @@ class TrainStep:
         if cfg.bsize == 0:
             cfg.bsize = float(batch)
 
+    def _adam_range(self, lo, hi, stream_ptr):
+        e, st = self.eng, self.eng.opt_state
+        off = lo * 4
+        p = lambda t: ctypes.c_void_p(t.data_ptr() + off)  # noqa: E731
+        L.check(e.lib.vame_adam_apply(p(e.flat), p(e.grad), p(st["exp_avg"]), p(st["exp_avg_sq"]), p(st["max_exp_avg_sq"]), hi - lo,
+                                      L.ptr(st["scratch"]), float(self.betas[0]), float(self.betas[1]), float(self.adam_eps),
+                                      1.0 / self.world, stream_ptr), "vame_adam_apply")
+
     def _phase1(self):
         e = self.eng
+        if self.early_opt:
+            # step counter + bias-corrected step size for this step, then fork the optimizer stream (it starts working when the
+            # backward pass signals that every gradient outside encoder layer 0 is final)
+            st = e.opt_state
+            L.check(e.lib.vame_adam_prepare(0.0, L.ptr(e.hyper), L.ptr(st["step"]), L.ptr(st["scratch"]), float(self.betas[0]),
+                                            float(self.betas[1]), L.cur_stream()), "vame_adam_prepare")
+            self._opt_stream.wait_stream(torch.cuda.current_stream())
         if self.sampler is not None:
             self.sampler.fill(self.x, self.fut if self.cfg.with_future else None, self.eps)
         if self.defer_repack:
@@ -422,12 +445,20 @@ class TrainStep:
             if self.early_prior:
                 e.lib.vame_arm_prior(None, None)
         e.loss(self.cfg, self.fut if self.cfg.with_future else None, want_grads=True, use_hyper=True, out=self.losses)
-        if self.overlap:
-            L.check(e.lib.vame_grad_overlap(1), "vame_grad_overlap")
+        if self.overlap or self.early_opt:
+            L.check(e.lib.vame_grad_overlap(2 if self.early_opt else 1), "vame_grad_overlap")
         try:
             e.backward(self.cfg, use_hyper=True)
+            if self.early_opt:
+                so = self._opt_stream
+                with torch.cuda.stream(so):
+                    sp = ctypes.c_void_p(so.cuda_stream)
+                    L.check(e.lib.vame_wait_grads_ready(sp), "vame_wait_grads_ready")
+                    self._adam_range(self.split, e.n_flat, sp)
+                    L.check(e.lib.vame_pack_weights_train_part(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), self.B, 1, sp),
+                            "vame_pack_weights_train_part")
         finally:
-            if self.overlap:
+            if self.overlap or self.early_opt:
                 e.lib.vame_grad_overlap(0)
         self.cfg.defer_prior_join = 0
 
@@ -450,6 +481,15 @@ class TrainStep:
     def _phase2(self):
         # with defer_repack the packed copies are refreshed at the start of the next step (and by _ensure_packed for any other caller)
         e = self.eng
+        if self.early_opt:
+            # encoder layer 0 (its gradients were final last), then join the optimizer stream
+            self._adam_range(0, self.split, L.cur_stream())
+            L.check(e.lib.vame_pack_weights_train_part(ctypes.byref(e.dims), L.ptr(e.flat), L.ptr(e.packed), self.B, 0, L.cur_stream()),
+                    "vame_pack_weights_train_part")
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
+            e._packed_version = None
+            self.acc.add_(self.losses)
+            return
         e.adam_step(betas=self.betas, eps=self.adam_eps, grad_scale=1.0 / self.world, use_hyper=True, repack=False)
         if not self.defer_repack:
             # only the weight formats a step of THIS batch size reads; any other consumer re-packs everything (mark_dirty in run())
