@@ -204,6 +204,8 @@ def test_embed_video1(golden_dir):
     assert rel(lat[:n][::40], g["latent_first"]) <= OUT_TOL
     ref = vo.embed_batched(port, clean.astype(np.float64), T)
     assert rel(lat, ref) <= OUT_TOL
+    from vame_b200 import _lib
+    assert _lib.lib().vame_get_option(b"rows_timeouts") == 0, "a bounded wait inside gru_rows_fwd_kernel gave up"
 
 
 def test_module_surface_and_autograd(golden_dir):

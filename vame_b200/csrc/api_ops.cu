@@ -55,6 +55,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "rw_priv") == 0) return vb::g_opt_rw_priv;
   if (strcmp(name, "rw_sw") == 0) return vb::g_opt_rw_sw;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
+  if (strcmp(name, "rows_timeouts") == 0) return (int)vb::rows_timeouts();
   if (strncmp(name, "rw_timeout_info", 15) == 0) return vb::rw_timeout_info(name[15] ? name[15] - '0' : 0);
   return -1;
 }

@@ -20,7 +20,17 @@
 
 namespace vb {
 
+__device__ unsigned int g_rows_timeouts = 0;   // bounded mbarrier waits that gave up (must stay 0; vame_get_option("rows_timeouts"))
+
 namespace {
+// a wait that cannot hang the GPU: a protocol bug shows up as a counted time-out (and wrong numbers), not as a dead box
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < (1 << 20); ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((i & 4095) == 4095 && *reinterpret_cast<volatile unsigned int*>(&g_rows_timeouts) != 0) return;   // someone already gave up
+  }
+  atomicAdd(&g_rows_timeouts, 1u);
+}
 constexpr int GR_H = 256, GR_NKC = 4, GR_NSL = 8;              // hidden units, 64-k chunks, 32-unit slices
 constexpr int GR_WTILE = 96 * KCHUNK * 2 * 2;                   // 24576 B: one (slice, k chunk) W tile, hi + lo planes
 constexpr int GR_HTILE = 128 * KCHUNK * 2 * 2;                  // 32768 B: one k chunk of the h operand, hi + lo planes
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(gr_threads(EW), 1) gru_rows_fwd_kernel(const G
       for (int s = 0; s < steps; ++s) {
         for (int i = 0; i < GR_NSL * GR_NKC; ++i, ++it) {
           const uint32_t st = it % GR_NST, use = it / GR_NST;
-          if (use > 0) mbar_wait(&wempty[st], (use - 1) & 1);
+          if (use > 0) mbar_wait_bounded(&wempty[st], (use - 1) & 1);
           mbar_expect_tx(&wfull[st], GR_WTILE);
           bulk_g2s(sW + (size_t)st * GR_WTILE, wp + (size_t)i * GR_WTILE, GR_WTILE, &wfull[st]);
         }
@@ -152,18 +162,18 @@ __global__ void __launch_bounds__(gr_threads(EW), 1) gru_rows_fwd_kernel(const G
       const uint32_t idesc = make_idesc_bf16(128, 96);
       uint32_t it = 0, acc_use = 0;
       for (int s = 0; s < steps; ++s) {
-        mbar_wait(hready, s & 1);
+        mbar_wait_bounded(hready, s & 1);
         fence_proxy_async_smem();
         tc_fence_after();
         for (int c = 0; c < GR_NSL; ++c, ++acc_use) {
           const uint32_t ab = acc_use & 1;
-          if (acc_use >= 2) mbar_wait(&accempty[ab], ((acc_use >> 1) - 1) & 1);
+          if (acc_use >= 2) mbar_wait_bounded(&accempty[ab], ((acc_use >> 1) - 1) & 1);
           tc_fence_after();
           const uint32_t dcol = tmem + ab * 96;
 #pragma unroll 1
           for (int kc = 0; kc < GR_NKC; ++kc, ++it) {
             const uint32_t st = it % GR_NST;
-            mbar_wait(&wfull[st], (it / GR_NST) & 1);
+            mbar_wait_bounded(&wfull[st], (it / GR_NST) & 1);
             tc_fence_after();
             const uint64_t dAhi = make_desc(smem_u32(sH) + kc * GR_HTILE), dAlo = make_desc(smem_u32(sH) + kc * GR_HTILE + GR_HTILE / 2);
             const uint64_t dBhi = make_desc(smem_u32(sW) + st * GR_WTILE), dBlo = make_desc(smem_u32(sW) + st * GR_WTILE + GR_WTILE / 2);
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(gr_threads(EW), 1) gru_rows_fwd_kernel(const G
     auto slice = [&](int c, const float* g_) {
       const uint32_t ab = acc_use & 1;
       const int u0 = 32 * c + UPT * hh;                           // first of this thread's units
-      mbar_wait(&accfull[ab], (acc_use >> 1) & 1);
+      mbar_wait_bounded(&accfull[ab], (acc_use >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       float ar[UPT], az[UPT], an[UPT], hp[UPT];
@@ -355,6 +365,11 @@ __global__ void __launch_bounds__(gr_threads(EW), 1) gru_rows_fwd_kernel(const G
 }
 
 bool rows_fwd_applicable(int H, int tiles) { return g_opt_rows && H == GR_H && tiles >= 1; }
+unsigned int rows_timeouts() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_rows_timeouts, sizeof(v));
+  return v;
+}
 
 void launch_gru_rows_fwd(const GruSeqFwdArgs& a, cudaStream_t st) {
   static bool attr = false;

@@ -189,6 +189,7 @@ void launch_gru_rw_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 extern int g_opt_rows;             // 1: inference sweeps of H = 256 layers that do not fit the rw kernels use gru_rows_fwd_kernel
 bool rows_fwd_applicable(int H, int tiles);
 void launch_gru_rows_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
+unsigned int rows_timeouts();      // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)
 unsigned int rw_timeouts();
 int rw_timeout_info(int i);        // first time-out: 0 site id, 1 parity, 2-4 blockIdx, 5 threadIdx.x
 void rw_timeouts_reset();       // bounded waits that gave up since the library was loaded (0 unless there is a protocol bug)
