@@ -1016,10 +1016,12 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   const ParamLayout L = param_layout(*d);
   const PackedWeights W = packed_layout(*d, const_cast<void*>(packed));
   const int T = d->time_window, F = d->num_features, Z = d->zdims, H = d->hidden_enc, Bp = w.B_pad, B = batch;
-  {   // SMs left for the weight-gradient GEMMs while a sweep (tiles x H/32 slices x 2 directions CTAs, 1 per SM) is running
-    int sweep = w.tiles * (H / 32) * 2 * (d->future_decoder ? 2 : 1);
-    if (g_opt_m64 && 2 * sweep <= 148) sweep *= 2;          // (same rule as gru_sweep_bwd: 64-row CTAs when they fit)
-    g_side_sms = g_opt_streams ? (sweep < 100 ? 148 - sweep : 48) : 148;
+  {   // Persistent-grid cap of the weight-gradient GEMMs that run on the side streams beside the sweeps.  Round 1 capped them to
+      // the SMs a sweep leaves free (20-48 CTAs); measured in round 2 (option "side_sms", profiles/r2_bench_v16_*): NO cap is
+      // better - the CTAs that do not fit wait in the hardware queue and take an SM the moment a sweep CTA exits, instead of a
+      // few resident CTAs working through the whole backlog (C2 296.1 -> 310.3 k, C5 363.0 -> 410.1 k windows/s; 20 CTAs: 219.5 k).
+    g_side_sms = 148;
+    if (g_opt_side_sms > 0) g_side_sms = g_opt_side_sms;      // (experiment knob: option "side_sms")
   }
   const int nkcB = Bp / KCHUNK;
   float* G = grads;

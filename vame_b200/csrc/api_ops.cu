@@ -18,10 +18,11 @@ int g_opt_rw = 3;              // bit 0 / bit 1: forward / backward sweeps by th
 int g_opt_rw_waves = 2;      // measured: two waves of resident-weight clusters beat the slice kernels at B = 512 (C5 +31 %, C3 +22 %)
 int g_opt_rw2 = 1;
 int g_opt_rows = 4;             // row-resident forward sweep (gru_rows.cu) for large inference batches: 0 off, 1 = 8 gate-math warps, 4 = 16 (measured: 3.03 vs 3.08 M windows/s at C4)
+int g_opt_side_sms = 0;
 int g_opt_rw_ng = 0;            // 16-row groups per cluster of the H = 256 rw kernels: 0 = automatic, 1 or 2 forced
 int g_opt_rw_exp = 0;
 int g_opt_rw_priv = 1;
-int g_opt_rw_sw = 5;             // bit 0: forward sweeps, bit 1: BPTT sweeps with 16 rows per cluster (measured neutral), bit 2: BPTT sweeps with 2 x 16 rows
+int g_opt_rw_sw = 7;             // store warps: bit 0 forward sweeps, bit 1 BPTT sweeps with 16 rows per cluster (round 2, after the per-role loops: 3.68 -> 3.22 us per step, C2 +3.4 %), bit 2 BPTT sweeps with 2 x 16 rows
 unsigned long long* g_dbg_buffer = nullptr;
 }
 
@@ -52,6 +53,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "rw2") == 0) return vb::g_opt_rw2;
   if (strcmp(name, "rw_ng") == 0) return vb::g_opt_rw_ng;
   if (strcmp(name, "rows") == 0) return vb::g_opt_rows;
+  if (strcmp(name, "side_sms") == 0) return vb::g_opt_side_sms;
   if (strcmp(name, "rw_priv") == 0) return vb::g_opt_rw_priv;
   if (strcmp(name, "rw_sw") == 0) return vb::g_opt_rw_sw;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
@@ -120,6 +122,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "rw_ng") == 0) {
     vb::g_opt_rw_ng = (value == 1 || value == 2) ? value : 0;
+    return 0;
+  }
+  if (strcmp(name, "side_sms") == 0) {
+    vb::g_opt_side_sms = value < 0 ? 0 : value;
     return 0;
   }
   if (strcmp(name, "rows") == 0) {
