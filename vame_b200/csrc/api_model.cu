@@ -1157,7 +1157,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
   cudaStream_t sC = g_opt_streams ? side().s[3] : st;
   cudaStream_t sdir[2] = {sB, sC};
   const int side_total = g_side_sms;
-  if (g_opt_streams) g_side_sms = side_total / 2;
+  if (g_opt_streams) g_side_sms = side_total / g_opt_side_split;
   edge(st, sB);
   edge(st, sC);
   w.e0.dout_pv = w.e0.priv && H == 256 && rw_priv_mode(H, w.tiles);
@@ -1194,7 +1194,7 @@ int vame_backward(const vame_dims* d, int batch, const float* params, const void
                 nullptr, nullptr, &L.e0, G);
   edge(st, sB);
   edge(st, sC);
-  g_side_sms = g_opt_streams ? 74 : 148;     // nothing else runs beside the last block: half of the GPU per direction
+  g_side_sms = g_opt_streams ? 148 / g_opt_side_split : 148;     // nothing else runs beside the last block: half of the GPU per direction
   gru_recurrent_grads(L.e0, w.e0, Bp, w.zeros_p, w.zeros_p, G, sB, true, sC);
   for (int dd = 0; dd < 2; ++dd) {           // dW_ih(l0)[dd] = dgi0[dd]^T x
     if (!w.e0.priv) launch_pack_p16_rowsum(w.e0.dgi[dd], rows, 3 * H, (int)rows, 3 * H, w.e0.dgiT_p[dd], G + L.e0.bih[dd], sdir[dd]);

@@ -19,6 +19,7 @@ int g_opt_rw_waves = 2;      // measured: two waves of resident-weight clusters 
 int g_opt_rw2 = 1;
 int g_opt_rows = 4;             // row-resident forward sweep (gru_rows.cu) for large inference batches: 0 off, 1 = 8 gate-math warps, 4 = 16 (measured: 3.03 vs 3.08 M windows/s at C4)
 int g_opt_side_sms = 0;
+int g_opt_side_split = 2;
 int g_opt_rw_ng = 0;            // 16-row groups per cluster of the H = 256 rw kernels: 0 = automatic, 1 or 2 forced
 int g_opt_rw_exp = 0;
 int g_opt_rw_priv = 1;
@@ -54,6 +55,7 @@ int vame_get_option(const char* name) {
   if (strcmp(name, "rw_ng") == 0) return vb::g_opt_rw_ng;
   if (strcmp(name, "rows") == 0) return vb::g_opt_rows;
   if (strcmp(name, "side_sms") == 0) return vb::g_opt_side_sms;
+  if (strcmp(name, "side_split") == 0) return vb::g_opt_side_split;
   if (strcmp(name, "rw_priv") == 0) return vb::g_opt_rw_priv;
   if (strcmp(name, "rw_sw") == 0) return vb::g_opt_rw_sw;
   if (strcmp(name, "rw_timeouts") == 0) return (int)vb::rw_timeouts();
@@ -126,6 +128,10 @@ int vame_set_option(const char* name, int value) {
   }
   if (strcmp(name, "side_sms") == 0) {
     vb::g_opt_side_sms = value < 0 ? 0 : value;
+    return 0;
+  }
+  if (strcmp(name, "side_split") == 0) {
+    vb::g_opt_side_split = value == 1 ? 1 : 2;
     return 0;
   }
   if (strcmp(name, "rows") == 0) {

@@ -186,6 +186,7 @@ size_t rw_whhT_bytes(int H);      // ... backward format
 void launch_gru_rw_fwd(const GruSeqFwdArgs& a, cudaStream_t st);
 void launch_gru_rw_bwd(const GruSeqBwdArgs& a, cudaStream_t st);
 // ---- gru_rows.cu: row-resident forward sweep for large inference batches (128 rows per persistent CTA, W_hh streamed from L2) ----
+extern int g_opt_side_split;       // 2: the two directions' weight-gradient GEMMs get half of the persistent-grid cap each; 1: the whole cap each
 extern int g_opt_side_sms;         // > 0: persistent-grid cap of the weight-gradient GEMMs that run beside a sweep (0 = built-in rule)
 extern int g_opt_rows;             // 1: inference sweeps of H = 256 layers that do not fit the rw kernels use gru_rows_fwd_kernel
 bool rows_fwd_applicable(int H, int tiles);
