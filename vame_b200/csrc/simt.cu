@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(1024, 1) cluster_prior_kernel(const float* __r
   // Gram matrix: sum_i sqrt(ev_i) = trace(G^{1/2}) and the gradient matrix V diag(0.5 / sqrt(ev)) V^T = 0.5 G^{-1/2} need no
   // eigen-decomposition at all.  The coupled Newton-Schulz iteration  Y <- Y (3I - ZY) / 2,  Z <- (3I - ZY) Z / 2  (Y0 = G / tr G,
   // Z0 = I) converges quadratically to (G / tr G)^{1/2} and its inverse with three Z x Z products and two barriers per iteration:
-  // ~0.4 us instead of the ~35 us of a Jacobi sweep, ~25-40 iterations instead of 8-9 sweeps (C2: 315 -> ~25 us).  If it has not
+  // ~25-40 cheap iterations instead of 8-9 Jacobi sweeps of ~35 us each (C2, ncu launch list: 315 -> ~120 us per launch).  If it has not
   // converged after 64 iterations (numerically singular Gram) the Jacobi path below takes over from the saved Gram entries.
   bool ns_done = false;
   if (kloss >= Z && B >= Z) {
