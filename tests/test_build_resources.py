@@ -1,7 +1,8 @@
 """Regression guard for the root cause documented in profiles/r2_ng2_sw_fault.md: `tcgen05.ld` writes its destination registers
 asynchronously, and every build in which ptxas had to SPILL inside a warp that executes it faulted on the GPU (and passed under
 compute-sanitizer).  The tensor-core kernels must therefore compile without a stack frame; the one known exception (the
-two-group forward sweep without store warps: 32 bytes in the MMA-issue role, which executes no tcgen05.ld) is pinned here so
+two-group forward sweep without store warps: 32 bytes - one kernel-wide scalar saved in the prologue and re-read once per role
+before its loop, the rest inside the MMA-issue role, which executes no tcgen05.ld; checked in the SASS) is pinned here so
 that any growth shows up on the CPU, before a GPU box is spent on it."""
 import os
 import re
